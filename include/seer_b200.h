@@ -1,0 +1,112 @@
+/* seer_b200.h — C ABI of libseer_b200.so: the sm_100a kernels behind Seer's DDIM+CFG denoising step.
+ *
+ * The reference (seervideodiffusion/SeerVideoLDM) has no native layer and no FFI: its hot path is PyTorch
+ * modules calling cuDNN / cuBLAS / xformers.  Each entry point below therefore cites the reference *operator*
+ * it replaces (paths relative to /root/reference).  Conventions:
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless noted;
+ *   - every function returns int: 0 = ok, >0 = cudaError_t of the failed launch, <0 = argument/support error
+ *     (SEER_B200_EINVAL -1, SEER_B200_EUNSUPPORTED -2, SEER_B200_ENODRIVER -3); nothing throws across the ABI;
+ *   - no hidden allocation and no host synchronisation: outputs and workspaces are caller-owned, launches go to
+ *     the caller's `stream` (a cudaStream_t passed as void*), so every call is CUDA-graph capturable;
+ *   - activations are channels-last "token-major": row = ((b*F + f)*H + y)*W + x, columns = channels.
+ */
+#ifndef SEER_B200_H
+#define SEER_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEER_B200_EINVAL (-1)
+#define SEER_B200_EUNSUPPORTED (-2)
+#define SEER_B200_ENODRIVER (-3)
+
+/* flags for the GEMM / conv epilogue */
+#define SEER_GEMM_OUT_BF16 1 /* store bf16 (default fp32) */
+#define SEER_GEMM_GEGLU 2    /* out[:, j] = (a + ba) * gelu_erf(g + bg); Wt/bias rows packed in value/gate blocks of 32 */
+
+/* attention modes */
+#define SEER_ATTN_SPATIAL 0
+#define SEER_ATTN_CROSS 1
+#define SEER_ATTN_SCTA 2
+
+const char* seer_b200_version(void);
+
+/* out[M,N] = A[M,K1] (|| A2[M,K2]) * Wt[N,K1+K2]^T + bias[(row/bias_div), :] (+ residual), tcgen05/TMEM/TMA.
+ * Replaces nn.Linear / 1x1 InflatedConv3d: seer/models/attention.py:484-489 (to_q/k/v/out), :111,126 (proj_in/out),
+ * :783,742 (GEGLU proj, FF out), resnet.py:172 (conv_shortcut).  A, A2, Wt bf16; bias/residual fp32; K1,K2 % 64 == 0;
+ * N % 64 == 0 (GEGLU: N % 128 == 0, out has N/2 columns).  bias is [rows, ldb] (ldb <= 0: ldb = N) and row
+ * (row / bias_div) is used; bias_div <= 0: one bias row (per-sample bias: bias_div = tokens per sample). */
+int seer_b200_gemm_bf16(const void* A, int lda, int K1, const void* A2, int lda2, int K2, const void* Wt, int M, int N,
+                        const float* bias, int ldb, int bias_div, const float* residual, int ldr, void* out, int ldo,
+                        int flags, void* stream);
+
+/* Frame-wise 3x3 conv, stride 1, pad 1, as implicit GEMM over 9 shifted TMA boxes of X[n_img,H,W,Cin] (bf16),
+ * optional fused 1x1 tail A2[M,K2] (ResNet shortcut).  Wt[Cout, 9*Cin + K2] with K order [ky][kx][Cin] then tail.
+ * Replaces InflatedConv3d(k=3): seer/models/resnet.py:8-16,147,155 and Upsample3D's conv :39.
+ * Requires Cin % 64 == 0, W | 128, and (128/W) | H or H | (128/W). */
+int seer_b200_conv3x3_bf16(const void* X, int n_img, int H, int W, int Cin, const void* A2, int lda2, int K2, const void* Wt,
+                           int Cout, const float* bias, int ldb, int bias_div, const float* residual, int ldr, void* out,
+                           int ldo, int flags, void* stream);
+
+/* GroupNorm(32 groups) over (C/32, T) per sample on the virtual concat [x1 | x2] (fp32, [B*T, C1] and [B*T, C2]),
+ * then optional SiLU; y is bf16 (or fp32 if y_is_f32) [B*T, C1+C2]; raw_bf16 (optional) receives the un-normalised
+ * concat as bf16.  workspace: seer_b200_groupnorm_workspace_floats(B,T) floats; scale_shift: 2*B*(C1+C2) floats.
+ * Replaces torch.nn.GroupNorm on the 5-D tensor: resnet.py:179-180,197-198; attention.py:133; unet_3d_condition.py:368-369. */
+int seer_b200_groupnorm_workspace_floats(int B, int T);
+int seer_b200_groupnorm(const float* x1, int C1, const float* x2, int C2, int B, int T, const float* gamma, const float* beta,
+                        float eps, int silu, float* workspace, float* scale_shift, void* y, int y_is_f32, void* raw_bf16,
+                        void* stream);
+
+/* LayerNorm over the last dim (fp32 in, bf16 out).  Replaces nn.LayerNorm: attention.py:198-200,237,244,311,322-323. */
+int seer_b200_layernorm(const float* x, int M, int C, int ldx, const float* gamma, const float* beta, float eps, void* y_bf16,
+                        int ldy, void* stream);
+
+/* softmax(Q K^T / sqrt(d)) V over token-major bf16 buffers; row gathers implement the reference's head split and window
+ * partition.  SPATIAL/CROSS: n_outer = b*f frames, sequences Lq/Lk rows per frame.  SCTA: n_outer = b, geometry (F,H,W),
+ * window rule and causal order of attention.py:632-703 (Lq/Lk ignored).  head_dim in {40, 80, 160}.
+ * Replaces xformers.ops.memory_efficient_attention at attention.py:622-630. */
+int seer_b200_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int mode,
+                        int heads, int head_dim, int n_outer, int Lq, int Lk, int F, int H, int W, void* stream);
+
+/* Writes the SCTA gather permutation used by seer_b200_attention: out_dev[(b*nwin + win)*L + s] = token row.
+ * out_nwin / out_L are HOST pointers.  Parity hook for window_partition (attention.py:42-53). */
+int seer_b200_scta_row_index(int B, int F, int H, int W, int* out_dev, int* out_nwin, int* out_L, void* stream);
+
+/* RoPE (interleaved pairs, first 2*n_freqs channels of every head) in place on the Q and K column blocks of a bf16
+ * buffer [M, ld]; position = row % tokens_per_clip.  Replaces rotary_emb.rotate_queries_or_keys, attention.py:649-651. */
+int seer_b200_rope_inplace(void* qk_bf16, int ld, int M, int tokens_per_clip, int heads, int head_dim, int q_col, int k_col,
+                           const float* freqs, int n_freqs, void* stream);
+
+/* diffusers Timesteps(dim, flip_sin_to_cos, shift): t[B] (fp32) -> out[B, dim].  unet_3d_condition.py:307. */
+int seer_b200_timestep_embedding(const float* t, float* out, int B, int dim, float shift, int flip_sin_to_cos, void* stream);
+
+/* out[b,n] = silu_out?( dot(silu_in?(in[b,:]), W[n,:]) + bias[n] + add[n] ), fp32, B small.
+ * time_embedding.linear_{1,2} (unet_3d_condition.py:308) and time_emb_proj (resnet.py:190-192). */
+int seer_b200_small_linear(const float* in, int ldi, const float* W, const float* bias, const float* add, float* out, int ldo,
+                           int B, int N, int K, int silu_in, int silu_out, void* stream);
+
+/* conv_in (3x3, 4 -> Cout, fp32): x (B,4,F,H,W) -> out [B*F*H*W, Cout].  unet_3d_condition.py:94,311. */
+int seer_b200_conv_in(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int F, int H, int W,
+                      int Cout, void* stream);
+/* conv_out (3x3, Cin -> <=4, fp32): x [B*F*H*W, Cin] -> out (B,Cout,F,H,W); w_packed[co][tap][Cin].  :205,370. */
+int seer_b200_conv_out(const float* x, const float* w_packed, const float* bias, float* out, int B, int Cin, int F, int H,
+                       int W, int Cout, void* stream);
+
+/* nearest 2x upsample fp32 [n,H,W,C] -> bf16 [n,2H,2W,C] (resnet.py:52). */
+int seer_b200_upsample2x_to_bf16(const float* x, void* y, int n_img, int H, int W, int C, void* stream);
+/* pad-1 3x3 im2col, stride 1 or 2: [n,H,W,C] (fp32, or bf16 if in_is_bf16) -> bf16 [n*(H/s)*(W/s), 9*C], K order [tap][C].
+ * Stride 2 = Downsample3D (resnet.py:95-104); stride 1 = fallback for image sizes the TMA-box conv does not tile. */
+int seer_b200_im2col3x3_to_bf16(const void* x, int in_is_bf16, void* y, int n_img, int H, int W, int C, int stride, void* stream);
+int seer_b200_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+
+/* e = e_u + s (e_c - e_u) on frames >= cond_f; pred_x0 = (x - c1 e)/c2; x_prev = c3 pred_x0 + c4 e — fp32, bit-identical
+ * to ldm/models/diffusion/ddim_video.py:209-211,229-237 (eta = 0).  eps: (2b|b, C, cond_f+F2, H, W). */
+int seer_b200_cfg_ddim_update(const float* eps, const float* x, float* x_prev, float* pred_x0, int b, int C, int F2, int cond_f,
+                              int HW, int use_cfg, float scale, float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev,
+                              float dir_coef, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEER_B200_H */

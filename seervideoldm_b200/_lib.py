@@ -1,0 +1,82 @@
+"""ctypes loader for libseer_b200.so (the C-ABI kernel library, include/seer_b200.h).
+
+The product path has NO CPU or PyTorch fallback: if the shared library is missing or a symbol is
+absent, importing the ops raises.  `build()` compiles it in-tree with nvcc for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libseer_b200.so")
+BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
+
+_c = ctypes
+_vp, _i, _f, _ll = _c.c_void_p, _c.c_int, _c.c_float, _c.c_longlong
+_ip = _c.POINTER(_c.c_int)
+
+# name -> (restype, argtypes): must list every symbol include/seer_b200.h declares
+SIGNATURES = {
+    "seer_b200_version": (_c.c_char_p, []),
+    "seer_b200_gemm_bf16": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
+    "seer_b200_conv3x3_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
+    "seer_b200_groupnorm_workspace_floats": (_i, [_i, _i]),
+    "seer_b200_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    "seer_b200_layernorm": (_i, [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp]),
+    "seer_b200_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "seer_b200_scta_row_index": (_i, [_i, _i, _i, _i, _vp, _ip, _ip, _vp]),
+    "seer_b200_rope_inplace": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "seer_b200_timestep_embedding": (_i, [_vp, _vp, _i, _i, _f, _i, _vp]),
+    "seer_b200_small_linear": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "seer_b200_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "seer_b200_conv_out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "seer_b200_upsample2x_to_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "seer_b200_im2col3x3_to_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "seer_b200_cast_f32_to_bf16": (_i, [_vp, _vp, _ll, _vp]),
+    "seer_b200_cfg_ddim_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f, _vp]),
+}
+
+_lib = None
+
+
+class SeerB200Error(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into seervideoldm_b200/libseer_b200.so."""
+    r = subprocess.run(["bash", BUILD_SCRIPT], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout)
+        print(r.stderr)
+    if r.returncode != 0:
+        raise SeerB200Error(f"nvcc build failed (exit {r.returncode})")
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SeerB200Error(
+                f"{LIB_PATH} not found — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU/PyTorch fallback for the seer_b200 kernels)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)       # AttributeError if the symbol is missing: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    if rc > 0:
+        raise SeerB200Error(f"{what}: CUDA error {rc}")
+    names = {-1: "invalid argument", -2: "unsupported shape", -3: "CUDA driver entry point unavailable"}
+    exc = ValueError if rc in (-1, -2) else SeerB200Error
+    raise exc(f"{what}: {names.get(rc, rc)}")

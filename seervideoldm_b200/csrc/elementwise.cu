@@ -1,0 +1,374 @@
+// Memory-bound pieces of the Seer denoising step: RoPE, timestep embedding + small-batch linears, the 4-channel
+// boundary convs (kept in fp32 — SURVEY F11), nearest-2x upsample, stride-2 im2col, dtype casts and the fused
+// CFG-combine + DDIM update.  Coalesced 128-bit accesses, warp-shuffle reductions.
+#include "common.cuh"
+#include "seer_b200.h"
+
+namespace seer {
+
+// ---------------------------------------------------------------------------------------------------
+// cast fp32 -> bf16 (context embeddings, once per clip)
+// ---------------------------------------------------------------------------------------------------
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = *reinterpret_cast<const float4*>(x + i * 8);
+    const float4 b = *reinterpret_cast<const float4*>(x + i * 8 + 4);
+    uint4 o;
+    o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w); o.z = pack_bf16(b.x, b.y); o.w = pack_bf16(b.z, b.w);
+    *reinterpret_cast<uint4*>(y + i * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// RoPE on the Q and K column blocks of a token-major projection buffer [M, ld] (bf16), in place.
+// Reference: rotary-embedding-torch 0.1.5 rotate_queries_or_keys at /root/reference/seer/models/attention.py:649-651:
+// position = flat token index f*h*w + y*w + x inside the clip; interleaved pairs (2j, 2j+1), j < rot/2,
+// angle = pos * freqs[j]; channels >= rot of each head pass through.
+// One thread per (token, pair j): sincos once, applied to all heads of Q and K.
+// ---------------------------------------------------------------------------------------------------
+__global__ void rope_kernel(__nv_bfloat16* __restrict__ qk, int ld, int M, int tokens_per_clip, int heads, int head_dim,
+                            int q_col, int k_col, const float* __restrict__ freqs, int half) {
+  const size_t total = (size_t)M * half;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / half);
+    const int j = (int)(i - (size_t)row * half);
+    const int pos = row % tokens_per_clip;
+    const float ang = (float)pos * __ldg(freqs + j);
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+    __nv_bfloat16* base = qk + (size_t)row * ld + 2 * j;
+    for (int h = 0; h < heads; ++h) {
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        uint32_t* ptr = reinterpret_cast<uint32_t*>(base + (w ? k_col : q_col) + h * head_dim);
+        const float2 x = unpack_bf16(*ptr);
+        *ptr = pack_bf16(x.x * cs - x.y * sn, x.y * cs + x.x * sn);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Timestep embedding (diffusers 0.10.2 Timesteps, flip_sin_to_cos): out[b] = [cos(t*f_i) | sin(t*f_i)],
+// f_i = exp(-ln(10000) * i / (half - shift)).   Call site unet_3d_condition.py:307.
+// ---------------------------------------------------------------------------------------------------
+__global__ void timestep_embed_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim, float shift,
+                                      int flip) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, k = i - b * half;
+  const float f = expf(-logf(10000.0f) * (float)k / ((float)half - shift));
+  const float a = t[b] * f;
+  float sn, cs;
+  sincosf(a, &sn, &cs);
+  float* o = out + (size_t)b * dim;
+  if (flip) { o[k] = cs; o[half + k] = sn; } else { o[k] = sn; o[half + k] = cs; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Small-batch linear: out[b, n] = dot(act(in[b, :]), W[n, :]) + bias[n] (+ add[n]);  fp32, one warp per n,
+// up to 8 batch rows per warp pass.  Used for time_embedding.linear_{1,2} and all 22 time_emb_proj at once
+// (their weights are concatenated along n).   resnet.py:190-192, unet_3d_condition.py:308.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SL_ROWS = 8;
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in, int ldi, const float* __restrict__ W,
+                                                           const float* __restrict__ bias, const float* __restrict__ add,
+                                                           float* __restrict__ out, int ldo, int B, int N, int K,
+                                                           int silu_in, int silu_out) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int b0 = blockIdx.y * SL_ROWS;
+  if (n >= N) return;
+  float acc[SL_ROWS];
+#pragma unroll
+  for (int r = 0; r < SL_ROWS; ++r) acc[r] = 0.f;
+  const float4* w4 = reinterpret_cast<const float4*>(W + (size_t)n * K);
+  for (int k4 = lane; k4 < K / 4; k4 += 32) {
+    const float4 w = __ldg(w4 + k4);
+#pragma unroll
+    for (int r = 0; r < SL_ROWS; ++r) {
+      if (b0 + r < B) {
+        float4 x = *reinterpret_cast<const float4*>(in + (size_t)(b0 + r) * ldi + k4 * 4);
+        if (silu_in) { x.x = silu_f(x.x); x.y = silu_f(x.y); x.z = silu_f(x.z); x.w = silu_f(x.w); }
+        acc[r] += (x.x * w.x + x.y * w.y) + (x.z * w.z + x.w * w.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < SL_ROWS; ++r) {
+    const float v = warp_sum(acc[r]);
+    if (lane == 0 && b0 + r < B) {
+      float o = v + (bias ? bias[n] : 0.f) + (add ? add[n] : 0.f);
+      if (silu_out) o = silu_f(o);
+      out[(size_t)(b0 + r) * ldo + n] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// conv_in: 3x3, Cin = 4 -> Cout, fp32, input in the reference's (B, Cin, F, H, W) layout, output token-major
+// [B*F*H*W, Cout] fp32.   unet_3d_condition.py:94,311.
+// ---------------------------------------------------------------------------------------------------
+constexpr int CI_PIX = 16;
+__global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                               float* __restrict__ out, int B, int Cin, int F, int H, int W, int Cout) {
+  extern __shared__ float s_in[];  // [CI_PIX][Cin*9]
+  constexpr int K = 36;  // Cin == 4 (checked on the host)
+  const int HW = H * W;
+  const size_t npix = (size_t)B * F * HW;
+  const size_t p0 = (size_t)blockIdx.x * CI_PIX;
+  for (int i = threadIdx.x; i < CI_PIX * K; i += blockDim.x) {
+    const int pi = i / K, k = i - pi * K;
+    const size_t pix = p0 + pi;
+    float v = 0.f;
+    if (pix < npix) {
+      const int c = k / 9, tap = k - c * 9, ky = tap / 3, kx = tap - ky * 3;
+      const int bf = (int)(pix / HW), rem = (int)(pix - (size_t)bf * HW);
+      const int b = bf / F, f = bf - b * F;
+      const int yy = rem / W + ky - 1, xx = rem % W + kx - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[((((size_t)b * Cin + c) * F + f) * H + yy) * W + xx];
+    }
+    s_in[i] = v;
+  }
+  __syncthreads();
+  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+    float wr[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) wr[k] = w[(size_t)co * K + k];  // weight (Cout, Cin, 3, 3) is already [co][c*9 + tap]
+    const float bz = bias[co];
+    for (int pi = 0; pi < CI_PIX; ++pi) {
+      if (p0 + pi >= npix) break;
+      float acc = bz;
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc += s_in[pi * K + k] * wr[k];
+      out[(p0 + pi) * Cout + co] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// conv_out: 3x3, Cin -> 4, fp32, input token-major [B*F*H*W, Cin] fp32 (already GroupNorm+SiLU'd), output in the
+// reference's (B, Cout, F, H, W) layout.  One warp per output pixel.   unet_3d_condition.py:205,370.
+// Weights pre-packed as wp[co][tap][Cin].
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__ x, const float* __restrict__ wp,
+                                                       const float* __restrict__ bias, float* __restrict__ out, int B, int Cin,
+                                                       int F, int H, int W, int Cout) {
+  const int HW = H * W;
+  const size_t npix = (size_t)B * F * HW;
+  const size_t pix = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= npix) return;
+  const int bf = (int)(pix / HW), rem = (int)(pix - (size_t)bf * HW);
+  const int y = rem / W, xq = rem % W;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = xq + tap % 3 - 1;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const float* src = x + ((size_t)bf * HW + yy * W + xx) * Cin;
+    for (int c = lane * 4; c < Cin; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(src + c);
+#pragma unroll
+      for (int co = 0; co < 4; ++co) {
+        if (co < Cout) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wp + ((size_t)co * 9 + tap) * Cin + c));
+          acc[co] += (v.x * wv.x + v.y * wv.y) + (v.z * wv.z + v.w * wv.w);
+        }
+      }
+    }
+  }
+  const int b = bf / F, f = bf - b * F;
+#pragma unroll
+  for (int co = 0; co < 4; ++co) {
+    const float v = warp_sum(acc[co]);
+    if (lane == 0 && co < Cout) out[((((size_t)b * Cout + co) * F + f) * H + y) * W + xq] = v + bias[co];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// nearest 2x upsample, fp32 [n_img, H, W, C] -> bf16 [n_img, 2H, 2W, C]   (resnet.py:52, conv input operand)
+// ---------------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n_img, int H, int W, int C) {
+  const int c8n = C / 8;
+  const size_t total = (size_t)n_img * 4 * H * W * c8n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8n) * 8;
+    size_t r = i / c8n;
+    const int ox = (int)(r % (2 * W)); r /= (2 * W);
+    const int oy = (int)(r % (2 * H));
+    const int img = (int)(r / (2 * H));
+    const float* src = x + (((size_t)img * H + oy / 2) * W + ox / 2) * C + c;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 b = *reinterpret_cast<const float4*>(src + 4);
+    uint4 o;
+    o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w); o.z = pack_bf16(b.x, b.y); o.w = pack_bf16(b.z, b.w);
+    *reinterpret_cast<uint4*>(y + i * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// im2col for pad-1 3x3 convs, stride 1 or 2: [n_img, H, W, C] (fp32 or bf16) -> bf16 [n_img*Ho*Wo, 9*C],
+// K order = [tap][C] (matches the packed conv weight).  Stride 2: Downsample3D (resnet.py:95-104).
+// ---------------------------------------------------------------------------------------------------
+template <bool IN_BF16>
+__global__ void im2col3x3_kernel(const void* __restrict__ xin, __nv_bfloat16* __restrict__ y, int n_img, int H, int W, int C,
+                                 int stride) {
+  const int c8n = C / 8;
+  const int Ho = H / stride, Wo = W / stride;
+  const size_t total = (size_t)n_img * Ho * Wo * 9 * c8n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8n) * 8;
+    size_t r = i / c8n;
+    const int tap = (int)(r % 9); r /= 9;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int img = (int)(r / Ho);
+    const int yy = stride * oy + tap / 3 - 1, xx = stride * ox + tap % 3 - 1;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const size_t off = (((size_t)img * H + yy) * W + xx) * C + c;
+      if (IN_BF16) {
+        o = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(xin) + off);
+      } else {
+        const float* src = reinterpret_cast<const float*>(xin) + off;
+        const float4 a = *reinterpret_cast<const float4*>(src);
+        const float4 b = *reinterpret_cast<const float4*>(src + 4);
+        o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w); o.z = pack_bf16(b.x, b.y); o.w = pack_bf16(b.z, b.w);
+      }
+    }
+    *reinterpret_cast<uint4*>(y + i * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CFG combine + DDIM update (eta = 0), fp32, in the reference's exact operation order with explicitly
+// rounded (non-contracted) arithmetic so the result is bit-identical to the PyTorch expressions at
+// /root/reference/ldm/models/diffusion/ddim_video.py:209-211, 229-237:
+//   e       = e_u + s * (e_c - e_u)                      (frames >= cond_f only)
+//   pred_x0 = (x - sqrt(1 - a_t) * e) / sqrt(a_t)
+//   x_prev  = sqrt(a_prev) * pred_x0 + sqrt(1 - a_prev) * e
+// eps is (2b | b, C, F, H, W) with F = cond_f + F2; x / x_prev / pred_x0 are (b, C, F2, H, W).
+// ---------------------------------------------------------------------------------------------------
+__global__ void cfg_ddim_kernel(const float* __restrict__ eps, const float* __restrict__ x, float* __restrict__ x_prev,
+                                float* __restrict__ pred_x0, int b, int C, int F2, int cond_f, int HW, int use_cfg, float scale,
+                                float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef) {
+  const size_t total = (size_t)b * C * F2 * HW;
+  const int F = F2 + cond_f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    size_t r = i / HW;
+    const int f = (int)(r % F2); r /= F2;
+    const int c = (int)(r % C);
+    const int bi = (int)(r / C);
+    const size_t eo = (((size_t)bi * C + c) * F + (f + cond_f)) * HW + p;
+    float e;
+    if (use_cfg) {
+      const float eu = eps[eo];
+      const float ec = eps[eo + (size_t)b * C * F * HW];
+      e = __fadd_rn(eu, __fmul_rn(scale, __fsub_rn(ec, eu)));
+    } else {
+      e = eps[eo];
+    }
+    const float xv = x[i];
+    const float p0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(sqrt_one_minus_at, e)), sqrt_at);
+    const float xp = __fadd_rn(__fmul_rn(sqrt_a_prev, p0), __fmul_rn(dir_coef, e));
+    pred_x0[i] = p0;
+    x_prev[i] = xp;
+  }
+}
+
+static inline int grid_for(size_t n, int threads) {
+  size_t b = (n + threads - 1) / threads;
+  const size_t cap = (size_t)148 * 32;
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+}  // namespace seer
+
+using namespace seer;
+
+extern "C" int seer_b200_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream) {
+  SEER_CHECK_ARG(x && y && n > 0 && n % 8 == 0);
+  cast_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, (size_t)n / 8);
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_rope_inplace(void* qk_bf16, int ld, int M, int tokens_per_clip, int heads, int head_dim, int q_col,
+                                      int k_col, const float* freqs, int n_freqs, void* stream) {
+  SEER_CHECK_ARG(qk_bf16 && freqs && M > 0 && tokens_per_clip > 0 && M % tokens_per_clip == 0);
+  SEER_CHECK_ARG(2 * n_freqs <= head_dim && ld % 2 == 0 && q_col % 2 == 0 && k_col % 2 == 0 && head_dim % 2 == 0);
+  rope_kernel<<<grid_for((size_t)M * n_freqs, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)qk_bf16, ld, M, tokens_per_clip,
+                                                                                   heads, head_dim, q_col, k_col, freqs, n_freqs);
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_timestep_embedding(const float* t, float* out, int B, int dim, float shift, int flip_sin_to_cos,
+                                            void* stream) {
+  SEER_CHECK_ARG(t && out && B > 0 && dim > 0 && dim % 2 == 0);
+  timestep_embed_kernel<<<ceil_div(B * dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(t, out, B, dim, shift, flip_sin_to_cos);
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_small_linear(const float* in, int ldi, const float* W, const float* bias, const float* add, float* out,
+                                      int ldo, int B, int N, int K, int silu_in, int silu_out, void* stream) {
+  SEER_CHECK_ARG(in && W && out && B > 0 && N > 0 && K > 0 && K % 4 == 0 && ldi % 4 == 0);
+  dim3 grid(ceil_div(N, 8), ceil_div(B, SL_ROWS));
+  small_linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ldi, W, bias, add, out, ldo, B, N, K, silu_in, silu_out);
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_conv_in(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int F, int H,
+                                 int W, int Cout, void* stream) {
+  SEER_CHECK_ARG(x && w && bias && out && Cin == 4);
+  const size_t npix = (size_t)B * F * H * W;
+  const int threads = Cout >= 320 ? 320 : ((Cout + 31) / 32) * 32;
+  conv_in_kernel<<<(unsigned)((npix + CI_PIX - 1) / CI_PIX), threads, CI_PIX * Cin * 9 * sizeof(float), (cudaStream_t)stream>>>(
+      x, w, bias, out, B, Cin, F, H, W, Cout);
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_conv_out(const float* x, const float* w_packed, const float* bias, float* out, int B, int Cin, int F,
+                                  int H, int W, int Cout, void* stream) {
+  SEER_CHECK_ARG(x && w_packed && bias && out && Cout <= 4 && Cin % 4 == 0);
+  const size_t npix = (size_t)B * F * H * W;
+  conv_out_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, w_packed, bias, out, B, Cin, F, H, W, Cout);
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_upsample2x_to_bf16(const float* x, void* y, int n_img, int H, int W, int C, void* stream) {
+  SEER_CHECK_ARG(x && y && C % 8 == 0);
+  const size_t total = (size_t)n_img * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n_img, H, W, C);
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_im2col3x3_to_bf16(const void* x, int in_is_bf16, void* y, int n_img, int H, int W, int C, int stride,
+                                           void* stream) {
+  SEER_CHECK_ARG(x && y && C % 8 == 0 && (stride == 1 || stride == 2) && H % stride == 0 && W % stride == 0);
+  const size_t total = (size_t)n_img * (H / stride) * (W / stride) * 9 * (C / 8);
+  if (in_is_bf16)
+    im2col3x3_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n_img, H, W, C, stride);
+  else
+    im2col3x3_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n_img, H, W, C, stride);
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_cfg_ddim_update(const float* eps, const float* x, float* x_prev, float* pred_x0, int b, int C, int F2,
+                                         int cond_f, int HW, int use_cfg, float scale, float sqrt_one_minus_at, float sqrt_at,
+                                         float sqrt_a_prev, float dir_coef, void* stream) {
+  SEER_CHECK_ARG(eps && x && x_prev && pred_x0 && b > 0 && C > 0 && F2 > 0 && HW > 0 && cond_f >= 0);
+  const size_t total = (size_t)b * C * F2 * HW;
+  cfg_ddim_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(eps, x, x_prev, pred_x0, b, C, F2, cond_f, HW, use_cfg,
+                                                                          scale, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef);
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}

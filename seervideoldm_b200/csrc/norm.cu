@@ -1,0 +1,246 @@
+// GroupNorm (statistics pooled over ALL frames of a clip — SURVEY F6) and LayerNorm for the channels-last
+// token layout [B, T = F*h*w, C].  Memory-bound kernels: coalesced 64/128-bit accesses, warp-shuffle /
+// shared-memory reductions, deterministic two-level partial sums (no float atomics across CTAs).
+//
+// Reference semantics:
+//   GroupNorm(32, C, eps) on the 5-D tensor (b, c, f, h, w): /root/reference/seer/models/resnet.py:179,197,
+//   attention.py:109,133, unet_3d_condition.py:368  — statistics over (C/32, F, H, W) per sample, fp32.
+//   LayerNorm(C), eps 1e-5: attention.py:198-200, 275-277.
+//
+// The GroupNorm input may be the virtual channel concatenation of two tensors (skip connections,
+// unet_3d_blocks.py:596,712): x = cat([x1 (C1 ch), x2 (C2 ch)], channel) is never materialised in fp32.
+#include "common.cuh"
+#include "seer_b200.h"
+
+namespace seer {
+
+constexpr int GN_GROUPS = 32;
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_SLOTS = 8;  // float2 columns per thread: C/2 <= 256*8 -> C <= 4096
+
+__device__ __forceinline__ float2 load_cat2(const float* x1, int C1, const float* x2, int C2, size_t row, int c) {
+  // c is even; C1 is even, so a float2 never straddles the two sources
+  return c < C1 ? *reinterpret_cast<const float2*>(x1 + row * C1 + c)
+                : *reinterpret_cast<const float2*>(x2 + row * C2 + (c - C1));
+}
+
+// partial[b][chunk][g][2] = (sum, sumsq) over this chunk's tokens and group g's channels
+__global__ void __launch_bounds__(GN_THREADS) gn_partial_kernel(const float* __restrict__ x1, int C1,
+                                                                const float* __restrict__ x2, int C2, int T, int tpc,
+                                                                float* __restrict__ partial) {
+  const int C = C1 + C2;
+  const int cpg = C / GN_GROUPS;
+  const int ncol = C / 2;
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int t0 = chunk * tpc, t1 = min(T, t0 + tpc);
+  __shared__ float2 s_col[GN_THREADS * GN_MAX_SLOTS];  // per-column (sum, sumsq): deterministic, no float atomics
+  float sum[GN_MAX_SLOTS], sq[GN_MAX_SLOTS];
+#pragma unroll
+  for (int s = 0; s < GN_MAX_SLOTS; ++s) { sum[s] = 0.f; sq[s] = 0.f; }
+  for (int t = t0; t < t1; ++t) {
+    const size_t row = (size_t)b * T + t;
+#pragma unroll
+    for (int s = 0; s < GN_MAX_SLOTS; ++s) {
+      const int col = threadIdx.x + s * GN_THREADS;
+      if (col < ncol) {
+        float2 v = load_cat2(x1, C1, x2, C2, row, col * 2);
+        sum[s] += v.x + v.y;
+        sq[s] += v.x * v.x + v.y * v.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < GN_MAX_SLOTS; ++s) {
+    const int col = threadIdx.x + s * GN_THREADS;
+    if (col < ncol) s_col[col] = make_float2(sum[s], sq[s]);
+  }
+  __syncthreads();
+  // 8 lanes per group, fixed summation order (cpg is even, so a float2 column never straddles two groups)
+  {
+    const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    const int c0 = g * (cpg / 2), c1 = c0 + cpg / 2;
+    float a = 0.f, q = 0.f;
+    for (int c = c0 + sub; c < c1; c += 8) { a += s_col[c].x; q += s_col[c].y; }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (sub == 0) {
+      float* dst = partial + (((size_t)b * nchunks + chunk) * GN_GROUPS + g) * 2;
+      dst[0] = a;
+      dst[1] = q;
+    }
+  }
+}
+
+// One warp per (b, g): combine chunk partials in double, then emit per-(b, c) affine: y = x*scale + shift.
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int nchunks, int C, int T, float eps,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_rstd) {
+  const int b = blockIdx.x;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cpg = C / GN_GROUPS;
+  double s = 0.0, q = 0.0;
+  for (int c = lane; c < nchunks; c += 32) {
+    const float* src = partial + (((size_t)b * nchunks + c) * GN_GROUPS + g) * 2;
+    s += (double)src[0];
+    q += (double)src[1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const double n = (double)cpg * (double)T;
+  const double mean = s / n;
+  double var = q / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float meanf = (float)mean;
+  if (lane == 0 && mean_rstd) {
+    mean_rstd[((size_t)b * GN_GROUPS + g) * 2] = meanf;
+    mean_rstd[((size_t)b * GN_GROUPS + g) * 2 + 1] = rstd;
+  }
+  for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+    const float sc = rstd * gamma[c];
+    scale[(size_t)b * C + c] = sc;
+    shift[(size_t)b * C + c] = beta[c] - meanf * sc;
+  }
+}
+
+// y = act(x * scale[b, c] + shift[b, c]);  8 channels per thread.  Optional second output: raw bf16 copy of x
+// (the un-normalised concat that feeds the fused ResNet 1x1 shortcut GEMM).
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
+                                                       int C2, int T, size_t total8, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, int silu, void* __restrict__ y,
+                                                       __nv_bfloat16* __restrict__ raw) {
+  const int C = C1 + C2;
+  const int c8n = C / 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / c8n;
+    const int c = (int)(i - row * c8n) * 8;
+    const int b = (int)(row / T);
+    const float* src = c < C1 ? x1 + row * C1 + c : x2 + row * C2 + (c - C1);
+    const float4 a0 = *reinterpret_cast<const float4*>(src);
+    const float4 a1 = *reinterpret_cast<const float4*>(src + 4);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * C + c));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * C + c + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + (size_t)b * C + c));
+    const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + (size_t)b * C + c + 4));
+    float v[8] = {a0.x * s0.x + h0.x, a0.y * s0.y + h0.y, a0.z * s0.z + h0.z, a0.w * s0.w + h0.w,
+                  a1.x * s1.x + h1.x, a1.y * s1.y + h1.y, a1.z * s1.z + h1.z, a1.w * s1.w + h1.w};
+    if (silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+    }
+    if (OUT_F32) {
+      float* dst = reinterpret_cast<float*>(y) + row * C + c;
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint4 o;
+      o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + row * C + c) = o;
+    }
+    if (raw) {
+      uint4 o;
+      o.x = pack_bf16(a0.x, a0.y); o.y = pack_bf16(a0.z, a0.w); o.z = pack_bf16(a1.x, a1.y); o.w = pack_bf16(a1.z, a1.w);
+      *reinterpret_cast<uint4*>(raw + row * C + c) = o;
+    }
+  }
+}
+
+// LayerNorm over the last dim, one warp per row, two-pass in registers (exact mean/variance), bf16 out.
+constexpr int LN_MAX_V4 = 10;  // C <= 1280
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int M, int C, int ldx,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, __nv_bfloat16* __restrict__ y, int ldy) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int nv = C / 4;
+  const float4* src = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
+  float4 v[LN_MAX_V4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int j = lane + i * 32;
+    if (j < nv) {
+      v[i] = src[j];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int j = lane + i * 32;
+    if (j < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  uint2* dst = reinterpret_cast<uint2*>(y + (size_t)row * ldy);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int j = lane + i * 32;
+    if (j < nv) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + j);
+      const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + j);
+      uint2 o;
+      o.x = pack_bf16((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y);
+      o.y = pack_bf16((v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w);
+      dst[j] = o;
+    }
+  }
+}
+
+}  // namespace seer
+
+using namespace seer;
+
+extern "C" int seer_b200_groupnorm_tokens_per_chunk(int T) { return T <= 4096 ? 16 : 32; }
+
+extern "C" int seer_b200_groupnorm_workspace_floats(int B, int T) {
+  const int tpc = seer_b200_groupnorm_tokens_per_chunk(T);
+  return B * ceil_div(T, tpc) * GN_GROUPS * 2;
+}
+
+extern "C" int seer_b200_groupnorm(const float* x1, int C1, const float* x2, int C2, int B, int T, const float* gamma,
+                                   const float* beta, float eps, int silu, float* workspace, float* scale_shift, void* y,
+                                   int y_is_f32, void* raw_bf16, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int C = C1 + C2;
+  SEER_CHECK_ARG(x1 && gamma && beta && workspace && scale_shift && y && B > 0 && T > 0);
+  SEER_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && (C2 == 0 || x2) && C % (2 * GN_GROUPS) == 0);
+  SEER_CHECK_ARG(C / 2 <= GN_THREADS * GN_MAX_SLOTS);
+  const int tpc = seer_b200_groupnorm_tokens_per_chunk(T);
+  const int nchunks = ceil_div(T, tpc);
+  float* scale = scale_shift;
+  float* shift = scale_shift + (size_t)B * C;
+  gn_partial_kernel<<<dim3(nchunks, B), GN_THREADS, 0, stream>>>(x1, C1, x2, C2, T, tpc, workspace);
+  SEER_LAUNCH_CHECK();
+  gn_finalize_kernel<<<B, GN_GROUPS * 32, 0, stream>>>(workspace, nchunks, C, T, eps, gamma, beta, scale, shift, nullptr);
+  SEER_LAUNCH_CHECK();
+  const size_t total8 = (size_t)B * T * (C / 8);
+  size_t nb = (total8 + 255) / 256; if (nb > (size_t)148 * 16) nb = (size_t)148 * 16;
+  const int blocks = (int)nb;
+  if (y_is_f32)
+    gn_apply_kernel<true><<<blocks, 256, 0, stream>>>(x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16);
+  else
+    gn_apply_kernel<false><<<blocks, 256, 0, stream>>>(x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16);
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_layernorm(const float* x, int M, int C, int ldx, const float* gamma, const float* beta, float eps,
+                                   void* y_bf16, int ldy, void* stream) {
+  SEER_CHECK_ARG(x && gamma && beta && y_bf16 && M > 0);
+  SEER_CHECK_ARG(C % 4 == 0 && C <= LN_MAX_V4 * 128 && ldx % 4 == 0 && ldy % 4 == 0);
+  layernorm_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(x, M, C, ldx, gamma, beta, eps, (__nv_bfloat16*)y_bf16, ldy);
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}

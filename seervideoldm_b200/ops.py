@@ -1,0 +1,307 @@
+"""Torch-tensor wrappers over the C ABI (include/seer_b200.h).
+
+PyTorch is plumbing here: device memory, the current stream, dtype/shape checks that raise Python
+exceptions (mirroring the reference's plain-exception convention, e.g. unet_3d_blocks.py:57,72).
+Every op launches hand-written sm_100a kernels from libseer_b200.so on `torch.cuda.current_stream()`;
+there is no PyTorch fallback.  `LAUNCHES` counts kernel launches (for bench.py's `gpu_launches`).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+GEMM_OUT_BF16 = 1
+GEMM_GEGLU = 2
+ATTN_SPATIAL, ATTN_CROSS, ATTN_SCTA = 0, 1, 2
+
+LAUNCHES = 0           # kernels launched through this module (graph replays are counted by the caller)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[ctypes.c_void_p]:
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _req(t: torch.Tensor, dtype: torch.dtype, name: str, ndim: Optional[int] = None) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (seer_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+    if t.stride(-1) != 1:
+        raise ValueError(f"{name}: last dim must be contiguous")
+
+
+def _rows(t: torch.Tensor) -> Tuple[int, int]:
+    """(rows, leading-dim) of a 2-D row-major view (possibly a column slice of a wider buffer)."""
+    return t.shape[0], t.stride(0)
+
+
+def gemm(a: torch.Tensor, wt: torch.Tensor, *, a2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+         bias_div: int = 0, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         out_dtype: torch.dtype = torch.float32, geglu: bool = False) -> torch.Tensor:
+    """out = [a | a2] @ wt.T + bias (+ residual).  a:[M,K1] bf16, a2:[M,K2] bf16, wt:[N,K1+K2] bf16."""
+    _req(a, torch.bfloat16, "a", 2); _req(wt, torch.bfloat16, "wt", 2)
+    M, K1 = a.shape
+    N = wt.shape[0]
+    K2 = 0
+    if a2 is not None:
+        _req(a2, torch.bfloat16, "a2", 2)
+        K2 = a2.shape[1]
+        if a2.shape[0] != M:
+            raise ValueError("a2 rows != a rows")
+    if wt.shape[1] != K1 + K2 or not wt.is_contiguous():
+        raise ValueError(f"wt must be contiguous [N, {K1 + K2}], got {tuple(wt.shape)}")
+    n_out = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=torch.bfloat16 if geglu else out_dtype)
+    if out.shape[0] != M or out.shape[1] != n_out:
+        raise ValueError(f"out shape {tuple(out.shape)} != ({M}, {n_out})")
+    _req(out, out.dtype, "out", 2)
+    flags = (GEMM_OUT_BF16 if out.dtype == torch.bfloat16 else 0) | (GEMM_GEGLU if geglu else 0)
+    if out.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("out must be bf16 or fp32")
+    ldb = 0
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+        ldb = bias.stride(0) if bias.dim() == 2 else N
+    if residual is not None:
+        _req(residual, torch.float32, "residual", 2)
+    rc = _lib.lib().seer_b200_gemm_bf16(_p(a), a.stride(0), K1, _p(a2), a2.stride(0) if a2 is not None else 0, K2, _p(wt), M, N,
+                                        _p(bias), ldb, bias_div, _p(residual), residual.stride(0) if residual is not None else 0,
+                                        _p(out), out.stride(0), flags, _stream())
+    _lib.check(rc, f"gemm_bf16(M={M},N={N},K={K1}+{K2})")
+    _count()
+    return out
+
+
+def conv3x3(x: torch.Tensor, wt: torch.Tensor, *, a2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+            bias_div: int = 0, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+            out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """Frame-wise 3x3 conv (stride 1, pad 1).  x:[n_img,H,W,Cin] bf16 contiguous; wt:[Cout, 9*Cin (+K2)] bf16 with
+    K order [ky][kx][Cin]; returns [n_img*H*W, Cout].  Falls back to im2col + GEMM (still seer_b200 kernels) for
+    image sizes the TMA-box tiling does not cover."""
+    _req(x, torch.bfloat16, "x", 4); _req(wt, torch.bfloat16, "wt", 2)
+    if not x.is_contiguous() or not wt.is_contiguous():
+        raise ValueError("x and wt must be contiguous")
+    n_img, H, W, Cin = x.shape
+    Cout = wt.shape[0]
+    M = n_img * H * W
+    K2 = 0
+    if a2 is not None:
+        _req(a2, torch.bfloat16, "a2", 2)
+        K2 = a2.shape[1]
+    if wt.shape[1] != 9 * Cin + K2:
+        raise ValueError(f"wt must be [Cout, {9 * Cin + K2}], got {tuple(wt.shape)}")
+    if out is None:
+        out = torch.empty((M, Cout), device=x.device, dtype=out_dtype)
+    flags = GEMM_OUT_BF16 if out.dtype == torch.bfloat16 else 0
+    ldb = 0
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+        ldb = bias.stride(0) if bias.dim() == 2 else Cout
+    if residual is not None:
+        _req(residual, torch.float32, "residual", 2)
+    rc = _lib.lib().seer_b200_conv3x3_bf16(_p(x), n_img, H, W, Cin, _p(a2), a2.stride(0) if a2 is not None else 0, K2, _p(wt),
+                                           Cout, _p(bias), ldb, bias_div, _p(residual),
+                                           residual.stride(0) if residual is not None else 0, _p(out), out.stride(0), flags,
+                                           _stream())
+    if rc == -2:      # geometry not tileable by TMA boxes: explicit im2col, same GEMM kernel
+        cols = im2col3x3(x, stride=1)
+        a_full = cols if a2 is None else torch.cat([cols, a2], dim=1)
+        return gemm(a_full, wt, bias=bias, bias_div=bias_div, residual=residual, out=out)
+    _lib.check(rc, f"conv3x3_bf16(n={n_img},H={H},W={W},Cin={Cin},Cout={Cout})")
+    _count()
+    return out
+
+
+def groupnorm(x1: torch.Tensor, x2: Optional[torch.Tensor], B: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              silu: bool, out_dtype: torch.dtype = torch.bfloat16, want_raw: bool = False):
+    """GroupNorm(32) over (C/32, T) per sample on the virtual concat [x1 | x2] (token-major fp32) (+SiLU)."""
+    _req(x1, torch.float32, "x1", 2)
+    M, C1 = x1.shape
+    C2 = 0
+    if x2 is not None:
+        _req(x2, torch.float32, "x2", 2)
+        C2 = x2.shape[1]
+        if x2.shape[0] != M or not x2.is_contiguous():
+            raise ValueError("x2 must be contiguous with the same rows as x1")
+    if not x1.is_contiguous() or M % B:
+        raise ValueError("x1 must be contiguous [B*T, C1]")
+    T = M // B
+    C = C1 + C2
+    _req(gamma, torch.float32, "gamma", 1); _req(beta, torch.float32, "beta", 1)
+    if gamma.numel() != C or beta.numel() != C:
+        raise ValueError("gamma/beta size != C1 + C2")
+    L = _lib.lib()
+    ws = torch.empty(L.seer_b200_groupnorm_workspace_floats(B, T), device=x1.device, dtype=torch.float32)
+    ss = torch.empty(2 * B * C, device=x1.device, dtype=torch.float32)
+    y = torch.empty((M, C), device=x1.device, dtype=out_dtype)
+    raw = torch.empty((M, C), device=x1.device, dtype=torch.bfloat16) if want_raw else None
+    rc = L.seer_b200_groupnorm(_p(x1), C1, _p(x2), C2, B, T, _p(gamma), _p(beta), float(eps), int(silu), _p(ws), _p(ss), _p(y),
+                               int(out_dtype == torch.float32), _p(raw), _stream())
+    _lib.check(rc, f"groupnorm(B={B},T={T},C={C1}+{C2})")
+    _count(3)
+    return (y, raw) if want_raw else y
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, torch.float32, "x", 2)
+    M, C = x.shape
+    if out is None:
+        out = torch.empty((M, C), device=x.device, dtype=torch.bfloat16)
+    rc = _lib.lib().seer_b200_layernorm(_p(x), M, C, x.stride(0), _p(gamma), _p(beta), float(eps), _p(out), out.stride(0), _stream())
+    _lib.check(rc, f"layernorm(M={M},C={C})")
+    _count()
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, mode: int, heads: int, n_outer: int, Lq: int = 0,
+              Lk: int = 0, F: int = 0, H: int = 0, W: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q/k/v: 2-D bf16 token-major views [rows, heads*d] (column slices of wider buffers are fine)."""
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _req(t, torch.bfloat16, n, 2)
+    C = q.shape[1]
+    d = C // heads
+    if out is None:
+        out = torch.empty((q.shape[0], C), device=q.device, dtype=torch.bfloat16)
+    rc = _lib.lib().seer_b200_attention(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0), mode,
+                                        heads, d, n_outer, Lq, Lk, F, H, W, _stream())
+    _lib.check(rc, f"attention(mode={mode},heads={heads},d={d},outer={n_outer},Lq={Lq},Lk={Lk},F={F},H={H},W={W})")
+    _count()
+    return out
+
+
+def scta_row_index(B: int, F: int, H: int, W: int, device="cuda") -> torch.Tensor:
+    """(B, n_windows, L) int32 gather permutation used by the SCTA kernel (parity hook)."""
+    nwin, L = ctypes.c_int(0), ctypes.c_int(0)
+    lib = _lib.lib()
+    _lib.check(lib.seer_b200_scta_row_index(B, F, H, W, None, ctypes.byref(nwin), ctypes.byref(L), None), "scta_row_index")
+    out = torch.empty((B, nwin.value, L.value), device=device, dtype=torch.int32)
+    _lib.check(lib.seer_b200_scta_row_index(B, F, H, W, _p(out), ctypes.byref(nwin), ctypes.byref(L), _stream()), "scta_row_index")
+    return out
+
+
+def rope_inplace(qkv: torch.Tensor, tokens_per_clip: int, heads: int, head_dim: int, q_col: int, k_col: int,
+                 freqs: torch.Tensor) -> None:
+    _req(qkv, torch.bfloat16, "qkv", 2); _req(freqs, torch.float32, "freqs", 1)
+    rc = _lib.lib().seer_b200_rope_inplace(_p(qkv), qkv.stride(0), qkv.shape[0], tokens_per_clip, heads, head_dim, q_col, k_col,
+                                           _p(freqs), freqs.numel(), _stream())
+    _lib.check(rc, "rope_inplace")
+    _count()
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, shift: float, flip_sin_to_cos: bool) -> torch.Tensor:
+    _req(t, torch.float32, "t", 1)
+    out = torch.empty((t.numel(), dim), device=t.device, dtype=torch.float32)
+    rc = _lib.lib().seer_b200_timestep_embedding(_p(t), _p(out), t.numel(), dim, float(shift), int(flip_sin_to_cos), _stream())
+    _lib.check(rc, "timestep_embedding")
+    _count()
+    return out
+
+
+def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], add: Optional[torch.Tensor] = None,
+                 silu_in: bool = False, silu_out: bool = False) -> torch.Tensor:
+    _req(x, torch.float32, "x", 2); _req(w, torch.float32, "w", 2)
+    B, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((B, N), device=x.device, dtype=torch.float32)
+    rc = _lib.lib().seer_b200_small_linear(_p(x), x.stride(0), _p(w), _p(bias), _p(add), _p(out), N, B, N, K, int(silu_in),
+                                           int(silu_out), _stream())
+    _lib.check(rc, "small_linear")
+    _count()
+    return out
+
+
+def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """x:(B,4,F,H,W) fp32 -> [B*F*H*W, Cout] fp32."""
+    _req(x, torch.float32, "x", 5)
+    if not x.is_contiguous():
+        raise ValueError("x must be contiguous (B,C,F,H,W)")
+    B, Cin, F, H, W = x.shape
+    Cout = w.shape[0]
+    out = torch.empty((B * F * H * W, Cout), device=x.device, dtype=torch.float32)
+    rc = _lib.lib().seer_b200_conv_in(_p(x), _p(w), _p(bias), _p(out), B, Cin, F, H, W, Cout, _stream())
+    _lib.check(rc, "conv_in")
+    _count()
+    return out
+
+
+def conv_out(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, B: int, F: int, H: int, W: int) -> torch.Tensor:
+    """x:[B*F*H*W, Cin] fp32 -> (B,Cout,F,H,W) fp32."""
+    _req(x, torch.float32, "x", 2)
+    Cin = x.shape[1]
+    Cout = w_packed.shape[0]
+    out = torch.empty((B, Cout, F, H, W), device=x.device, dtype=torch.float32)
+    rc = _lib.lib().seer_b200_conv_out(_p(x), _p(w_packed), _p(bias), _p(out), B, Cin, F, H, W, Cout, _stream())
+    _lib.check(rc, "conv_out")
+    _count()
+    return out
+
+
+def upsample2x(x: torch.Tensor, n_img: int, H: int, W: int) -> torch.Tensor:
+    """x:[n_img*H*W, C] fp32 -> [n_img, 2H, 2W, C] bf16."""
+    _req(x, torch.float32, "x", 2)
+    C = x.shape[1]
+    y = torch.empty((n_img, 2 * H, 2 * W, C), device=x.device, dtype=torch.bfloat16)
+    rc = _lib.lib().seer_b200_upsample2x_to_bf16(_p(x), _p(y), n_img, H, W, C, _stream())
+    _lib.check(rc, "upsample2x")
+    _count()
+    return y
+
+
+def im2col3x3(x: torch.Tensor, stride: int) -> torch.Tensor:
+    """x:[n_img,H,W,C] fp32 or bf16 -> [n_img*(H/s)*(W/s), 9*C] bf16."""
+    if x.dim() != 4 or not x.is_contiguous() or not x.is_cuda:
+        raise ValueError("x must be a contiguous CUDA [n_img,H,W,C] tensor")
+    n_img, H, W, C = x.shape
+    y = torch.empty((n_img * (H // stride) * (W // stride), 9 * C), device=x.device, dtype=torch.bfloat16)
+    rc = _lib.lib().seer_b200_im2col3x3_to_bf16(_p(x), int(x.dtype == torch.bfloat16), _p(y), n_img, H, W, C, stride, _stream())
+    _lib.check(rc, "im2col3x3")
+    _count()
+    return y
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _req(x, torch.float32, "x")
+    if not x.is_contiguous():
+        raise ValueError("x must be contiguous")
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    rc = _lib.lib().seer_b200_cast_f32_to_bf16(_p(x), _p(y), x.numel(), _stream())
+    _lib.check(rc, "cast_f32_to_bf16")
+    _count()
+    return y
+
+
+def cfg_ddim_update(eps: torch.Tensor, x: torch.Tensor, cond_f: int, use_cfg: bool, scale: float, sqrt_one_minus_at: float,
+                    sqrt_at: float, sqrt_a_prev: float, dir_coef: float, x_prev: Optional[torch.Tensor] = None,
+                    pred_x0: Optional[torch.Tensor] = None):
+    """eps:(2b|b,C,cond_f+F2,H,W) fp32, x:(b,C,F2,H,W) fp32 -> (x_prev, pred_x0)."""
+    _req(eps, torch.float32, "eps", 5); _req(x, torch.float32, "x", 5)
+    if not (eps.is_contiguous() and x.is_contiguous()):
+        raise ValueError("eps and x must be contiguous")
+    b, C, F2, H, W = x.shape
+    if eps.shape != ((2 * b if use_cfg else b), C, F2 + cond_f, H, W):
+        raise ValueError(f"eps shape {tuple(eps.shape)} inconsistent with x {tuple(x.shape)}")
+    x_prev = torch.empty_like(x) if x_prev is None else x_prev
+    pred_x0 = torch.empty_like(x) if pred_x0 is None else pred_x0
+    rc = _lib.lib().seer_b200_cfg_ddim_update(_p(eps), _p(x), _p(x_prev), _p(pred_x0), b, C, F2, cond_f, H * W, int(use_cfg),
+                                              float(scale), float(sqrt_one_minus_at), float(sqrt_at), float(sqrt_a_prev),
+                                              float(dir_coef), _stream())
+    _lib.check(rc, "cfg_ddim_update")
+    _count()
+    return x_prev, pred_x0

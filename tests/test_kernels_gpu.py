@@ -1,0 +1,288 @@
+"""Kernel-level parity (-m gpu): every C-ABI entry point against a plain PyTorch fp32 statement of the same op
+on the same seeded inputs.  bf16 operands are rounded once and the reference is computed in fp32/fp64 from the
+ROUNDED values, so the only difference left is accumulation order (tolerances are written per test)."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():  # pragma: no cover
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from oracle import seer_oracle as so  # noqa: E402  (checker only)
+from seervideoldm_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    return so.rel_l2(a.detach().cpu(), b.detach().cpu())
+
+
+def rn(seed, *shape, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 160, 64), (256, 320, 320), (384, 640, 1280), (192, 1280, 2560), (1000, 128, 192),
+                                   (24576, 320, 320), (77 * 24, 640, 768), (128, 64, 64)])
+def test_gemm_plain(M, N, K):
+    a = rn(1, M, K).bfloat16()
+    w = rn(2, N, K, scale=K ** -0.5).bfloat16()
+    out = ops.gemm(a, w)
+    ref = a.float() @ w.float().t()
+    assert out.dtype == torch.float32
+    assert rel(out, ref) < 2e-5
+
+
+def test_gemm_epilogues():
+    M, N, K, K2 = 512, 320, 640, 320
+    a, a2 = rn(3, M, K).bfloat16(), rn(4, M, K2).bfloat16()
+    w = rn(5, N, K + K2, scale=(K + K2) ** -0.5).bfloat16()
+    bias, res = rn(6, N), rn(7, M, N)
+    ref = torch.cat([a, a2], 1).float() @ w.float().t() + bias + res
+    out = ops.gemm(a, w, a2=a2, bias=bias, residual=res)
+    assert rel(out, ref) < 2e-5
+    out16 = ops.gemm(a, w, a2=a2, bias=bias, residual=res, out_dtype=torch.bfloat16)
+    assert out16.dtype == torch.bfloat16 and rel(out16.float(), ref) < 4e-3
+    # per-sample bias rows (time-embedding add): 4 samples of 128 rows, bias matrix is a column slice (ldb > N)
+    wide = rn(8, 4, 2 * N)
+    pb = wide[:, N:]
+    out = ops.gemm(a, w[:, :K].contiguous(), bias=pb, bias_div=128)
+    ref = a.float() @ w[:, :K].float().t() + pb.repeat_interleave(128, 0)
+    assert rel(out, ref) < 2e-5
+    # A given as a column slice of a wider buffer (lda > K), out written into a column slice
+    wide_a = rn(9, M, 3 * K).bfloat16()
+    dst = torch.zeros(M, 2 * N, device=DEV)
+    ops.gemm(wide_a[:, K:2 * K], w[:, :K].contiguous(), out=dst[:, N:])
+    assert rel(dst[:, N:], wide_a[:, K:2 * K].float() @ w[:, :K].float().t()) < 2e-5
+    assert float(dst[:, :N].abs().max()) == 0.0
+
+
+def test_gemm_geglu():
+    M, C = 384, 320
+    a = rn(10, M, C).bfloat16()
+    w = rn(11, 8 * C, C, scale=C ** -0.5)
+    b = rn(12, 8 * C)
+    u = a.float() @ w.bfloat16().float().t() + b
+    ref = u[:, :4 * C] * F.gelu(u[:, 4 * C:])
+    from seervideoldm_b200.packing import pack_geglu
+    wp, bp = pack_geglu(w, b)
+    out = ops.gemm(a, wp.to(DEV), bias=bp.to(DEV), geglu=True)
+    assert out.shape == (M, 4 * C) and out.dtype == torch.bfloat16
+    assert rel(out.float(), ref) < 4e-3
+
+
+def test_gemm_rejects_bad_shapes():
+    a = rn(1, 128, 100).bfloat16()
+    w = rn(2, 160, 100).bfloat16()
+    with pytest.raises(ValueError):
+        ops.gemm(a, w)                      # K % 64 != 0
+    with pytest.raises(TypeError):
+        ops.gemm(a.float(), w)
+
+
+# ------------------------------------------------------------------------------------------------ conv
+@pytest.mark.parametrize("n_img,H,Cin,Cout", [(3, 32, 64, 160), (2, 16, 320, 640), (5, 8, 128, 320), (11, 4, 192, 160),
+                                             (24, 32, 320, 320), (3, 2, 64, 160), (130, 1, 64, 160), (2, 64, 64, 160)])
+def test_conv3x3(n_img, H, Cin, Cout):
+    x = rn(20, n_img, H, H, Cin).bfloat16()
+    w = rn(21, Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5)
+    b = rn(22, Cout)
+    from seervideoldm_b200.packing import pack_conv3x3
+    out = ops.conv3x3(x, pack_conv3x3(w).to(DEV), bias=b)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    assert rel(out, ref) < 2e-5
+
+
+def test_conv3x3_fused_shortcut_and_temb():
+    n_img, H, Cin, Cout, Csc, frames = 4, 16, 128, 320, 192, 2
+    x = rn(23, n_img, H, H, Cin).bfloat16()
+    raw = rn(24, n_img * H * H, Csc).bfloat16()
+    w, wsc = rn(25, Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5), rn(26, Cout, Csc, 1, 1, scale=Csc ** -0.5)
+    temb = rn(27, n_img // frames, Cout)
+    from seervideoldm_b200.packing import pack_conv3x3
+    wt = torch.cat([pack_conv3x3(w), wsc.reshape(Cout, Csc).bfloat16()], 1).contiguous().to(DEV)
+    out = ops.conv3x3(x, wt, a2=raw, bias=temb, bias_div=frames * H * H)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), None, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    ref = ref + raw.float() @ wsc.reshape(Cout, Csc).bfloat16().float().t() + temb.repeat_interleave(frames * H * H, 0)
+    assert rel(out, ref) < 2e-5
+
+
+def test_conv3x3_generic_fallback_and_stride2():
+    from seervideoldm_b200.packing import pack_conv3x3
+    x = rn(28, 2, 12, 12, 64).bfloat16()          # 12 does not divide 128 -> im2col path
+    w = rn(29, 160, 64, 3, 3, scale=(9 * 64) ** -0.5)
+    out = ops.conv3x3(x, pack_conv3x3(w).to(DEV))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), None, padding=1).permute(0, 2, 3, 1).reshape(-1, 160)
+    assert rel(out, ref) < 2e-5
+    xf = rn(30, 3, 16, 16, 64)
+    cols = ops.im2col3x3(xf.reshape(3, 16, 16, 64), stride=2)
+    out = ops.gemm(cols, pack_conv3x3(w).to(DEV))
+    ref = F.conv2d(xf.bfloat16().float().permute(0, 3, 1, 2), w.bfloat16().float(), None, stride=2, padding=1)
+    assert rel(out, ref.permute(0, 2, 3, 1).reshape(-1, 160)) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("B,T,C1,C2", [(2, 3 * 64, 320, 0), (1, 2 * 256, 1280, 640), (2, 48, 640, 320), (3, 1000, 64, 0)])
+def test_groupnorm(B, T, C1, C2):
+    x1 = rn(40, B * T, C1) * 2 + 0.5
+    x2 = rn(41, B * T, C2) - 0.3 if C2 else None
+    C = C1 + C2
+    g, b = rn(42, C), rn(43, C)
+    full = x1 if x2 is None else torch.cat([x1, x2], 1)
+    ref = F.group_norm(full.reshape(B, T, C).permute(0, 2, 1).double(), 32, g.double(), b.double(), 1e-5)
+    ref = F.silu(ref).permute(0, 2, 1).reshape(B * T, C).float()
+    y, raw = ops.groupnorm(x1, x2, B, g, b, 1e-5, True, out_dtype=torch.float32, want_raw=True)
+    assert rel(y, ref) < 2e-6
+    assert torch.equal(raw, full.bfloat16())
+    y16 = ops.groupnorm(x1, x2, B, g, b, 1e-5, True)
+    assert y16.dtype == torch.bfloat16 and rel(y16.float(), ref) < 4e-3
+    again = ops.groupnorm(x1, x2, B, g, b, 1e-5, True, out_dtype=torch.float32)
+    assert torch.equal(again, y)            # deterministic (no float atomics)
+
+
+@pytest.mark.parametrize("M,C", [(100, 320), (333, 640), (64, 1280)])
+def test_layernorm(M, C):
+    x = rn(50, M, C) * 3 + 1
+    g, b = rn(51, C), rn(52, C)
+    ref = F.layer_norm(x.double(), (C,), g.double(), b.double(), 1e-5).float()
+    y = ops.layernorm(x, g, b)
+    assert rel(y.float(), ref) < 4e-3
+    assert (y.float() - ref).abs().max() < 0.05 * ref.abs().max()
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, causal):
+    s = (q.double() @ k.double().transpose(-1, -2)) * q.shape[-1] ** -0.5
+    if causal:
+        L = s.shape[-1]
+        s = s.masked_fill(~torch.ones(L, L, dtype=torch.bool, device=s.device).tril(), float("-inf"))
+    return (s.softmax(-1) @ v.double()).float()
+
+
+@pytest.mark.parametrize("d,frames,L", [(40, 3, 1024), (80, 2, 256), (160, 5, 64), (160, 3, 16), (40, 1, 100)])
+def test_attention_spatial(d, frames, L):
+    heads = 8
+    C = heads * d
+    qkv = rn(60, frames * L, 3 * C).bfloat16()
+    out = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], mode=ops.ATTN_SPATIAL, heads=heads, n_outer=frames, Lq=L, Lk=L)
+    t = qkv.float().reshape(frames, L, 3, heads, d).permute(2, 0, 3, 1, 4)
+    ref = _attn_ref(t[0], t[1], t[2], False).permute(0, 2, 1, 3).reshape(frames * L, C)
+    assert rel(out.float(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("d,frames,L", [(40, 3, 1024), (80, 2, 256), (160, 4, 16)])
+def test_attention_cross_77(d, frames, L):
+    heads, Lk = 8, 77
+    C = heads * d
+    q = rn(61, frames * L, C).bfloat16()
+    kv = rn(62, frames * Lk, 2 * C).bfloat16()
+    out = ops.attention(q, kv[:, :C], kv[:, C:], mode=ops.ATTN_CROSS, heads=heads, n_outer=frames, Lq=L, Lk=Lk)
+    qh = q.float().reshape(frames, L, heads, d).permute(0, 2, 1, 3)
+    kh = kv[:, :C].float().reshape(frames, Lk, heads, d).permute(0, 2, 1, 3)
+    vh = kv[:, C:].float().reshape(frames, Lk, heads, d).permute(0, 2, 1, 3)
+    ref = _attn_ref(qh, kh, vh, False).permute(0, 2, 1, 3).reshape(frames * L, C)
+    assert rel(out.float(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("d,B,Fr,H", [(40, 2, 3, 32), (80, 1, 4, 16), (160, 2, 3, 8), (160, 2, 5, 4), (40, 1, 2, 64)])
+def test_attention_scta(d, B, Fr, H):
+    heads = 8
+    C = heads * d
+    T = Fr * H * H
+    qkv = rn(63, B * T, 3 * C).bfloat16()
+    out = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], mode=ops.ATTN_SCTA, heads=heads, n_outer=B, F=Fr, H=H, W=H)
+    t = qkv.float().reshape(B, T, 3, heads, d).permute(2, 0, 3, 1, 4)      # (3, B, heads, T, d)
+    ref = torch.empty(B, heads, T, d, device=DEV)
+    for seq in torch.from_numpy(so.scta_sequences(Fr, H, H)).to(DEV):
+        ref[:, :, seq] = _attn_ref(t[0][:, :, seq], t[1][:, :, seq], t[2][:, :, seq], True)
+    ref = ref.permute(0, 2, 1, 3).reshape(B * T, C)
+    assert rel(out.float(), ref) < 6e-3
+
+
+def test_scta_row_permutation_bit_exact(golden_dir):
+    """The kernel's gather permutation == the reference's window_partition order (golden from the reference)."""
+    g = torch.load(os.path.join(golden_dir, "scta_index.pt"), weights_only=False)
+    for key, seqs in g.items():
+        if key.startswith("heads"):
+            continue
+        f, h, w = (int(v) for v in key.split("x"))
+        idx = ops.scta_row_index(2, f, h, w).cpu().long()
+        assert torch.equal(idx[0], seqs), key
+        assert torch.equal(idx[1], seqs + f * h * w), key
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def test_rope_matches_oracle():
+    heads, d, Fr, hw, B = 8, 40, 3, 64, 2
+    C = heads * d
+    M = B * Fr * hw
+    qkv = rn(70, M, 3 * C).bfloat16()
+    freqs = (1.0 / (10000.0 ** (torch.arange(0, 32, 2).float() / 32))).to(DEV)
+    ref = qkv.clone().float().reshape(B, Fr * hw, 3, heads, d)
+    pos = torch.arange(Fr * hw)
+    for which in (0, 1):
+        r = so.rope_interleaved(ref[:, :, which].permute(0, 2, 1, 3).cpu(), pos, 32)     # (B, heads, T, d)
+        ref[:, :, which] = r.permute(0, 2, 1, 3).to(DEV)
+    ops.rope_inplace(qkv, Fr * hw, heads, d, 0, C, freqs)
+    assert rel(qkv.float(), ref.reshape(M, 3 * C)) < 4e-3
+    assert torch.equal(qkv[:, 2 * C:].float(), ref.reshape(M, 3 * C)[:, 2 * C:])          # V untouched
+
+
+def test_time_embedding_and_small_linear():
+    t = torch.tensor([991.0, 1.0, 496.0], device=DEV)
+    emb = ops.timestep_embedding(t, 320, 0.0, True)
+    ref = so.timestep_embedding(t.cpu(), 320, True, 0)
+    assert rel(emb, ref) < 1e-5
+    w, b, add = rn(71, 1280, 320, scale=320 ** -0.5), rn(72, 1280), rn(73, 1280)
+    out = ops.small_linear(emb, w, b, add, silu_in=True, silu_out=True)
+    refo = F.silu(F.linear(F.silu(emb), w, b) + add)
+    assert rel(out, refo) < 1e-5
+    x = rn(74, 19, 1280)
+    assert rel(ops.small_linear(x, rn(75, 640, 1280), None), x @ rn(75, 640, 1280).t()) < 1e-5
+
+
+def test_conv_in_out():
+    B, Fr, H = 2, 3, 8
+    x = rn(80, B, 4, Fr, H, H)
+    w, b = rn(81, 320, 4, 3, 3), rn(82, 320)
+    out = ops.conv_in(x, w.reshape(320, 36).contiguous(), b)
+    ref = so.conv_framewise(x.cpu(), w.cpu(), b.cpu()).permute(0, 2, 3, 4, 1).reshape(-1, 320)
+    assert rel(out, ref) < 1e-5
+    h = rn(83, B * Fr * H * H, 320)
+    wo, bo = rn(84, 4, 320, 3, 3, scale=0.02), rn(85, 4)
+    from seervideoldm_b200.packing import pack_conv_out
+    eps = ops.conv_out(h, pack_conv_out(wo.cpu()).to(DEV), bo, B, Fr, H, H)
+    ref = so.conv_framewise(h.cpu().reshape(B, Fr, H, H, 320).permute(0, 4, 1, 2, 3), wo.cpu(), bo.cpu())
+    assert eps.shape == (B, 4, Fr, H, H) and rel(eps, ref) < 1e-5
+
+
+def test_upsample_and_cast():
+    x = rn(90, 3 * 4 * 4, 64)
+    y = ops.upsample2x(x, 3, 4, 4)
+    ref = x.reshape(3, 4, 4, 64).repeat_interleave(2, 1).repeat_interleave(2, 2).bfloat16()
+    assert torch.equal(y, ref)
+    assert torch.equal(ops.cast_bf16(x), x.bfloat16())
+
+
+def test_cfg_ddim_update_bit_exact():
+    """Integer-like exactness: same fp32 operation order as ddim_video.py:209-237 -> bit-identical to PyTorch."""
+    b, C, F1, F2, H = 2, 4, 2, 5, 8
+    sch = so.make_schedule(30)
+    for idx in (30, 17, 0):
+        eps = rn(100 + idx, 2 * b, C, F1 + F2, H, H)
+        x = rn(200 + idx, b, C, F2, H, H) * 3
+        a_t, a_p, s1m = sch.alphas[idx], sch.alphas_prev[idx], sch.sqrt_one_minus_alphas[idx]
+        xp, p0 = ops.cfg_ddim_update(eps, x, F1, True, 7.5, float(s1m), float(a_t.sqrt()), float(a_p.sqrt()),
+                                     float((1.0 - a_p).sqrt()))
+        e_u, e_c = eps.cpu().chunk(2)
+        e = so.cfg_combine(e_u[:, :, F1:], e_c[:, :, F1:], 7.5)
+        full = lambda v: torch.full((b, 1, 1, 1, 1), float(v))
+        xr, pr = so.ddim_update(x.cpu(), e, full(a_t), full(a_p), full(s1m))
+        assert torch.equal(p0.cpu(), pr) and torch.equal(xp.cpu(), xr)
