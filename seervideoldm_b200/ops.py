@@ -19,6 +19,26 @@ GEMM_GEGLU = 2
 ATTN_SPATIAL, ATTN_CROSS, ATTN_SCTA = 0, 1, 2
 
 LAUNCHES = 0           # kernels launched through this module (graph replays are counted by the caller)
+PROFILE = None         # bench.py sets this to a list: (name, algorithmic flops, start event, end event) per GEMM/conv launch
+
+
+class _Timed:
+    """CUDA events on the launching stream around one kernel launch (only while ops.PROFILE is a list)."""
+
+    def __init__(self, name: str, flops: float):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.name, self.flops, self.e0, self.e1))
+        return False
 
 
 def _count(n: int = 1) -> None:
@@ -80,9 +100,11 @@ def gemm(a: torch.Tensor, wt: torch.Tensor, *, a2: Optional[torch.Tensor] = None
         ldb = bias.stride(0) if bias.dim() == 2 else N
     if residual is not None:
         _req(residual, torch.float32, "residual", 2)
-    rc = _lib.lib().seer_b200_gemm_bf16(_p(a), a.stride(0), K1, _p(a2), a2.stride(0) if a2 is not None else 0, K2, _p(wt), M, N,
-                                        _p(bias), ldb, bias_div, _p(residual), residual.stride(0) if residual is not None else 0,
-                                        _p(out), out.stride(0), flags, _stream())
+    with _Timed(f"gemm M={M} N={N} K={K1 + K2}", 2.0 * M * N * (K1 + K2)):
+        rc = _lib.lib().seer_b200_gemm_bf16(_p(a), a.stride(0), K1, _p(a2), a2.stride(0) if a2 is not None else 0, K2, _p(wt), M,
+                                            N, _p(bias), ldb, bias_div, _p(residual),
+                                            residual.stride(0) if residual is not None else 0, _p(out), out.stride(0), flags,
+                                            _stream())
     _lib.check(rc, f"gemm_bf16(M={M},N={N},K={K1}+{K2})")
     _count()
     return out
@@ -115,10 +137,11 @@ def conv3x3(x: torch.Tensor, wt: torch.Tensor, *, a2: Optional[torch.Tensor] = N
         ldb = bias.stride(0) if bias.dim() == 2 else Cout
     if residual is not None:
         _req(residual, torch.float32, "residual", 2)
-    rc = _lib.lib().seer_b200_conv3x3_bf16(_p(x), n_img, H, W, Cin, _p(a2), a2.stride(0) if a2 is not None else 0, K2, _p(wt),
-                                           Cout, _p(bias), ldb, bias_div, _p(residual),
-                                           residual.stride(0) if residual is not None else 0, _p(out), out.stride(0), flags,
-                                           _stream())
+    with _Timed(f"conv3x3 M={M} N={Cout} K={9 * Cin + K2}", 2.0 * M * Cout * (9 * Cin + K2)):
+        rc = _lib.lib().seer_b200_conv3x3_bf16(_p(x), n_img, H, W, Cin, _p(a2), a2.stride(0) if a2 is not None else 0, K2,
+                                               _p(wt), Cout, _p(bias), ldb, bias_div, _p(residual),
+                                               residual.stride(0) if residual is not None else 0, _p(out), out.stride(0),
+                                               flags, _stream())
     if rc == -2:      # geometry not tileable by TMA boxes: explicit im2col, same GEMM kernel
         cols = im2col3x3(x, stride=1)
         a_full = cols if a2 is None else torch.cat([cols, a2], dim=1)

@@ -1,0 +1,415 @@
+"""SeerUNet — host-side mirror of the reference's module API over the seer_b200 kernels.
+
+Drop-in for /root/reference/seer/models/unet_3d_condition.py:61-376 on the denoising hot path:
+same constructor arguments, same `forward(sample, timestep, context, cond_frame=0, return_attn=False)`
+signature (plus the `encoder_hidden_states=` alias), same state-dict keys/shapes
+(Appendix C, loads reference checkpoints with strict=True), same exceptions style.  Underneath, the
+whole forward runs on hand-written sm_100a kernels in one canonical channels-last layout
+[(b f h w), C]; there is no PyTorch/CPU fallback — a missing libseer_b200.so raises.
+
+Data layout in HBM (per evaluation, B = UNet batch after CFG):
+  * residual stream   fp32 [B*F*h*w, C]            (GroupNorm/LayerNorm inputs, skip connections)
+  * GEMM/conv operands bf16, same token-major shape (normalised activations, q/k/v, FF hidden)
+  * packed weights    bf16 [N, K] K-major           (conv3x3: K = [ky][kx][Cin] (+ fused 1x1 shortcut))
+  * text K/V          bf16 [B*F*77, 2C] per cross-attention layer, cached across the 31 DDIM steps
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import asdict
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops, packing
+from .config import UNetConfig
+from .weights import unet_schema
+
+
+class _Node(nn.Module):
+    """Container whose children are registered under the reference's attribute names (numeric names index like
+    nn.ModuleList), so state_dict keys match the reference exactly."""
+
+    def __getitem__(self, i):
+        return self._modules[str(i)]
+
+    def __len__(self):
+        return len(self._modules)
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("seer_b200 sub-modules are parameter containers; call SeerUNet.forward")
+
+
+class _Config(SimpleNamespace):
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+
+class SeerUNet(nn.Module):
+    def __init__(self, sample_size=None, in_channels=4, out_channels=4, center_input_sample=False, flip_sin_to_cos=True,
+                 freq_shift=0,
+                 down_block_types=("CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "DownBlock3D"),
+                 up_block_types=("UpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D"),
+                 block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, downsample_padding=1,
+                 mid_block_scale_factor=1, act_fn="silu", norm_num_groups=32, norm_eps=1e-5, cross_attention_dim=1280,
+                 attention_head_dim=8):
+        super().__init__()
+        if len(block_out_channels) != 4:
+            raise ValueError("SeerUNet hard-codes 4 resolution levels (unet_3d_condition.py:90-91)")
+        if norm_num_groups != 32:
+            raise ValueError("block GroupNorms are fixed at 32 groups in the reference (SURVEY F15)")
+        if act_fn not in ("silu", "swish"):
+            raise ValueError(f"unsupported act_fn {act_fn}")
+        self.cfg = UNetConfig(sample_size=sample_size, in_channels=in_channels, out_channels=out_channels,
+                              center_input_sample=center_input_sample, flip_sin_to_cos=flip_sin_to_cos, freq_shift=freq_shift,
+                              block_out_channels=tuple(block_out_channels), layers_per_block=layers_per_block,
+                              mid_block_scale_factor=mid_block_scale_factor, act_fn=act_fn, norm_num_groups=norm_num_groups,
+                              norm_eps=norm_eps, cross_attention_dim=cross_attention_dim, attention_head_dim=attention_head_dim)
+        self.config = _Config(**asdict(self.cfg))
+        self.sample_size = sample_size
+        self._packed: Optional[dict] = None
+        self._kv_key = None
+        self._kv: List[torch.Tensor] = []
+        self._build_tree()
+        self.reset_parameters()
+
+    # ------------------------------------------------------------------ parameters / state dict
+    def _build_tree(self) -> None:
+        for key, shape in unet_schema(self.cfg).items():
+            parts = key.split(".")
+            mod: nn.Module = self
+            for p in parts[:-1]:
+                if p not in mod._modules:
+                    mod.add_module(p, _Node())
+                mod = mod._modules[p]
+            if key.endswith("rotary_emb.freqs"):
+                dim = 2 * shape[0]
+                mod.register_buffer("freqs", 1.0 / (10000.0 ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim)))
+            else:
+                mod.register_parameter(parts[-1], nn.Parameter(torch.empty(shape), requires_grad=False))
+
+    @torch.no_grad()
+    def reset_parameters(self) -> None:
+        """PyTorch-default-scale init; `proj_out` zero-initialised like the reference (attention.py:126-127)."""
+        params = dict(self.named_parameters())
+        for name, p in params.items():
+            owner = name.split(".")[-2]
+            if owner.startswith("norm") or owner == "conv_norm_out":
+                p.fill_(1.0 if name.endswith("weight") else 0.0)
+            elif owner == "proj_out":
+                p.zero_()
+            else:
+                ref = p if name.endswith("weight") else params[name[: -len("bias")] + "weight"]
+                bound = 1.0 / math.sqrt(max(1, ref[0].numel()))
+                p.uniform_(-bound, bound)
+        self._packed = None
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._packed = None
+        self._kv_key = None
+        return out
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._packed = None
+        self._kv_key = None
+        return out
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.conv_in.weight.dtype
+
+    @property
+    def device(self) -> torch.device:
+        return self.conv_in.weight.device
+
+    # API parity no-ops (xformers / slicing are memory-saving switches of the reference's PyTorch path)
+    def enable_xformers_memory_efficient_attention(self):
+        return None
+
+    def set_use_memory_efficient_attention_xformers(self, valid: bool = True):
+        return None
+
+    def set_attention_slice(self, slice_size=None):
+        return None
+
+    # ------------------------------------------------------------------ weight packing
+    def _P(self, key: str) -> torch.Tensor:
+        mod: nn.Module = self
+        parts = key.split(".")
+        for p in parts[:-1]:
+            mod = mod._modules[p]
+        t = mod._parameters.get(parts[-1])
+        if t is None:
+            t = mod._buffers[parts[-1]]
+        return t.detach()
+
+    def _has(self, key: str) -> bool:
+        try:
+            self._P(key)
+            return True
+        except KeyError:
+            return False
+
+    @torch.no_grad()
+    def _pack(self) -> dict:
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("SeerUNet (seer_b200) runs on CUDA only: move the module with .cuda() before calling it")
+        if self.dtype != torch.float32:
+            raise RuntimeError("keep parameters in fp32 (the reference cannot run otherwise either — SURVEY F10); "
+                               "the kernels compute in bf16 with fp32 accumulation")
+        P = self._P
+        f32 = lambda k: P(k).float().contiguous()
+        pk: dict = {}
+        pk["conv_in_w"] = P("conv_in.weight").float().reshape(self.cfg.block_out_channels[0], -1).contiguous()
+        pk["conv_in_b"] = f32("conv_in.bias")
+        pk["te1_w"], pk["te1_b"] = f32("time_embedding.linear_1.weight"), f32("time_embedding.linear_1.bias")
+        pk["te2_w"], pk["te2_b"] = f32("time_embedding.linear_2.weight"), f32("time_embedding.linear_2.bias")
+        pk["gno_g"], pk["gno_b"] = f32("conv_norm_out.weight"), f32("conv_norm_out.bias")
+        pk["conv_out_w"] = packing.pack_conv_out(P("conv_out.weight"))
+        pk["conv_out_b"] = f32("conv_out.bias")
+
+        temb_w, temb_b = [], []
+        off = 0
+
+        def resnet(prefix: str) -> dict:
+            nonlocal off
+            w1 = P(prefix + "conv1.weight")
+            cout, cin = w1.shape[:2]
+            r = dict(cin=cin, cout=cout, off=off, sc=self._has(prefix + "conv_shortcut.weight"))
+            r["g1"], r["b1"] = f32(prefix + "norm1.weight"), f32(prefix + "norm1.bias")
+            r["g2"], r["b2"] = f32(prefix + "norm2.weight"), f32(prefix + "norm2.bias")
+            r["w1"] = packing.pack_conv3x3(w1)
+            temb_w.append(f32(prefix + "time_emb_proj.weight"))
+            temb_b.append(f32(prefix + "time_emb_proj.bias") + f32(prefix + "conv1.bias"))   # conv1 bias folded in
+            off += cout
+            if r["sc"]:
+                r["w2"] = packing.pack_conv3x3(P(prefix + "conv2.weight"), P(prefix + "conv_shortcut.weight"))
+                r["bias2"] = f32(prefix + "conv2.bias") + f32(prefix + "conv_shortcut.bias")
+            else:
+                r["w2"] = packing.pack_conv3x3(P(prefix + "conv2.weight"))
+                r["bias2"] = f32(prefix + "conv2.bias")
+            return r
+
+        def xf(prefix: str, temporal: bool) -> dict:
+            b = prefix + "transformer_blocks.0."
+            t = dict(temporal=temporal, C=P(prefix + "proj_in.weight").shape[0])
+            t["gn_g"], t["gn_b"] = f32(prefix + "norm.weight"), f32(prefix + "norm.bias")
+            t["pin_w"], t["pin_b"] = packing.pack_conv1x1(P(prefix + "proj_in.weight")), f32(prefix + "proj_in.bias")
+            t["pout_w"], t["pout_b"] = packing.pack_conv1x1(P(prefix + "proj_out.weight")), f32(prefix + "proj_out.bias")
+            t["ln1_g"], t["ln1_b"] = f32(b + "norm1.weight"), f32(b + "norm1.bias")
+            t["ln3_g"], t["ln3_b"] = f32(b + "norm3.weight"), f32(b + "norm3.bias")
+            t["qkv_w"] = packing.pack_qkv(P(b + "attn1.to_q.weight"), P(b + "attn1.to_k.weight"), P(b + "attn1.to_v.weight"))
+            t["o1_w"], t["o1_b"] = packing.pack_linear(P(b + "attn1.to_out.0.weight")), f32(b + "attn1.to_out.0.bias")
+            t["ff1_w"], t["ff1_b"] = packing.pack_geglu(P(b + "ff.net.0.proj.weight"), P(b + "ff.net.0.proj.bias"))
+            t["ff2_w"], t["ff2_b"] = packing.pack_linear(P(b + "ff.net.2.weight")), f32(b + "ff.net.2.bias")
+            if temporal:
+                t["freqs"] = f32(b + "attn1.rotary_emb.freqs")
+            else:
+                t["ln2_g"], t["ln2_b"] = f32(b + "norm2.weight"), f32(b + "norm2.bias")
+                t["q2_w"] = packing.pack_linear(P(b + "attn2.to_q.weight"))
+                t["kv2_w"] = packing.pack_kv(P(b + "attn2.to_k.weight"), P(b + "attn2.to_v.weight"))
+                t["o2_w"], t["o2_b"] = packing.pack_linear(P(b + "attn2.to_out.0.weight")), f32(b + "attn2.to_out.0.bias")
+            return t
+
+        n = len(self.cfg.block_out_channels)
+        L = self.cfg.layers_per_block
+        pk["down"] = []
+        for i in range(n):
+            blk = dict(res=[], attn=[], tattn=[], down=None)
+            for j in range(L):
+                blk["res"].append(resnet(f"down_blocks.{i}.resnets.{j}."))
+                if i < n - 1:
+                    blk["attn"].append(xf(f"down_blocks.{i}.attentions.{j}.", False))
+                    blk["tattn"].append(xf(f"down_blocks.{i}.temporal_attentions.{j}.", True))
+            if i < n - 1:
+                blk["down"] = (packing.pack_conv3x3(P(f"down_blocks.{i}.downsamplers.0.conv.weight")),
+                               f32(f"down_blocks.{i}.downsamplers.0.conv.bias"))
+            pk["down"].append(blk)
+        pk["mid"] = dict(res=[resnet("mid_block.resnets.0."), resnet("mid_block.resnets.1.")],
+                         attn=xf("mid_block.attentions.0.", False), tattn=xf("mid_block.temporal_attentions.0.", True))
+        pk["up"] = []
+        for i in range(n):
+            blk = dict(res=[], attn=[], tattn=[], up=None)
+            for j in range(L + 1):
+                blk["res"].append(resnet(f"up_blocks.{i}.resnets.{j}."))
+                if i > 0:
+                    blk["attn"].append(xf(f"up_blocks.{i}.attentions.{j}.", False))
+                    blk["tattn"].append(xf(f"up_blocks.{i}.temporal_attentions.{j}.", True))
+            if i < n - 1:
+                blk["up"] = (packing.pack_conv3x3(P(f"up_blocks.{i}.upsamplers.0.conv.weight")),
+                             f32(f"up_blocks.{i}.upsamplers.0.conv.bias"))
+            pk["up"].append(blk)
+        pk["temb_w"] = torch.cat(temb_w, 0).contiguous()
+        pk["temb_b"] = torch.cat(temb_b, 0).contiguous()
+        self._packed = pk
+        return pk
+
+    # ------------------------------------------------------------------ operators
+    def _resnet(self, r: dict, x1, x2, B, F, H, W, temb_all):
+        """ResnetBlock3D.forward (resnet.py:174-208) on the virtual concat [x1 | x2]."""
+        T = F * H * W
+        eps = self.cfg.norm_eps
+        cin, cout = r["cin"], r["cout"]
+        if r["sc"]:
+            h, raw = ops.groupnorm(x1, x2, B, r["g1"], r["b1"], eps, True, want_raw=True)
+        else:
+            if x2 is not None:
+                raise RuntimeError("concat input without a shortcut conv cannot occur in this architecture")
+            h, raw = ops.groupnorm(x1, None, B, r["g1"], r["b1"], eps, True), None
+        tb = temb_all[:, r["off"]: r["off"] + cout]
+        h1 = ops.conv3x3(h.view(B * F, H, W, cin), r["w1"], bias=tb, bias_div=T)
+        h2 = ops.groupnorm(h1, None, B, r["g2"], r["b2"], eps, True)
+        if r["sc"]:
+            return ops.conv3x3(h2.view(B * F, H, W, cout), r["w2"], a2=raw, bias=r["bias2"])
+        return ops.conv3x3(h2.view(B * F, H, W, cout), r["w2"], bias=r["bias2"], residual=x1)
+
+    def _ff(self, t: dict, tok, out_rows=None):
+        """x + FF(LN3(x)) -> bf16 (feeds proj_out only).  attention.py:244,323 + 744-747,791-793."""
+        n3 = ops.layernorm(tok, t["ln3_g"], t["ln3_b"])
+        hid = ops.gemm(n3, t["ff1_w"], bias=t["ff1_b"], geglu=True)
+        return ops.gemm(hid, t["ff2_w"], bias=t["ff2_b"], residual=tok, out=out_rows, out_dtype=torch.bfloat16)
+
+    def _transformer(self, t: dict, x, B, F, H, W, kv, cond_frame):
+        """SpatialTransformer3D.forward (attention.py:129-145) with its text (:308-327) or temporal (:231-248) block."""
+        C, heads = t["C"], self.cfg.heads
+        d = C // heads
+        hw, T = H * W, F * H * W
+        M = B * T
+        hn = ops.groupnorm(x, None, B, t["gn_g"], t["gn_b"], 1e-6, False)
+        tok = ops.gemm(hn, t["pin_w"], bias=t["pin_b"])                                   # fp32 token stream
+        n1 = ops.layernorm(tok, t["ln1_g"], t["ln1_b"])
+        qkv = ops.gemm(n1, t["qkv_w"], out_dtype=torch.bfloat16)                          # [M, 3C]
+        if t["temporal"]:
+            ops.rope_inplace(qkv, T, heads, d, 0, C, t["freqs"])
+            att = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], mode=ops.ATTN_SCTA, heads=heads, n_outer=B,
+                                F=F, H=H, W=W)
+        else:
+            att = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], mode=ops.ATTN_SPATIAL, heads=heads,
+                                n_outer=B * F, Lq=hw, Lk=hw)
+        tok = ops.gemm(att, t["o1_w"], bias=t["o1_b"], residual=tok)
+        if not t["temporal"]:
+            n2 = ops.layernorm(tok, t["ln2_g"], t["ln2_b"])
+            q2 = ops.gemm(n2, t["q2_w"], out_dtype=torch.bfloat16)
+            Lk = kv.shape[0] // (B * F)
+            att2 = ops.attention(q2, kv[:, :C], kv[:, C:], mode=ops.ATTN_CROSS, heads=heads, n_outer=B * F, Lq=hw, Lk=Lk)
+            tok = ops.gemm(att2, t["o2_w"], bias=t["o2_b"], residual=tok)
+        if t["temporal"] and cond_frame > 0:
+            # the first cond_frame frames of every clip bypass the feed-forward (attention.py:240-246)
+            y = torch.empty((M, C), device=x.device, dtype=torch.bfloat16)
+            c0 = min(cond_frame, F) * hw
+            for b in range(B):
+                lo, mid, hi = b * T, b * T + c0, (b + 1) * T
+                y[lo:mid] = ops.cast_bf16(tok[lo:mid].contiguous())
+                if mid < hi:
+                    self._ff(t, tok[mid:hi], out_rows=y[mid:hi])
+        else:
+            y = self._ff(t, tok)
+        return ops.gemm(y, t["pout_w"], bias=t["pout_b"], residual=x)
+
+    def _cross_layers(self, pk: dict) -> List[dict]:
+        return [a for blk in pk["down"] for a in blk["attn"]] + [pk["mid"]["attn"]] + [a for blk in pk["up"] for a in blk["attn"]]
+
+    def compute_context_kv(self, context: torch.Tensor, out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+        """K/V projections of the text context for every cross-attention layer: [B*F*L, 2C] bf16 each
+        (attention.py:517-518 with the per-frame context of :314-315).  `out` recomputes into existing buffers."""
+        pk = self._packed or self._pack()
+        ctx = ops.cast_bf16(context.reshape(-1, context.shape[-1]).float().contiguous())
+        layers = self._cross_layers(pk)
+        if out is None:
+            return [ops.gemm(ctx, a["kv2_w"], out_dtype=torch.bfloat16) for a in layers]
+        for a, o in zip(layers, out):
+            ops.gemm(ctx, a["kv2_w"], out=o)
+        return out
+
+    def _context_kv(self, pk: dict, context: torch.Tensor) -> List[torch.Tensor]:
+        """K/V of every cross-attention layer depend only on the text context -> computed once per clip and reused
+        for all 31 DDIM evaluations (SURVEY §7.1 'exploitable redundancy' (i)).  The cache is keyed on tensor identity
+        + version and holds a reference: a data_ptr()-only key would go stale when the caching allocator hands a
+        freed context's address to a new tensor."""
+        if self._kv_key is not None and self._kv_key[0] is context and self._kv_key[1] == context._version:
+            return self._kv
+        self._kv = self.compute_context_kv(context)
+        self._kv_key = (context, context._version)
+        return self._kv
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, sample: torch.Tensor, timestep, context: Optional[torch.Tensor] = None, cond_frame: int = 0,
+                return_attn: bool = False, encoder_hidden_states: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if context is None:
+            context = encoder_hidden_states
+        if context is None:
+            raise ValueError("context (B, F, L, cross_attention_dim) is required")
+        if return_attn:
+            raise NotImplementedError("return_attn=True (pre-softmax score dump) is not on the sampling path")
+        if sample.dim() != 5 or context.dim() != 4:
+            raise ValueError("expected sample (B,C,F,H,W) and context (B,F,L,D)")
+        pk = self._packed or self._pack()
+        cfg = self.cfg
+        dev = self.device
+        B, Cin, F, H, W = sample.shape
+        if Cin != cfg.in_channels or context.shape[0] != B or context.shape[1] != F or context.shape[3] != cfg.cross_attention_dim:
+            raise ValueError(f"shape mismatch: sample {tuple(sample.shape)} context {tuple(context.shape)}")
+        if H % 8 or W % 8:
+            raise ValueError("latent height/width must be multiples of 8 (three stride-2 levels)")
+        sample = sample.to(device=dev, dtype=torch.float32)
+        if cfg.center_input_sample:
+            sample = 2 * sample - 1.0
+        # 1. time (unet_3d_condition.py:298-308)
+        t = timestep
+        if not torch.is_tensor(t):
+            t = torch.tensor([t], dtype=torch.long, device=dev)
+        elif t.dim() == 0:
+            t = t[None].to(dev)
+        t = t.to(dev).broadcast_to((B,)).to(torch.float32).contiguous()
+        temb = ops.timestep_embedding(t, cfg.block_out_channels[0], float(cfg.freq_shift), cfg.flip_sin_to_cos)
+        e1 = ops.small_linear(temb, pk["te1_w"], pk["te1_b"], silu_out=True)
+        emb = ops.small_linear(e1, pk["te2_w"], pk["te2_b"])
+        temb_all = ops.small_linear(emb, pk["temb_w"], pk["temb_b"], silu_in=True)      # all 22 time_emb_proj at once
+        kvs = iter(self._context_kv(pk, context.to(dev)))
+
+        # 2. conv_in -> token-major fp32 stream
+        x = ops.conv_in(sample.contiguous(), pk["conv_in_w"], pk["conv_in_b"])
+        h, w = H, W
+        skips: List[torch.Tensor] = [x]
+        n = len(cfg.block_out_channels)
+        # 3. down
+        for i, blk in enumerate(pk["down"]):
+            for j, r in enumerate(blk["res"]):
+                x = self._resnet(r, x, None, B, F, h, w, temb_all)
+                if blk["attn"]:
+                    x = self._transformer(blk["attn"][j], x, B, F, h, w, next(kvs), cond_frame)
+                    x = self._transformer(blk["tattn"][j], x, B, F, h, w, None, cond_frame)
+                skips.append(x)
+            if blk["down"] is not None:
+                wd, bd = blk["down"]
+                cols = ops.im2col3x3(x.view(B * F, h, w, x.shape[1]), stride=2)
+                x = ops.gemm(cols, wd, bias=bd)
+                h, w = h // 2, w // 2
+                skips.append(x)
+        # 4. mid
+        m = pk["mid"]
+        x = self._resnet(m["res"][0], x, None, B, F, h, w, temb_all)
+        x = self._transformer(m["attn"], x, B, F, h, w, next(kvs), cond_frame)
+        x = self._transformer(m["tattn"], x, B, F, h, w, None, cond_frame)
+        x = self._resnet(m["res"][1], x, None, B, F, h, w, temb_all)
+        # 5. up
+        for i, blk in enumerate(pk["up"]):
+            for j, r in enumerate(blk["res"]):
+                x = self._resnet(r, x, skips.pop(), B, F, h, w, temb_all)
+                if blk["attn"]:
+                    x = self._transformer(blk["attn"][j], x, B, F, h, w, next(kvs), cond_frame)
+                    x = self._transformer(blk["tattn"][j], x, B, F, h, w, None, cond_frame)
+            if blk["up"] is not None:
+                wu, bu = blk["up"]
+                up = ops.upsample2x(x, B * F, h, w)
+                h, w = 2 * h, 2 * w
+                x = ops.conv3x3(up, wu, bias=bu)
+        # 6. out: GN -> SiLU -> conv_out, fp32, back to (B, C, F, H, W)
+        y = ops.groupnorm(x, None, B, pk["gno_g"], pk["gno_b"], cfg.norm_eps, True, out_dtype=torch.float32)
+        return ops.conv_out(y, pk["conv_out_w"], pk["conv_out_b"], B, F, h, w)

@@ -1,0 +1,151 @@
+"""Step- and loop-level parity (-m gpu): the CUDA SeerUNet / DDIMSampler against the oracle on identical seeded
+weights, inputs and noise, and against golden outputs of the unmodified reference.
+
+Tolerances are north_star's: per-step eps rel-L2 <= 2e-2 for the bf16 path, 31-evaluation DDIM final latents
+<= 5e-2 (BASELINE.json).  PyTorch's own bf16 autocast sits at 1.3e-2 on this network."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():  # pragma: no cover
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from oracle import seer_oracle as so  # noqa: E402  (checker only)
+from seervideoldm_b200 import DDIMSampler, SeerUNet, ops  # noqa: E402
+from seervideoldm_b200.config import sd15_config  # noqa: E402
+from seervideoldm_b200.pipeline import ddim_sample_latents  # noqa: E402
+from seervideoldm_b200.weights import random_state_dict  # noqa: E402
+
+STEP_TOL_BF16 = 2e-2
+LOOP_TOL = 5e-2
+
+
+def gen(seed, *shape):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.fixture(scope="module")
+def model():
+    cfg = sd15_config(sample_size=32)
+    sd = random_state_dict(cfg, seed=0)
+    net = SeerUNet(sample_size=32, cross_attention_dim=768)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    return net, sd
+
+
+@pytest.mark.parametrize("B,Fr,H,cf,tval", [(1, 2, 8, 0, 991), (2, 3, 16, 0, 496), (1, 4, 16, 2, 1), (2, 2, 32, 1, 750)])
+def test_step_vs_oracle(model, B, Fr, H, cf, tval):
+    net, sd = model
+    x, c = gen(11, B, 4, Fr, H, H), gen(12, B, Fr, 77, 768)
+    t = torch.full((B,), tval, dtype=torch.long)
+    ref = so.unet_forward(sd, x, t, c, cf)
+    out = net(x.cuda(), t.cuda(), c.cuda(), cond_frame=cf)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    err = so.rel_l2(out.cpu(), ref)
+    print(f"step rel-L2 B={B} F={Fr} H={H} cond_frame={cf}: {err:.3e}")
+    assert err < STEP_TOL_BF16
+
+
+def test_step_vs_reference_golden(model, golden_dir):
+    """Golden eps produced by the UNMODIFIED reference (oracle/make_golden.py) on the same seeded weights/inputs."""
+    net, _ = model
+    g = torch.load(os.path.join(golden_dir, "unet_sd15.pt"), weights_only=False)
+    for case in g["cases"]:
+        B, Fr, H = case["shape"]
+        x, c = gen(case["x_seed"], B, 4, Fr, H, H), gen(case["c_seed"], B, Fr, 77, 768)
+        out = net(x.cuda(), case["t"].cuda(), c.cuda(), cond_frame=case["cond_frame"])
+        assert so.rel_l2(out.cpu(), case["y"]) < STEP_TOL_BF16
+
+
+def test_api_variants(model):
+    net, _ = model
+    x, c = gen(21, 1, 4, 2, 8, 8).cuda(), gen(22, 1, 2, 77, 768).cuda()
+    a = net(x, torch.tensor([500], device="cuda"), c)
+    b = net(x, 500, encoder_hidden_states=c)                      # int timestep + diffusers kwarg alias
+    d = net(x, torch.tensor(500), context=c)                      # 0-d tensor
+    assert torch.equal(a, b) and torch.equal(a, d)
+    with pytest.raises(NotImplementedError):
+        net(x, 500, c, return_attn=True)
+    with pytest.raises(ValueError):
+        net(x, 500, c[:, :1])
+    assert len(net.state_dict()) == 1006
+    # regression: the text-K/V cache must not be fooled by the allocator recycling a freed context's address
+    c1 = gen(23, 1, 2, 77, 768).cuda()
+    net(x, 500, c1)
+    del c1
+    c2 = gen(24, 1, 2, 77, 768).cuda()
+    got = net(x, 500, c2)
+    net._kv_key = None
+    assert torch.equal(got, net(x, 500, c2))
+
+
+def test_batch_independence_bit_exact(model):
+    """Clips never interact: evaluating two clips together == evaluating each alone, bit for bit."""
+    net, _ = model
+    x, c = gen(31, 2, 4, 3, 16, 16).cuda(), gen(32, 2, 3, 77, 768).cuda()
+    t = torch.tensor([700, 700], device="cuda")
+    both = net(x, t, c)
+    for i in range(2):
+        one = net(x[i:i + 1].contiguous(), t[i:i + 1], c[i:i + 1].contiguous())
+        assert torch.equal(one[0], both[i])
+
+
+def test_ddim_loop_vs_oracle(model):
+    """31-evaluation DDIM + CFG 7.5 with 1 reference frame, identical x_T: final latents within 5e-2."""
+    net, sd = model
+    b, F1, F2, H = 1, 1, 3, 16
+    xT, x0 = gen(41, b, 4, F2, H, H), gen(42, b, 4, F1, H, H)
+    c = gen(43, b, F1 + F2, 77, 768)
+    uc = gen(44, b, 1, 77, 768).expand(-1, F1 + F2, -1, -1).contiguous()
+    evals = []
+
+    def unet_fn(x, t, cc, cond_frame):
+        evals.append(t.tolist())
+        return so.unet_forward(sd, x, t, cc, cond_frame)
+
+    ref, ref_inter = so.ddim_sample_latents(unet_fn, xT, c, x0, 30, 7.5, uc)
+    assert len(evals) == 31 and evals[0] == [991, 991] and evals[-1] == [1, 1]
+    sampler = DDIMSampler(torch.device("cuda"))
+    lat, inter = sampler.sample(unet=net, S=30, conditioning=c.cuda(), batch_size=b, shape=(4, F2, H, H), x0_emb=x0.cuda(),
+                                verbose=False, unconditional_guidance_scale=7.5, unconditional_conditioning=uc.cuda(), eta=0.0,
+                                x_T=xT.cuda(), is_3d=True)
+    err = so.rel_l2(lat.cpu(), ref)
+    print(f"31-step DDIM+CFG final-latent rel-L2: {err:.3e}; rms {float(ref.pow(2).mean().sqrt()):.2f}")
+    assert err < LOOP_TOL
+    assert len(inter["x_inter"]) == len(ref_inter["x_inter"]) and len(inter["pred_x0"]) == len(ref_inter["pred_x0"])
+    # CUDA-graph replay and eager evaluation are the same kernels in the same order: bit-identical
+    eager = DDIMSampler(torch.device("cuda"), use_cuda_graph=False)
+    lat2 = ddim_sample_latents(eager, net, (b, 4, F2, H, H), c.cuda(), xT.cuda(), x0.cuda(), ddim_steps=30, scale=7.5, uc=uc.cuda())
+    assert torch.equal(lat, lat2)
+
+
+def test_scale_one_skips_cfg(model):
+    net, sd = model
+    b, F2, H = 1, 2, 8
+    xT, c = gen(51, b, 4, F2, H, H), gen(52, b, F2, 77, 768)
+    sampler = DDIMSampler(torch.device("cuda"))
+    lat = ddim_sample_latents(sampler, net, (b, 4, F2, H, H), c.cuda(), xT.cuda(), None, ddim_steps=10, scale=1.0,
+                              uc=gen(53, b, F2, 77, 768).cuda())
+    ref, _ = so.ddim_sample_latents(lambda x, t, cc, cf: so.unet_forward(sd, x, t, cc, cf), xT, c, None, 10, 1.0, None)
+    assert so.rel_l2(lat.cpu(), ref) < LOOP_TOL
+
+
+@pytest.mark.slow
+def test_full_size_sthv2_step(model):
+    """BASELINE.json config 2 shape: UNet batch 2 (CFG), 12 frames, 32x32 latent, t = 991."""
+    net, sd = model
+    x, c = gen(61, 2, 4, 12, 32, 32), gen(62, 2, 12, 77, 768)
+    t = torch.full((2,), 991, dtype=torch.long)
+    ref = so.unet_forward(sd, x, t, c, 0)
+    out = net(x.cuda(), t.cuda(), c.cuda())
+    err = so.rel_l2(out.cpu(), ref)
+    print(f"full-size Sthv2 step rel-L2: {err:.3e}")
+    assert err < STEP_TOL_BF16
+    # size-independent property: eps of frame f in clip b is unchanged by permuting the CFG halves
+    out2 = net(x.flip(0).contiguous().cuda(), t.cuda(), c.flip(0).contiguous().cuda())
+    assert torch.equal(out2.flip(0), out)
