@@ -1,0 +1,127 @@
+"""CPU-side tests (-m "not gpu"): host logic, state-dict schema, sampler schedule vs golden, the C-ABI library's
+exports, and the rule that the product never imports the oracle."""
+import ast
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from seervideoldm_b200 import _lib, packing
+from seervideoldm_b200.config import UNetConfig, sd15_config
+from seervideoldm_b200.weights import random_state_dict, unet_schema
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_schema_known_answers():
+    """SURVEY §8c (3),(8): 1006 entries, 1,082,772,804 parameters, 16 rotary buffers of shape (16,)."""
+    s = unet_schema(sd15_config(sample_size=32))
+    assert len(s) == 1006
+    freqs = [k for k in s if k.endswith("rotary_emb.freqs")]
+    assert len(freqs) == 16 and all(s[k] == (16,) for k in freqs)
+    assert sum(int(np.prod(v)) for k, v in s.items() if k not in freqs) == 1_082_772_804
+    assert len([k for k in s if k.endswith("conv_shortcut.weight")]) == 14
+    assert len({k.rsplit(".resnets.", 1)[0] + k.rsplit(".resnets.", 1)[1][0] for k in s if ".resnets." in k}) == 22
+
+
+def test_random_state_dict_is_deterministic_and_loads():
+    from seervideoldm_b200.unet import SeerUNet
+    cfg = UNetConfig(sample_size=32, block_out_channels=(64, 128, 128, 128), cross_attention_dim=64)
+    a, b = random_state_dict(cfg, 3), random_state_dict(cfg, 3)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert not torch.equal(a["conv_in.weight"], random_state_dict(cfg, 4)["conv_in.weight"])
+    net = SeerUNet(sample_size=32, block_out_channels=(64, 128, 128, 128), cross_attention_dim=64)
+    assert list(net.state_dict().keys()) == list(a.keys())
+    net.load_state_dict(a, strict=True)
+    with pytest.raises(RuntimeError):
+        bad = dict(a); bad.pop("conv_in.bias")
+        net.load_state_dict(bad, strict=True)
+    # zero-init proj_out at construction, like the reference (attention.py:126-127)
+    fresh = SeerUNet(sample_size=32, block_out_channels=(64, 128, 128, 128), cross_attention_dim=64)
+    assert float(fresh.down_blocks[0].attentions[0].proj_out.weight.abs().max()) == 0.0
+    assert fresh.config.cross_attention_dim == 64 and fresh.config["layers_per_block"] == 2
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        fresh(torch.zeros(1, 4, 2, 8, 8), 3, torch.zeros(1, 2, 77, 64))
+
+
+def test_sampler_schedule_matches_reference_golden(golden_dir):
+    from seervideoldm_b200.ddim import DDIMSampler
+    for S in (30, 10):
+        g = torch.load(os.path.join(golden_dir, f"schedule_{S}.pt"), weights_only=False)
+        s = DDIMSampler("cpu")
+        s.make_schedule(S, verbose=False)
+        assert np.array_equal(s.ddim_timesteps, g["timesteps"].numpy())
+        assert torch.equal(s.ddim_alphas, g["alphas"])
+        assert np.array_equal(np.asarray(s.ddim_alphas_prev), g["alphas_prev"].numpy())
+        assert torch.equal(s.ddim_sqrt_one_minus_alphas, g["sqrt_one_minus_alphas"])
+        assert torch.equal(s.alphas_cumprod, g["alphas_cumprod_fp32"])
+        a, ap = g["alphas"], g["alphas_prev"].float()
+        assert torch.equal(s._coef[:, 0], torch.sqrt(1 - a)) and torch.equal(s._coef[:, 1], a.sqrt())
+        assert torch.equal(s._coef[:, 2], ap.sqrt()) and torch.equal(s._coef[:, 3], (1 - ap).sqrt())
+    assert len(DDIMSampler("cpu").__dict__) > 0
+
+
+def test_packing_layouts():
+    w = torch.arange(2 * 3 * 9, dtype=torch.float32).reshape(2, 3, 3, 3)
+    p = packing.pack_conv3x3(w).float()
+    for co in range(2):
+        for ci in range(3):
+            for ky in range(3):
+                for kx in range(3):
+                    assert p[co, (ky * 3 + kx) * 3 + ci] == w[co, ci, ky, kx]
+    perm = packing.geglu_permutation(128)
+    assert perm[:32].tolist() == list(range(32)) and perm[32:64].tolist() == list(range(128, 160))
+    assert perm[64:96].tolist() == list(range(32, 64)) and sorted(perm.tolist()) == list(range(256))
+    sc = torch.ones(2, 5, 1, 1)
+    assert packing.pack_conv3x3(w, sc).shape == (2, 27 + 5)
+    assert packing.pack_conv_out(torch.zeros(4, 8, 3, 3)).shape == (4, 9, 8)
+
+
+def test_shared_library_exports_every_declared_symbol():
+    """The C-ABI library loads without a GPU and exports exactly what include/seer_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "seer_b200.h")).read()
+    declared = set(re.findall(r"\b(seer_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.seer_b200_version().startswith(b"seer_b200")
+    assert lib.seer_b200_groupnorm_workspace_floats(2, 12288) == 2 * 384 * 32 * 2
+    # argument validation happens before any CUDA call: bad shapes are rejected with -1 even without a device
+    assert lib.seer_b200_gemm_bf16(None, 0, 0, None, 0, 0, None, 0, 0, None, 0, 0, None, 0, None, 0, 0, None) == -1
+
+
+def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under seervideoldm_b200/ may import it, and bench.py only inside the
+    cpu baseline / reference-arm function."""
+    pkg = os.path.join(ROOT, "seervideoldm_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            tree = ast.parse(open(os.path.join(pkg, fn)).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                assert not any(n.split(".")[0] == "oracle" for n in names), f"{fn} imports oracle"
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for fn in tree.body:
+        if isinstance(fn, ast.FunctionDef):
+            uses = any(isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle") for n in ast.walk(fn))
+            assert (not uses) or fn.name == "cpu_eval_fn", fn.name
+        else:
+            assert not (isinstance(fn, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(fn))
+
+
+def test_ops_fail_loudly_without_cuda():
+    from seervideoldm_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(ValueError, match="no CPU path"):
+        ops.gemm(torch.zeros(128, 64, dtype=torch.bfloat16), torch.zeros(64, 64, dtype=torch.bfloat16))
+    with pytest.raises(ValueError, match="no CPU path"):
+        ops.layernorm(torch.zeros(4, 320), torch.ones(320), torch.zeros(320))
