@@ -41,6 +41,42 @@ int seer_b200_gemm_bf16(const void* A, int lda, int K1, const void* A2, int lda2
                         const float* bias, int ldb, int bias_div, const float* residual, int ldr, void* out, int ldo,
                         int flags, void* stream);
 
+/* Full descriptor of one tcgen05 GEMM / implicit-GEMM conv launch (superset of the two entry points around it):
+ *
+ *   acc[M,N]  = [A | A2] * Wt^T                       A: plain A[M,K1] bf16, or (X != NULL) the 3x3/pad-1 im2col of
+ *                                                      X[n_img,H,W,Cin] bf16 (K1 = 9*Cin, K order [ky][kx][Cin])
+ *   v         = ln ? rstd_r * (acc - mean_r * ln_colsum[n]) : acc        (LayerNorm folded into the GEMM: Wt holds
+ *                                                      W*gamma, bias holds beta*W^T (+b); mean/rstd of row r come from
+ *                                                      row_stats_in = `row_parts_in` partial (sum, sumsq) pairs)
+ *   v        += bias[(r / bias_div), n] + residual[r, n]                 (residual fp32 or bf16)
+ *   geglu: v[:, j] = value * gelu_erf(gate)            (Wt / bias / ln_colsum rows packed value/gate in blocks of 32)
+ *   outputs   : out_f32 and/or out_bf16 (either may be NULL, not both), written through TMA stores;
+ *   col_stats : optional [ceil(M/32)][N][2] fp32 (sum, sumsq) of v per 32-row slab and column (feeds GroupNorm);
+ *   row_stats_out : optional [parts][M][2] fp32 partial (sum, sumsq) of v per row (feeds the next folded LayerNorm);
+ *                   parts = seer_b200_gemm_row_parts(desc).
+ * Requirements: K1, K2 % 64 == 0; N % 64 == 0 (geglu: % 128); lda/lda2/ldo_bf16 % 8 == 0; ldr/ldo_f32 % 4 == 0
+ * (ldr % 8 for a bf16 residual); all bases 16-byte aligned; conv: Cin % 64 == 0, W | 128, (128/W) | H or H | (128/W).
+ * col_stats needs out_f32. */
+typedef struct SeerGemmDesc {
+  const void* A; int lda; int K1;
+  const void* X; int n_img, H, W, Cin;
+  const void* A2; int lda2; int K2;
+  const void* Wt; int M, N;
+  const float* bias; int ldb; int bias_div;
+  const void* residual; int ldr; int residual_bf16;
+  void* out_f32; int ldo_f32;
+  void* out_bf16; int ldo_bf16;
+  int geglu;
+  float* col_stats;
+  float* row_stats_out;
+  const float* row_stats_in; int row_parts_in; float ln_eps; const float* ln_colsum;
+} SeerGemmDesc;
+int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream);
+/* sizeof(SeerGemmDesc) as compiled into the library (binding sanity check) */
+int seer_b200_gemm_desc_size(void);
+/* number of per-row partial (sum, sumsq) pairs seer_b200_gemm_ex writes to row_stats_out for this descriptor (<= 0: error) */
+int seer_b200_gemm_row_parts(const SeerGemmDesc* desc);
+
 /* Frame-wise 3x3 conv, stride 1, pad 1, as implicit GEMM over 9 shifted TMA boxes of X[n_img,H,W,Cin] (bf16),
  * optional fused 1x1 tail A2[M,K2] (ResNet shortcut).  Wt[Cout, 9*Cin + K2] with K order [ky][kx][Cin] then tail.
  * Replaces InflatedConv3d(k=3): seer/models/resnet.py:8-16,147,155 and Upsample3D's conv :39.
@@ -57,6 +93,13 @@ int seer_b200_groupnorm_workspace_floats(int B, int T);
 int seer_b200_groupnorm(const float* x1, int C1, const float* x2, int C2, int B, int T, const float* gamma, const float* beta,
                         float eps, int silu, float* workspace, float* scale_shift, void* y, int y_is_f32, void* raw_bf16,
                         void* stream);
+
+/* Same GroupNorm, but the statistics come from the per-(32-row slab, channel) partial sums a seer_b200_gemm_ex launch
+ * emitted while producing x1 / x2 (SeerGemmDesc::col_stats, [B*T/32][Ci][2]): no statistics pass over the activation.
+ * Requires T % 32 == 0. */
+int seer_b200_groupnorm_from_stats(const float* x1, int C1, const float* stats1, const float* x2, int C2, const float* stats2,
+                                   int B, int T, const float* gamma, const float* beta, float eps, int silu, float* scale_shift,
+                                   void* y, int y_is_f32, void* raw_bf16, void* stream);
 
 /* LayerNorm over the last dim (fp32 in, bf16 out).  Replaces nn.LayerNorm: attention.py:198-200,237,244,311,322-323. */
 int seer_b200_layernorm(const float* x, int M, int C, int ldx, const float* gamma, const float* beta, float eps, void* y_bf16,

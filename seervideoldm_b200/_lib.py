@@ -17,8 +17,34 @@ _c = ctypes
 _vp, _i, _f, _ll = _c.c_void_p, _c.c_int, _c.c_float, _c.c_longlong
 _ip = _c.POINTER(_c.c_int)
 
+
+
+class GemmDesc(ctypes.Structure):
+    """Mirror of `SeerGemmDesc` (include/seer_b200.h) — field order and types must match the C struct."""
+    _fields_ = [
+        ("A", _vp), ("lda", _i), ("K1", _i),
+        ("X", _vp), ("n_img", _i), ("H", _i), ("W", _i), ("Cin", _i),
+        ("A2", _vp), ("lda2", _i), ("K2", _i),
+        ("Wt", _vp), ("M", _i), ("N", _i),
+        ("bias", _vp), ("ldb", _i), ("bias_div", _i),
+        ("residual", _vp), ("ldr", _i), ("residual_bf16", _i),
+        ("out_f32", _vp), ("ldo_f32", _i),
+        ("out_bf16", _vp), ("ldo_bf16", _i),
+        ("geglu", _i),
+        ("col_stats", _vp),
+        ("row_stats_out", _vp),
+        ("row_stats_in", _vp), ("row_parts_in", _i), ("ln_eps", _f), ("ln_colsum", _vp),
+    ]
+
+
+_dp = _c.POINTER(GemmDesc)
+
 # name -> (restype, argtypes): must list every symbol include/seer_b200.h declares
 SIGNATURES = {
+    "seer_b200_gemm_ex": (_i, [_dp, _vp]),
+    "seer_b200_gemm_row_parts": (_i, [_dp]),
+    "seer_b200_gemm_desc_size": (_i, []),
+    "seer_b200_groupnorm_from_stats": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _i, _vp, _vp]),
     "seer_b200_version": (_c.c_char_p, []),
     "seer_b200_gemm_bf16": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "seer_b200_conv3x3_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
@@ -68,6 +94,8 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)       # AttributeError if the symbol is missing: fail loudly
             fn.restype = res
             fn.argtypes = args
+        if handle.seer_b200_gemm_desc_size() != ctypes.sizeof(GemmDesc):
+            raise SeerB200Error("SeerGemmDesc layout mismatch between libseer_b200.so and _lib.GemmDesc — rebuild the library")
         _lib = handle
     return _lib
 

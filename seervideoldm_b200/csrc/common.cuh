@@ -53,6 +53,22 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-erf GELU for hot epilogues: Phi(x) through Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the
+// bf16 rounding of the result) = 2 MUFU (rcp, ex2) + ~12 FMA-pipe ops instead of erff()'s branchy ~35.
+// With w = |x| sqrt(log2(e)/2):  erfc(|x|/sqrt2) = poly(t) 2^(-w^2),  t = 1/(1 + p |x|/sqrt2).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float w = fabsf(x) * 0.84932180028801904272f;            // sqrt(log2(e) / 2)
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(w, 0.2727374808792225f, 1.0f)));   // p / sqrt(log2 e)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-w * w));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(t, poly, 0.5f * 1.421413741f);
+  poly = fmaf(t, poly, 0.5f * -0.284496736f);
+  poly = fmaf(t, poly, 0.5f * 0.254829592f);
+  const float h = poly * t * e;                                  // 0.5 erfc(|x| / sqrt 2) = Phi(-|x|)
+  const float phi = x >= 0.f ? 1.0f - h : h;
+  return x * phi;
+}
 
 // ---- mbarrier --------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -108,6 +124,23 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* tm, u
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+
+// TMA store smem -> global (bulk async-group completion).  Generic-proxy writes to the smem source must be
+// followed by fence_proxy_async_smem() in the writing threads and a barrier before the issuing thread calls this.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still have to READ their smem source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// wait until all of this thread's bulk groups have fully completed (writes performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- tcgen05 / TMEM --------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_smem, uint32_t ncols) {  // whole warp

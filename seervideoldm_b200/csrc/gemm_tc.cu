@@ -1,94 +1,119 @@
-// tcgen05 / TMEM / TMA tile GEMM for sm_100a — the contraction engine behind every Linear, 1x1 conv and
-// (as an implicit GEMM with shifted 4-D TMA boxes) every frame-wise 3x3 conv of the Seer UNet.
+// tcgen05 / TMEM / TMA persistent tile GEMM for sm_100a (v2) — the contraction engine behind every Linear, 1x1 conv
+// and (as an implicit GEMM with shifted 4-D TMA boxes) every frame-wise 3x3 conv of the Seer UNet.
 //
-//   out[M, N] = epilogue( A[M, K] * Wt[N, K]^T )          A, Wt bf16 K-major, fp32 accumulate in TMEM
+//   acc[M, N] = A[M, K] * Wt[N, K]^T          A, Wt bf16 K-major, fp32 accumulation in TMEM
+//   out       = epilogue(acc)                  LN-fold / bias / residual / GEGLU / fp32 + bf16 outputs / norm statistics
 //
 // Replaces (on B200) the cuBLAS / cuDNN calls behind nn.Linear and InflatedConv3d in the reference:
 //   /root/reference/seer/models/resnet.py:8-16 (InflatedConv3d), attention.py:484-489 (to_q/k/v/out),
-//   attention.py:781-793 (GEGLU proj), attention.py:742 (FF out).
+//   attention.py:781-793 (GEGLU proj), attention.py:742 (FF out); and absorbs the statistics passes of
+//   nn.GroupNorm (resnet.py:179,197) and nn.LayerNorm (attention.py:198-200) into the producing / consuming GEMM.
 //
-// Tile: 128 (M) x BN (N) x 64 (K) per pipeline stage, SWIZZLE_128B operand tiles written by TMA and read by
-// tcgen05.mma through shared-memory descriptors.  Warp roles: warp 0 = TMA producer (one elected lane),
-// warp 1 = TMEM allocator + MMA issuer (one lane), warps 2..5 = epilogue (one TMEM lane quarter each).
-// Two CTAs are co-resident per SM (<= 110 KB smem, <= 256 TMEM columns each) so one CTA's epilogue overlaps
-// the other's main loop.
+// Structure (one persistent CTA per SM, static round-robin over 128 x BN output tiles, n fastest so the CTAs that
+// share an A row-block run at the same time and A is read from HBM once):
+//   warp 0      TMA producer: A (2-D box, or 9 shifted 4-D boxes for the 3x3 conv; OOB zero fill = padding) and
+//               Wt tiles into a `stages`-deep SWIZZLE_128B smem ring, mbarrier full/empty.
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one lane): 128 x BN x 16 UMMAs into one of TWO TMEM
+//               accumulator buffers, so the epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 2..   epilogue warps (4 or 8).  Each owns one TMEM lane quarter (32 rows) and a private ring of smem
+//               slots: the fp32/bf16 residual chunk (32 rows x 32 cols) is PREFETCHED into the slot by TMA one or
+//               two chunks ahead, the warp adds accumulator + bias in place (thread = row, 128B/64B-swizzled so the
+//               16-byte accesses are bank-conflict free) and a TMA store writes the slot back with full-line
+//               transactions.  No epilogue global load/store is issued by the LSU except the bias vector.
 //
-// A-operand sources (K-blocks are consumed in this order):
-//   mode 0: 2-D row-major A[M, K1]                              (Linear / 1x1 conv)
-//   mode 1: 4-D activation X[n_img, H, W, Cin] read as 9 shifted boxes (tap-major K = 9*Cin), zero padding
-//           comes from TMA out-of-bounds fill                     (3x3 conv, stride 1, pad 1)
-//   tail  : optional second 2-D source A2[M, K2] appended to K   (fused ResNet 1x1 shortcut / skip concat)
-//
-// Epilogue: + bias[(row / bias_div), col]  (+ fp32 residual[row, col]) -> fp32 or bf16;  or GEGLU:
-// value/gate column blocks of 32 are interleaved in Wt so out[:, j] = (a + ba) * gelu_erf(g + bg) -> bf16.
+// Epilogue options (all warp-uniform runtime branches): see SeerGemmDesc in include/seer_b200.h.
 #include "common.cuh"
 #include "seer_b200.h"
 
-namespace seer {
+#include <stdlib.h>
 
-struct GemmParams {
-  int M, N;
-  int mode;        // 0 plain, 1 conv3x3
-  int kb_main;     // k-blocks (of 64) from the main source
-  int kb_total;    // + k-blocks from the tail source
-  int cblk;        // conv: Cin / 64
-  int H, W;        // conv image geometry
-  const float* bias;
-  int ldb;         // bias row stride (elements)
-  int bias_div;    // rows per bias row (>= M for a plain bias vector)
-  const float* residual;
-  int ldr;
-  void* out;
-  int ldo;
-  int out_bf16;
-  int geglu;
-};
+namespace seer {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_EPI_WARPS = 8;
+constexpr int MAX_RING = 4;
+constexpr int GEMM_MAX_THREADS = 64 + 32 * MAX_EPI_WARPS;
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int BAR_BYTES = 1024;
 
-template <int BN>
-struct GemmSmem {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN <= 128) ? 3 : (BN <= 160 ? 3 : 4);
-  static constexpr int CTAS_PER_SM = (BN <= 160) ? 2 : 1;
-  static constexpr int TMEM_COLS = (BN <= 128) ? 128 : 256;
-  static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+struct GemmParams {
+  int M, N;            // N = accumulator columns (GEGLU: twice the output columns)
+  int mode;            // 0 plain, 1 conv3x3
+  int kb_main;         // k-blocks (of 64) from the main source
+  int kb_total;        // + k-blocks from the tail source
+  int cblk;            // conv: Cin / 64
+  int H, W;            // conv image geometry
+  int tiles_n, num_tiles;
+  int stages, nepi, ring, slot_bytes;
+  int res_off, outf_off, outh_off;   // byte offsets of the residual / fp32-out / bf16-out regions inside a slot
+  const float* bias;
+  int ldb;
+  int bias_div;
+  int res_mode;        // 0 none, 1 fp32, 2 bf16
+  int out_f32, out_bf16;
+  int geglu;
+  float* col_stats;
+  float* row_stats_out;
+  const float* row_stats_in;
+  int row_parts_in;
+  float ln_inv_dim, ln_eps;
+  const float* ln_colsum;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, GemmSmem<BN>::CTAS_PER_SM)
+struct GemmCfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TBUF = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // TMEM column stride between the 2 buffers
+  static constexpr int TMEM_COLS = 2 * TBUF;
+};
+
+// byte offset of 16-byte chunk `j` of row `r` inside a TMA-swizzled box whose rows are 128 B / 64 B wide
+__device__ __forceinline__ int sw128(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
+__device__ __forceinline__ int sw64(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_MAX_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using S = GemmSmem<BN>;
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmRes,
+               const __grid_constant__ CUtensorMap tmOutF, const __grid_constant__ CUtensorMap tmOutH, const GemmParams p) {
+  using C = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + S::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + S::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint8_t* ring_base = smem + p.stages * C::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring_base + p.nepi * p.ring * p.slot_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
+  uint64_t* res_full_bar = tmem_empty_bar + 2;          // [MAX_EPI_WARPS][MAX_RING]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full_bar + MAX_EPI_WARPS * MAX_RING);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.kb_total > p.kb_main) tma_prefetch_desc(&tmA2);
-    for (int s = 0; s < S::STAGES; ++s) {
+    if (p.res_mode) tma_prefetch_desc(&tmRes);
+    if (p.out_f32) tma_prefetch_desc(&tmOutF);
+    if (p.out_bf16) tma_prefetch_desc(&tmOutH);
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], p.nepi);
+    }
+    for (int i = 0; i < MAX_EPI_WARPS * MAX_RING; ++i) mbar_init(&res_full_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, S::TMEM_COLS);
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -99,155 +124,291 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int img0 = 0, y0 = 0;
-      if (p.mode == 1) {
-        const int hw = p.H * p.W;
-        img0 = m0 / hw;
-        y0 = (m0 % hw) / p.W;
-      }
-      for (int kb = 0; kb < p.kb_total; ++kb) {
-        const int s = kb % S::STAGES;
-        const uint32_t ph = (kb / S::STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sA = smem + s * S::STAGE_BYTES;
-        uint8_t* sB = sA + S::A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        if (kb < p.kb_main) {
-          if (p.mode == 0) {
-            tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m0);
-          } else {
-            const int tap = kb / p.cblk;
-            const int c0 = (kb - tap * p.cblk) * BK;
-            const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(sA, &tmA, &full_bar[s], c0, kx - 1, y0 + ky - 1, img0);
-          }
-        } else {
-          tma_load_2d(sA, &tmA2, &full_bar[s], (kb - p.kb_main) * BK, m0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int mb = tile / p.tiles_n, nb = tile - mb * p.tiles_n;
+        const int m0 = mb * BM, n0 = nb * BN;
+        int img0 = 0, y0 = 0;
+        if (p.mode == 1) {
+          const int hw = p.H * p.W;
+          img0 = m0 / hw;
+          y0 = (m0 % hw) / p.W;
         }
-        tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sA = smem + s * C::STAGE_BYTES;
+          uint8_t* sB = sA + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          if (kb < p.kb_main) {
+            if (p.mode == 0) {
+              tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m0);
+            } else {
+              const int tap = kb / p.cblk;
+              const int c0 = (kb - tap * p.cblk) * BK;
+              const int ky = tap / 3, kx = tap - ky * 3;
+              tma_load_4d(sA, &tmA, &full_bar[s], c0, kx - 1, y0 + ky - 1, img0);
+            }
+          } else {
+            tma_load_2d(sA, &tmA2, &full_bar[s], (kb - p.kb_main) * BK, m0);
+          }
+          tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      for (int kb = 0; kb < p.kb_total; ++kb) {
-        const int s = kb % S::STAGES;
-        const uint32_t ph = (kb / S::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tmem_empty_bar[buf], (((uint32_t)it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + S::A_BYTES;
-        const uint64_t a_desc = umma_desc_sw128(a_addr);
-        const uint64_t b_desc = umma_desc_sw128(b_addr);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * C::TBUF);
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint64_t a_desc = umma_desc_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_sw128(a_addr + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[s]);   // frees this smem stage once the MMAs above have read it
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+        umma_commit(&tmem_full_bar[buf]);   // accumulator complete
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
     }
     __syncwarp();
-  } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int brow = row_ok ? (row / p.bias_div) : 0;
-    const float* bias_row = p.bias ? p.bias + (size_t)brow * p.ldb : nullptr;
+  } else if (warp < 2 + p.nepi) {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int nhalf = p.nepi >> 2;           // 1 or 2 warps per quarter; they interleave the column chunks
+    const int half = ew >> 2;
+    const int cw = p.geglu ? 64 : 32;        // accumulator columns per chunk (always 32 output columns)
+    const int nch = BN / cw;
+    const int my_nch = (nch - half + nhalf - 1) / nhalf;
+    const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = my_tiles * my_nch;
+    const int R = p.ring, P = p.ring - 2;
+    uint8_t* ring = ring_base + (size_t)ew * R * p.slot_bytes;
+    uint64_t* rfull = res_full_bar + ew * MAX_RING;
+    const uint32_t res_bytes = p.res_mode == 1 ? 4096u : 2048u;
 
-    if (!p.geglu) {
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr_row + c, v);
-        tmem_ld_wait();
-        if (row_ok) {
-          const int col0 = n0 + c;
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (bias_row) {
-            const float4* b4 = reinterpret_cast<const float4*>(bias_row + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 b = __ldg(b4 + j);
-              f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+    auto issue_res = [&](int step) {         // lane 0: TMA-prefetch the residual chunk of a future step
+      const int it2 = step / my_nch, j2 = step - it2 * my_nch;
+      const int tile2 = blockIdx.x + it2 * gridDim.x;
+      const int mb2 = tile2 / p.tiles_n, nb2 = tile2 - mb2 * p.tiles_n;
+      const int s2 = step % R;
+      mbar_arrive_expect_tx(&rfull[s2], res_bytes);
+      tma_load_2d(ring + s2 * p.slot_bytes + p.res_off, &tmRes, &rfull[s2], nb2 * BN + (half + j2 * nhalf) * 32,
+                  mb2 * BM + q * 32);
+    };
+    if (p.res_mode && lane == 0)
+      for (int st = 0; st < P && st < total; ++st) issue_res(st);
+
+    const bool want_stats = p.col_stats != nullptr || p.row_stats_out != nullptr;
+    int g = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int mb = tile / p.tiles_n, nb = tile - mb * p.tiles_n;
+      const int m0 = mb * BM, n0 = nb * BN;
+      const int buf = it & 1;
+      const int row0 = m0 + q * 32;
+      const int row = row0 + lane;
+      const bool row_ok = row < p.M;
+      const float* bias_row = p.bias ? p.bias + (size_t)(row_ok ? row / p.bias_div : 0) * p.ldb : nullptr;
+      float mean = 0.f, rstd = 1.f;
+      if (p.row_stats_in && row_ok) {        // folded LayerNorm: combine the producer's per-row partial sums
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < p.row_parts_in; ++i) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(p.row_stats_in) + (size_t)i * p.M + row);
+          s1 += t.x;
+          s2 += t.y;
+        }
+        mean = s1 * p.ln_inv_dim;
+        rstd = rsqrtf(fmaxf(s2 * p.ln_inv_dim - mean * mean, 0.f) + p.ln_eps);
+      }
+      const float nmr = -mean * rstd;
+      float rs = 0.f, rq = 0.f;
+
+      for (int j = 0; j < my_nch; ++j, ++g) {
+        const int c = half + j * nhalf;
+        const int s = g % R;
+        uint8_t* slot = ring + s * p.slot_bytes;
+        if (lane == 0) {
+          bulk_wait_read<1>();               // the store that last used slot (g+P)%R (and (g-R)%R) has read its smem
+          if (p.res_mode && g + P < total) issue_res(g + P);
+        }
+        __syncwarp();
+        if (j == 0) {
+          mbar_wait(&tmem_full_bar[buf], ((uint32_t)it >> 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * C::TBUF + c * cw);
+        float f[32];
+        {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr, v);
+          if (!p.geglu) {
+            tmem_ld_wait();
+            if (j == my_nch - 1) {           // last TMEM read of this tile by this warp: hand the buffer back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
             }
-          }
-          if (p.residual) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ldr + col0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 r = r4[j];
-              f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+            for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
+            const int col0 = n0 + c * 32;
+            if (p.row_stats_in) {
+              const float4* s4 = reinterpret_cast<const float4*>(p.ln_colsum + col0);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float4 t = __ldg(s4 + k);
+                f[4 * k] = fmaf(f[4 * k], rstd, nmr * t.x);
+                f[4 * k + 1] = fmaf(f[4 * k + 1], rstd, nmr * t.y);
+                f[4 * k + 2] = fmaf(f[4 * k + 2], rstd, nmr * t.z);
+                f[4 * k + 3] = fmaf(f[4 * k + 3], rstd, nmr * t.w);
+              }
             }
-          }
-          if (p.out_bf16) {
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0);
+            if (bias_row) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias_row + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16(f[8 * j], f[8 * j + 1]);
-              o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-              o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
-              o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
-              o4[j] = o;
+              for (int k = 0; k < 8; ++k) {
+                const float4 t = __ldg(b4 + k);
+                f[4 * k] += t.x; f[4 * k + 1] += t.y; f[4 * k + 2] += t.z; f[4 * k + 3] += t.w;
+              }
             }
           } else {
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0);
+            uint32_t vg[32];
+            tmem_ld_32x32(taddr + 32, vg);
+            tmem_ld_wait();
+            if (j == my_nch - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+            }
+            // GEGLU: accumulator columns [c*64, +32) are "value", [c*64+32, +64) the matching "gate"
+            const int col0 = n0 + c * 64;
+            const float4* ba = reinterpret_cast<const float4*>(bias_row + col0);
+            const float4* bg = reinterpret_cast<const float4*>(bias_row + col0 + 32);
+            const float4* sa = reinterpret_cast<const float4*>(p.ln_colsum + col0);
+            const float4* sg = reinterpret_cast<const float4*>(p.ln_colsum + col0 + 32);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int k = 0; k < 8; ++k) {
+              float a[4] = {__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
+                            __uint_as_float(v[4 * k + 3])};
+              float gt[4] = {__uint_as_float(vg[4 * k]), __uint_as_float(vg[4 * k + 1]), __uint_as_float(vg[4 * k + 2]),
+                             __uint_as_float(vg[4 * k + 3])};
+              if (p.row_stats_in) {
+                const float4 t1 = __ldg(sa + k), t2 = __ldg(sg + k);
+                a[0] = fmaf(a[0], rstd, nmr * t1.x); a[1] = fmaf(a[1], rstd, nmr * t1.y);
+                a[2] = fmaf(a[2], rstd, nmr * t1.z); a[3] = fmaf(a[3], rstd, nmr * t1.w);
+                gt[0] = fmaf(gt[0], rstd, nmr * t2.x); gt[1] = fmaf(gt[1], rstd, nmr * t2.y);
+                gt[2] = fmaf(gt[2], rstd, nmr * t2.z); gt[3] = fmaf(gt[3], rstd, nmr * t2.w);
+              }
+              const float4 b1 = __ldg(ba + k), b2 = __ldg(bg + k);
+              f[4 * k] = (a[0] + b1.x) * gelu_erf_fast(gt[0] + b2.x);
+              f[4 * k + 1] = (a[1] + b1.y) * gelu_erf_fast(gt[1] + b2.y);
+              f[4 * k + 2] = (a[2] + b1.z) * gelu_erf_fast(gt[2] + b2.z);
+              f[4 * k + 3] = (a[3] + b1.w) * gelu_erf_fast(gt[3] + b2.w);
+            }
           }
         }
-      }
-    } else {
-      // GEGLU: columns [c, c+32) are "value", [c+32, c+64) the matching "gate" (weights packed that way).
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 64) {
-        uint32_t va[32], vg[32];
-        tmem_ld_32x32(taddr_row + c, va);
-        tmem_ld_32x32(taddr_row + c + 32, vg);
-        tmem_ld_wait();
-        if (row_ok) {
-          const int col0 = n0 + c;
-          float o[32];
+        // ---- residual (prefetched into the slot by TMA) ----
+        if (p.res_mode) {
+          mbar_wait(&rfull[s], ((uint32_t)(g / R)) & 1);
+          const uint8_t* rsrc = slot + p.res_off;
+          if (p.res_mode == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(va[j]) + __ldg(bias_row + col0 + j);
-            float g = __uint_as_float(vg[j]) + __ldg(bias_row + col0 + 32 + j);
-            o[j] = a * gelu_erf_f(g);
-          }
-          uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + (col0 >> 1));
+            for (int k = 0; k < 8; ++k) {
+              const float4 t = *reinterpret_cast<const float4*>(rsrc + sw128(lane, k));
+              f[4 * k] += t.x; f[4 * k + 1] += t.y; f[4 * k + 2] += t.z; f[4 * k + 3] += t.w;
+            }
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            u.x = pack_bf16(o[8 * j], o[8 * j + 1]);
-            u.y = pack_bf16(o[8 * j + 2], o[8 * j + 3]);
-            u.z = pack_bf16(o[8 * j + 4], o[8 * j + 5]);
-            u.w = pack_bf16(o[8 * j + 6], o[8 * j + 7]);
-            o4[j] = u;
+            for (int k = 0; k < 4; ++k) {
+              const uint4 t = *reinterpret_cast<const uint4*>(rsrc + sw64(lane, k));
+              const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), cc = unpack_bf16(t.z), d = unpack_bf16(t.w);
+              f[8 * k] += a.x; f[8 * k + 1] += a.y; f[8 * k + 2] += b.x; f[8 * k + 3] += b.y;
+              f[8 * k + 4] += cc.x; f[8 * k + 5] += cc.y; f[8 * k + 6] += d.x; f[8 * k + 7] += d.y;
+            }
           }
         }
+        if (want_stats) {
+          if (!row_ok) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) f[k] = 0.f;
+          }
+          if (p.row_stats_out) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) { rs += f[k]; rq = fmaf(f[k], f[k], rq); }
+          }
+        }
+        // ---- stage the outputs in the slot (thread = row, swizzled 16-byte chunks) and TMA-store them ----
+        if (p.out_f32) {
+          uint8_t* dst = slot + p.outf_off;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(dst + sw128(lane, k)) = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+        }
+        if (p.out_bf16) {
+          uint8_t* dst = slot + p.outh_off;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 o;
+            o.x = pack_bf16(f[8 * k], f[8 * k + 1]);
+            o.y = pack_bf16(f[8 * k + 2], f[8 * k + 3]);
+            o.z = pack_bf16(f[8 * k + 4], f[8 * k + 5]);
+            o.w = pack_bf16(f[8 * k + 6], f[8 * k + 7]);
+            *reinterpret_cast<uint4*>(dst + sw64(lane, k)) = o;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        const int ocol = (p.geglu ? (n0 >> 1) : n0) + c * 32;
+        if (lane == 0) {
+          if (p.out_f32) tma_store_2d(&tmOutF, slot + p.outf_off, ocol, row0);
+          if (p.out_bf16) tma_store_2d(&tmOutH, slot + p.outh_off, ocol, row0);
+          bulk_commit();
+        }
+        if (p.col_stats) {
+          // lane = column: (sum, sumsq) over this warp's 32 rows, read back from the staged fp32 tile
+          const uint8_t* src = slot + p.outf_off + (lane & 3) * 4;
+          float cs = 0.f, cq = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const float t = *reinterpret_cast<const float*>(src + sw128(r, lane >> 2));
+            cs += t;
+            cq = fmaf(t, t, cq);
+          }
+          if (row0 < p.M)
+            reinterpret_cast<float2*>(p.col_stats)[(size_t)(mb * 4 + q) * p.N + ocol + lane] = make_float2(cs, cq);
+        }
       }
+      if (p.row_stats_out && row_ok)
+        reinterpret_cast<float2*>(p.row_stats_out)[(size_t)(nb * nhalf + half) * p.M + row] = make_float2(rs, rq);
     }
+    if (lane == 0) bulk_wait_all();          // smem must outlive the last TMA stores
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, S::TMEM_COLS);
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// host side: tensor maps + launch
+// host side: tensor maps, launch plan
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -267,23 +428,26 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] (cols contiguous), box = {64 cols, box_rows}, 128 B swizzle.
-static int make_map_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+// 2-D row-major [rows, cols] (cols contiguous, leading dim ld elements), box = {box_cols, box_rows}.
+static int make_map_2d(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, uint64_t rows, uint64_t cols,
+                       uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle sw) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return SEER_ENODRIVER;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld_elems * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {ld_elems * (uint64_t)esize};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    fprintf(stderr, "[seer_b200] cuTensorMapEncodeTiled(2d) failed: %d (rows=%llu cols=%llu ld=%llu box_rows=%u)\n", (int)r,
-            (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows);
+    fprintf(stderr, "[seer_b200] cuTensorMapEncodeTiled(2d) failed: %d (rows=%llu cols=%llu ld=%llu box=%ux%u esize=%d)\n", (int)r,
+            (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_cols, box_rows, esize);
     return SEER_EINVAL;
   }
   return SEER_OK;
+}
+static int make_map_bf16_k64(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  return make_map_2d(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld, 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // 4-D bf16 activation [n_img, H, W, C] (C contiguous), box = {64, bw, bh, bn}.
@@ -305,49 +469,126 @@ static int make_map_4d(CUtensorMap* tm, const void* base, uint64_t n_img, uint64
   return SEER_OK;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+struct Plan {
+  int bn, stages, nepi, ring, slot_bytes, res_off, outf_off, outh_off, tiles_n, num_tiles, grid, smem_bytes;
+};
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+static int make_plan(const SeerGemmDesc& d, Plan& pl) {
+  const int N = d.N;
+  const int tiles_m = ceil_div(d.M, BM);
+  const int nsm = num_sms();
+  // tile width: the widest BN that divides N, unless a narrower one fills the SMs with fewer rounds of tiles
+  static const int cand_plain[] = {256, 192, 160, 128, 64};
+  static const int cand_geglu[] = {256, 128};
+  const int* cand = d.geglu ? cand_geglu : cand_plain;
+  const int ncand = d.geglu ? 2 : 5;
+  int best = 0;
+  double best_cost = 1e30;
+  const int forced = env_int("SEER_GEMM_BN", 0);   // tuning hook
+  for (int i = 0; i < ncand; ++i) {
+    const int bn = cand[i];
+    if (N % bn) continue;
+    if (forced && bn != forced) continue;
+    const long tiles = (long)tiles_m * (N / bn);
+    const long rounds = (tiles + nsm - 1) / nsm;
+    const double cost = (double)rounds * (bn + 24);     // per-tile time ~ BN + fixed overhead (in column units)
+    if (cost < best_cost * 0.999) { best_cost = cost; best = bn; }
+  }
+  if (!best) {
+    for (int i = 0; i < ncand && !best; ++i)
+      if (N % cand[i] == 0) best = cand[i];
+    if (!best) return SEER_EUNSUPPORTED;
+  }
+  pl.bn = best;
+  pl.tiles_n = N / best;
+  pl.num_tiles = tiles_m * pl.tiles_n;
+  pl.grid = pl.num_tiles < nsm ? pl.num_tiles : nsm;
+  // slot layout
+  const bool of = d.out_f32 != nullptr, oh = d.out_bf16 != nullptr;
+  const int rm = d.residual ? (d.residual_bf16 ? 2 : 1) : 0;
+  pl.res_off = 0; pl.outf_off = 0; pl.outh_off = 0;
+  int extent;
+  if (rm == 1) {            // fp32 residual at 0 (fp32 output in place), bf16 output behind it
+    pl.outh_off = 4096;
+    extent = oh ? 6144 : 4096;
+  } else if (rm == 2) {
+    if (of) { pl.res_off = 4096; pl.outh_off = 4096; extent = 6144; }
+    else { extent = 2048; }
+  } else {
+    pl.outh_off = of ? 4096 : 0;
+    extent = of ? (oh ? 6144 : 4096) : 2048;
+  }
+  pl.slot_bytes = extent;
+  pl.nepi = env_int("SEER_GEMM_NEPI", d.geglu ? 8 : 4);
+  if (pl.nepi != 4 && pl.nepi != 8) pl.nepi = 4;
+  if (best / (d.geglu ? 64 : 32) < 2) pl.nepi = 4;   // every epilogue warp needs at least one chunk
+  const int stage_bytes = A_BYTES + best * BK * 2;
+  const int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - BAR_BYTES;
+  pl.ring = 4;
+  pl.stages = (avail - pl.nepi * pl.ring * pl.slot_bytes) / stage_bytes;
+  if (pl.stages < 4) {
+    pl.ring = 3;
+    pl.stages = (avail - pl.nepi * pl.ring * pl.slot_bytes) / stage_bytes;
+  }
+  if (pl.stages < 3 && pl.nepi == 8) {
+    pl.nepi = 4; pl.ring = 4;
+    pl.stages = (avail - pl.nepi * pl.ring * pl.slot_bytes) / stage_bytes;
+  }
+  if (pl.stages < 2) return SEER_EUNSUPPORTED;
+  if (pl.stages > 6) pl.stages = 6;
+  const int fs = env_int("SEER_GEMM_STAGES", 0);
+  if (fs >= 2 && fs <= pl.stages) pl.stages = fs;
+  pl.smem_bytes = pl.stages * stage_bytes + pl.nepi * pl.ring * pl.slot_bytes + BAR_BYTES + 1024;
+  // > half of the SM's shared memory, so two CTAs (2 x TMEM_COLS could exceed 512 columns) never share an SM
+  if (pl.smem_bytes < 120 * 1024) pl.smem_bytes = 120 * 1024;
+  return SEER_OK;
+}
+
 template <int BN>
-static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const GemmParams& p,
-                       cudaStream_t stream) {
-  using S = GemmSmem<BN>;
+static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, const Plan& pl, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  dim3 grid(p.N / BN, ceil_div(p.M, BM));
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, S::BYTES, stream>>>(tA, tA2, tB, p);
+  gemm_tc_kernel<BN><<<pl.grid, 64 + 32 * pl.nepi, pl.smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
 
-static int pick_bn(int N, int geglu) {
-  if (geglu) return (N % 128 == 0) ? 128 : 0;
-  if (N % 160 == 0) return 160;
-  if (N % 128 == 0) return 128;
-  if (N % 64 == 0) return 64;
-  return 0;
-}
-
-static int dispatch(int bn, const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const GemmParams& p,
-                    cudaStream_t stream) {
-  switch (bn) {
-    case 64: return launch_gemm<64>(tA, tA2, tB, p, stream);
-    case 128: return launch_gemm<128>(tA, tA2, tB, p, stream);
-    case 160: return launch_gemm<160>(tA, tA2, tB, p, stream);
-    default: return SEER_EUNSUPPORTED;
+static int check_desc(const SeerGemmDesc& d) {
+  SEER_CHECK_ARG(d.Wt && d.M > 0 && d.N > 0 && (d.A || d.X));
+  SEER_CHECK_ARG(d.out_f32 || d.out_bf16);
+  SEER_CHECK_ARG(d.K2 % 64 == 0 && (d.K2 == 0 || (d.A2 && d.lda2 % 8 == 0)));
+  if (d.X) {
+    SEER_CHECK_ARG(d.n_img > 0 && d.H > 0 && d.W > 0 && d.Cin > 0 && d.Cin % 64 == 0);
+    SEER_CHECK_ARG(d.M == d.n_img * d.H * d.W);
+  } else {
+    SEER_CHECK_ARG(d.K1 > 0 && d.K1 % 64 == 0 && d.lda % 8 == 0);
   }
-}
-
-static int fill_epilogue(GemmParams& p, int M, int N, const float* bias, int ldb, int bias_div, const float* residual, int ldr,
-                         void* out, int ldo, int flags) {
-  p.M = M; p.N = N;
-  p.bias = bias; p.ldb = ldb > 0 ? ldb : N; p.bias_div = bias_div > 0 ? bias_div : 0x7fffffff;
-  p.residual = residual; p.ldr = ldr;
-  p.out = out; p.ldo = ldo;
-  p.out_bf16 = (flags & SEER_GEMM_OUT_BF16) ? 1 : 0;
-  p.geglu = (flags & SEER_GEMM_GEGLU) ? 1 : 0;
-  if (p.geglu && (!p.out_bf16 || !bias || residual)) return SEER_EINVAL;
+  SEER_CHECK_ARG(!d.out_f32 || d.ldo_f32 % 4 == 0);
+  SEER_CHECK_ARG(!d.out_bf16 || d.ldo_bf16 % 8 == 0);
+  SEER_CHECK_ARG(!d.residual || (d.residual_bf16 ? d.ldr % 8 == 0 : d.ldr % 4 == 0));
+  SEER_CHECK_ARG(d.ldb <= 0 || d.ldb % 4 == 0);
+  if (d.geglu) SEER_CHECK_ARG(d.N % 128 == 0 && d.out_bf16 && !d.out_f32 && d.bias && !d.residual && !d.col_stats && !d.row_stats_out);
+  SEER_CHECK_ARG(!d.col_stats || d.out_f32);
+  if (d.row_stats_in) SEER_CHECK_ARG(d.row_parts_in > 0 && d.ln_colsum && !d.X);
   return SEER_OK;
 }
 
@@ -355,62 +596,119 @@ static int fill_epilogue(GemmParams& p, int M, int N, const float* bias, int ldb
 
 using namespace seer;
 
+extern "C" int seer_b200_gemm_row_parts(const SeerGemmDesc* desc) {
+  if (!desc) return SEER_EINVAL;
+  Plan pl{};
+  int rc = make_plan(*desc, pl);
+  if (rc) return rc;
+  return pl.tiles_n * (pl.nepi >> 2);
+}
+
+extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
+  if (!desc) return SEER_EINVAL;
+  const SeerGemmDesc& d = *desc;
+  int rc = check_desc(d);
+  if (rc) return rc;
+  Plan pl{};
+  if ((rc = make_plan(d, pl))) return rc;
+
+  GemmParams p{};
+  p.M = d.M; p.N = d.N;
+  p.tiles_n = pl.tiles_n; p.num_tiles = pl.num_tiles;
+  p.stages = pl.stages; p.nepi = pl.nepi; p.ring = pl.ring; p.slot_bytes = pl.slot_bytes;
+  p.res_off = pl.res_off; p.outf_off = pl.outf_off; p.outh_off = pl.outh_off;
+  p.bias = d.bias; p.ldb = d.ldb > 0 ? d.ldb : d.N; p.bias_div = d.bias_div > 0 ? d.bias_div : 0x7fffffff;
+  p.res_mode = d.residual ? (d.residual_bf16 ? 2 : 1) : 0;
+  p.out_f32 = d.out_f32 ? 1 : 0; p.out_bf16 = d.out_bf16 ? 1 : 0;
+  p.geglu = d.geglu ? 1 : 0;
+  p.col_stats = d.col_stats; p.row_stats_out = d.row_stats_out;
+  p.row_stats_in = d.row_stats_in; p.row_parts_in = d.row_parts_in; p.ln_eps = d.ln_eps; p.ln_colsum = d.ln_colsum;
+
+  CUtensorMap maps[6];
+  int Ktot;
+  if (d.X) {
+    // A 128-pixel M tile must be a whole number of image rows (or of images): W | 128 and the tile never
+    // straddles an image boundary mid-row.
+    const int W = d.W, H = d.H;
+    if (W > 128 || 128 % W != 0) return SEER_EUNSUPPORTED;
+    const int rows = 128 / W;
+    int bh, bn_img;
+    if (rows <= H) {
+      if (H % rows != 0) return SEER_EUNSUPPORTED;
+      bh = rows; bn_img = 1;
+    } else {
+      if (rows % H != 0) return SEER_EUNSUPPORTED;
+      bh = H; bn_img = rows / H;
+    }
+    p.mode = 1;
+    p.cblk = d.Cin / 64;
+    p.kb_main = 9 * p.cblk;
+    p.H = H; p.W = W;
+    Ktot = 9 * d.Cin + d.K2;
+    if ((rc = make_map_4d(&maps[0], d.X, d.n_img, H, W, d.Cin, W, bh, bn_img))) return rc;
+  } else {
+    p.mode = 0;
+    p.cblk = 1; p.H = 1; p.W = 1;
+    p.kb_main = d.K1 / 64;
+    Ktot = d.K1 + d.K2;
+    if ((rc = make_map_bf16_k64(&maps[0], d.A, d.M, d.K1, d.lda, BM))) return rc;
+  }
+  p.kb_total = Ktot / 64;
+  p.ln_inv_dim = 1.0f / (float)(d.X ? 1 : d.K1);
+  if (d.K2) { if ((rc = make_map_bf16_k64(&maps[1], d.A2, d.M, d.K2, d.lda2, BM))) return rc; } else maps[1] = maps[0];
+  if ((rc = make_map_bf16_k64(&maps[2], d.Wt, d.N, Ktot, Ktot, pl.bn))) return rc;
+  const int n_out = d.geglu ? d.N / 2 : d.N;
+  maps[3] = maps[0]; maps[4] = maps[0]; maps[5] = maps[0];
+  if (d.residual) {
+    if (d.residual_bf16)
+      rc = make_map_2d(&maps[3], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.residual, d.M, n_out, d.ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    else
+      rc = make_map_2d(&maps[3], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.residual, d.M, n_out, d.ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  if (d.out_f32 &&
+      (rc = make_map_2d(&maps[4], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out_f32, d.M, n_out, d.ldo_f32, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)))
+    return rc;
+  if (d.out_bf16 &&
+      (rc = make_map_2d(&maps[5], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out_bf16, d.M, n_out, d.ldo_bf16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
+    return rc;
+
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (pl.bn) {
+    case 64: return launch_gemm<64>(maps, p, pl, st);
+    case 128: return launch_gemm<128>(maps, p, pl, st);
+    case 160: return launch_gemm<160>(maps, p, pl, st);
+    case 192: return launch_gemm<192>(maps, p, pl, st);
+    case 256: return launch_gemm<256>(maps, p, pl, st);
+    default: return SEER_EUNSUPPORTED;
+  }
+}
+
+// ---- the two original entry points, now thin wrappers over the descriptor call ----
 extern "C" int seer_b200_gemm_bf16(const void* A, int lda, int K1, const void* A2, int lda2, int K2, const void* Wt, int M, int N,
                                    const float* bias, int ldb, int bias_div, const float* residual, int ldr, void* out,
                                    int ldo, int flags, void* stream) {
-  SEER_CHECK_ARG(A && Wt && out && M > 0 && N > 0 && K1 > 0);
-  SEER_CHECK_ARG(K1 % 64 == 0 && K2 % 64 == 0 && lda % 8 == 0 && (K2 == 0 || (A2 && lda2 % 8 == 0)));
-  SEER_CHECK_ARG(ldo % 8 == 0 && (residual == nullptr || ldr % 4 == 0) && (ldb <= 0 || ldb % 4 == 0));
-  const int geglu = (flags & SEER_GEMM_GEGLU) ? 1 : 0;
-  const int bn = pick_bn(N, geglu);
-  if (!bn) return SEER_EUNSUPPORTED;
-  GemmParams p{};
-  int rc = fill_epilogue(p, M, N, bias, ldb, bias_div, residual, ldr, out, ldo, flags);
-  if (rc) return rc;
-  p.mode = 0;
-  p.kb_main = K1 / 64;
-  p.kb_total = (K1 + K2) / 64;
-  p.cblk = 1; p.H = 1; p.W = 1;
-  CUtensorMap tA, tA2, tB;
-  if ((rc = make_map_2d(&tA, A, M, K1, lda, BM))) return rc;
-  if (K2) { if ((rc = make_map_2d(&tA2, A2, M, K2, lda2, BM))) return rc; } else tA2 = tA;
-  if ((rc = make_map_2d(&tB, Wt, N, K1 + K2, K1 + K2, bn))) return rc;
-  return dispatch(bn, tA, tA2, tB, p, (cudaStream_t)stream);
+  SeerGemmDesc d{};
+  d.A = A; d.lda = lda; d.K1 = K1;
+  d.A2 = A2; d.lda2 = lda2; d.K2 = K2;
+  d.Wt = Wt; d.M = M; d.N = N;
+  d.bias = bias; d.ldb = ldb; d.bias_div = bias_div;
+  d.residual = residual; d.ldr = ldr;
+  if (flags & SEER_GEMM_OUT_BF16) { d.out_bf16 = out; d.ldo_bf16 = ldo; } else { d.out_f32 = out; d.ldo_f32 = ldo; }
+  d.geglu = (flags & SEER_GEMM_GEGLU) ? 1 : 0;
+  return seer_b200_gemm_ex(&d, stream);
 }
 
 extern "C" int seer_b200_conv3x3_bf16(const void* X, int n_img, int H, int W, int Cin, const void* A2, int lda2, int K2,
                                       const void* Wt, int Cout, const float* bias, int ldb, int bias_div, const float* residual,
                                       int ldr, void* out, int ldo, int flags, void* stream) {
-  SEER_CHECK_ARG(X && Wt && out && n_img > 0 && H > 0 && W > 0);
-  SEER_CHECK_ARG(Cin % 64 == 0 && K2 % 64 == 0 && (K2 == 0 || (A2 && lda2 % 8 == 0)));
-  SEER_CHECK_ARG(ldo % 8 == 0 && (residual == nullptr || ldr % 4 == 0) && (ldb <= 0 || ldb % 4 == 0));
-  SEER_CHECK_ARG(!(flags & SEER_GEMM_GEGLU));
-  // A 128-pixel M tile must be a whole number of image rows (or of images): W | 128 and the tile never
-  // straddles an image boundary mid-row.
-  if (W > 128 || 128 % W != 0) return SEER_EUNSUPPORTED;
-  int rows = 128 / W, bh, bn_img;
-  if (rows <= H) {
-    if (H % rows != 0) return SEER_EUNSUPPORTED;
-    bh = rows; bn_img = 1;
-  } else {
-    if (rows % H != 0) return SEER_EUNSUPPORTED;
-    bh = H; bn_img = rows / H;
-  }
-  const int M = n_img * H * W;
-  const int bn = pick_bn(Cout, 0);
-  if (!bn) return SEER_EUNSUPPORTED;
-  GemmParams p{};
-  int rc = fill_epilogue(p, M, Cout, bias, ldb, bias_div, residual, ldr, out, ldo, flags);
-  if (rc) return rc;
-  p.mode = 1;
-  p.cblk = Cin / 64;
-  p.kb_main = 9 * p.cblk;
-  p.kb_total = p.kb_main + K2 / 64;
-  p.H = H; p.W = W;
-  CUtensorMap tA, tA2, tB;
-  if ((rc = make_map_4d(&tA, X, n_img, H, W, Cin, W, bh, bn_img))) return rc;
-  if (K2) { if ((rc = make_map_2d(&tA2, A2, M, K2, lda2, BM))) return rc; } else tA2 = tA;
-  const int Kt = 9 * Cin + K2;
-  if ((rc = make_map_2d(&tB, Wt, Cout, Kt, Kt, bn))) return rc;
-  return dispatch(bn, tA, tA2, tB, p, (cudaStream_t)stream);
+  if (flags & SEER_GEMM_GEGLU) return SEER_EINVAL;
+  SeerGemmDesc d{};
+  d.X = X; d.n_img = n_img; d.H = H; d.W = W; d.Cin = Cin;
+  d.A2 = A2; d.lda2 = lda2; d.K2 = K2;
+  d.Wt = Wt; d.M = n_img * H * W; d.N = Cout;
+  d.bias = bias; d.ldb = ldb; d.bias_div = bias_div;
+  d.residual = residual; d.ldr = ldr;
+  if (flags & SEER_GEMM_OUT_BF16) { d.out_bf16 = out; d.ldo_bf16 = ldo; } else { d.out_f32 = out; d.ldo_f32 = ldo; }
+  return seer_b200_gemm_ex(&d, stream);
 }

@@ -109,6 +109,52 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nchunk
   }
 }
 
+// GroupNorm statistics from the per-(32-row slab, channel) partial sums the producing GEMM's epilogue emitted
+// (SeerGemmDesc::col_stats): one block per (group, sample) sums its channels over the sample's T/32 slabs in double
+// and emits the same per-(b, c) affine as gn_finalize_kernel.  The input may be the virtual concat of two tensors,
+// each with its own statistics buffer.
+__global__ void __launch_bounds__(256) gn_finalize_cols_kernel(const float2* __restrict__ st1, int C1,
+                                                               const float2* __restrict__ st2, int C2, int T, float eps,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float* __restrict__ scale, float* __restrict__ shift) {
+  const int C = C1 + C2;
+  const int cpg = C / GN_GROUPS;
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int slabs = T / 32;
+  const int total = slabs * cpg;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int sl = i / cpg;
+    const int c = g * cpg + (i - sl * cpg);
+    const size_t slab = (size_t)b * slabs + sl;
+    const float2 v = c < C1 ? st1[slab * C1 + c] : st2[slab * C2 + (c - C1)];
+    s += (double)v.x;
+    q += (double)v.y;
+  }
+  __shared__ double sh[2][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  s = 0.0; q = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { s += sh[0][w]; q += sh[1][w]; }     // fixed order: deterministic
+  const double n = (double)cpg * (double)T;
+  const double mean = s / n;
+  double var = q / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float meanf = (float)mean;
+  for (int c = g * cpg + threadIdx.x; c < (g + 1) * cpg; c += blockDim.x) {
+    const float sc = rstd * gamma[c];
+    scale[(size_t)b * C + c] = sc;
+    shift[(size_t)b * C + c] = beta[c] - meanf * sc;
+  }
+}
+
 // y = act(x * scale[b, c] + shift[b, c]);  8 channels per thread.  Optional second output: raw bf16 copy of x
 // (the un-normalised concat that feeds the fused ResNet 1x1 shortcut GEMM).
 template <bool OUT_F32>
@@ -224,6 +270,29 @@ extern "C" int seer_b200_groupnorm(const float* x1, int C1, const float* x2, int
   gn_partial_kernel<<<dim3(nchunks, B), GN_THREADS, 0, stream>>>(x1, C1, x2, C2, T, tpc, workspace);
   SEER_LAUNCH_CHECK();
   gn_finalize_kernel<<<B, GN_GROUPS * 32, 0, stream>>>(workspace, nchunks, C, T, eps, gamma, beta, scale, shift, nullptr);
+  SEER_LAUNCH_CHECK();
+  const size_t total8 = (size_t)B * T * (C / 8);
+  size_t nb = (total8 + 255) / 256; if (nb > (size_t)148 * 16) nb = (size_t)148 * 16;
+  const int blocks = (int)nb;
+  if (y_is_f32)
+    gn_apply_kernel<true><<<blocks, 256, 0, stream>>>(x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16);
+  else
+    gn_apply_kernel<false><<<blocks, 256, 0, stream>>>(x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16);
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_groupnorm_from_stats(const float* x1, int C1, const float* stats1, const float* x2, int C2,
+                                              const float* stats2, int B, int T, const float* gamma, const float* beta, float eps,
+                                              int silu, float* scale_shift, void* y, int y_is_f32, void* raw_bf16, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int C = C1 + C2;
+  SEER_CHECK_ARG(x1 && stats1 && gamma && beta && scale_shift && y && B > 0 && T > 0 && T % 32 == 0);
+  SEER_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && (C2 == 0 || (x2 && stats2)) && C % (2 * GN_GROUPS) == 0);
+  float* scale = scale_shift;
+  float* shift = scale_shift + (size_t)B * C;
+  gn_finalize_cols_kernel<<<dim3(GN_GROUPS, B), 256, 0, stream>>>((const float2*)stats1, C1, (const float2*)stats2, C2, T, eps,
+                                                                  gamma, beta, scale, shift);
   SEER_LAUNCH_CHECK();
   const size_t total8 = (size_t)B * T * (C / 8);
   size_t nb = (total8 + 255) / 256; if (nb > (size_t)148 * 16) nb = (size_t)148 * 16;

@@ -70,12 +70,46 @@ def _rows(t: torch.Tensor) -> Tuple[int, int]:
     return t.shape[0], t.stride(0)
 
 
-def gemm(a: torch.Tensor, wt: torch.Tensor, *, a2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-         bias_div: int = 0, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-         out_dtype: torch.dtype = torch.float32, geglu: bool = False) -> torch.Tensor:
-    """out = [a | a2] @ wt.T + bias (+ residual).  a:[M,K1] bf16, a2:[M,K2] bf16, wt:[N,K1+K2] bf16."""
-    _req(a, torch.bfloat16, "a", 2); _req(wt, torch.bfloat16, "wt", 2)
-    M, K1 = a.shape
+class GemmOut:
+    """Outputs of one `gemm_ex` launch: `out` (fp32 or bf16 primary), `out16` (extra bf16 copy when both were asked),
+    `col_stats` ([ceil(M/32), N, 2] per-slab channel (sum, sumsq) for GroupNorm), `row_stats` ([parts, M, 2] per-row
+    partial (sum, sumsq) for a LayerNorm folded into the next GEMM)."""
+    __slots__ = ("out", "out16", "col_stats", "row_stats")
+
+    def __init__(self, out, out16=None, col_stats=None, row_stats=None):
+        self.out, self.out16, self.col_stats, self.row_stats = out, out16, col_stats, row_stats
+
+
+def gemm_ex(a: Optional[torch.Tensor], wt: torch.Tensor, *, x_img: Optional[torch.Tensor] = None,
+            a2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, bias_div: int = 0,
+            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+            out_dtype: torch.dtype = torch.float32, also_bf16=False, geglu: bool = False, col_stats: bool = False,
+            row_stats: bool = False, ln: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None) -> GemmOut:
+    """One tcgen05 GEMM / implicit-GEMM conv launch (SeerGemmDesc, include/seer_b200.h).
+
+    acc = [a | a2] @ wt.T   (a:[M,K1] bf16, or x_img:[n_img,H,W,Cin] bf16 for the 3x3/pad-1 conv; a2:[M,K2] bf16)
+    v   = LN-fold(acc) + bias[(row // bias_div)] + residual;  geglu: value * gelu(gate)
+    `ln` = (row_stats [parts, M, 2] from the producer, colsum [N] fp32, eps) folds LayerNorm(a) into this GEMM (wt must
+    hold W*gamma and bias beta@W.T (+b)).  `also_bf16` (True or a tensor) adds a bf16 copy next to an fp32 `out`.
+    residual may be fp32 or bf16."""
+    _req(wt, torch.bfloat16, "wt", 2)
+    if not wt.is_contiguous():
+        raise ValueError("wt must be contiguous")
+    d = _lib.GemmDesc()
+    keep = []
+    if x_img is not None:
+        _req(x_img, torch.bfloat16, "x_img", 4)
+        if not x_img.is_contiguous():
+            raise ValueError("x_img must be contiguous [n_img,H,W,Cin]")
+        n_img, H, W, Cin = x_img.shape
+        M, K1 = n_img * H * W, 9 * Cin
+        d.X, d.n_img, d.H, d.W, d.Cin = x_img.data_ptr(), n_img, H, W, Cin
+        dev = x_img.device
+    else:
+        _req(a, torch.bfloat16, "a", 2)
+        M, K1 = a.shape
+        d.A, d.lda, d.K1 = a.data_ptr(), a.stride(0), K1
+        dev = a.device
     N = wt.shape[0]
     K2 = 0
     if a2 is not None:
@@ -83,77 +117,101 @@ def gemm(a: torch.Tensor, wt: torch.Tensor, *, a2: Optional[torch.Tensor] = None
         K2 = a2.shape[1]
         if a2.shape[0] != M:
             raise ValueError("a2 rows != a rows")
-    if wt.shape[1] != K1 + K2 or not wt.is_contiguous():
-        raise ValueError(f"wt must be contiguous [N, {K1 + K2}], got {tuple(wt.shape)}")
+        d.A2, d.lda2, d.K2 = a2.data_ptr(), a2.stride(0), K2
+    if wt.shape[1] != K1 + K2:
+        raise ValueError(f"wt must be [N, {K1 + K2}], got {tuple(wt.shape)}")
+    d.Wt, d.M, d.N = wt.data_ptr(), M, N
     n_out = N // 2 if geglu else N
     if out is None:
-        out = torch.empty((M, n_out), device=a.device, dtype=torch.bfloat16 if geglu else out_dtype)
-    if out.shape[0] != M or out.shape[1] != n_out:
+        out = torch.empty((M, n_out), device=dev, dtype=torch.bfloat16 if geglu else out_dtype)
+    if out.dim() != 2 or out.shape[0] != M or out.shape[1] != n_out:
         raise ValueError(f"out shape {tuple(out.shape)} != ({M}, {n_out})")
-    _req(out, out.dtype, "out", 2)
-    flags = (GEMM_OUT_BF16 if out.dtype == torch.bfloat16 else 0) | (GEMM_GEGLU if geglu else 0)
     if out.dtype not in (torch.bfloat16, torch.float32):
         raise TypeError("out must be bf16 or fp32")
-    ldb = 0
+    _req(out, out.dtype, "out", 2)
+    out16 = None
+    if out.dtype == torch.float32:
+        d.out_f32, d.ldo_f32 = out.data_ptr(), out.stride(0)
+        if also_bf16 is not False and also_bf16 is not None:
+            out16 = torch.empty((M, n_out), device=dev, dtype=torch.bfloat16) if also_bf16 is True else also_bf16
+            _req(out16, torch.bfloat16, "also_bf16", 2)
+            if out16.shape != out.shape:
+                raise ValueError("also_bf16 shape != out shape")
+            d.out_bf16, d.ldo_bf16 = out16.data_ptr(), out16.stride(0)
+    else:
+        if also_bf16 is not False and also_bf16 is not None:
+            raise ValueError("also_bf16 needs an fp32 primary output")
+        d.out_bf16, d.ldo_bf16 = out.data_ptr(), out.stride(0)
     if bias is not None:
         _req(bias, torch.float32, "bias")
-        ldb = bias.stride(0) if bias.dim() == 2 else N
+        d.bias, d.ldb, d.bias_div = bias.data_ptr(), (bias.stride(0) if bias.dim() == 2 else N), bias_div
     if residual is not None:
-        _req(residual, torch.float32, "residual", 2)
-    with _Timed(f"gemm M={M} N={N} K={K1 + K2}", 2.0 * M * N * (K1 + K2)):
-        rc = _lib.lib().seer_b200_gemm_bf16(_p(a), a.stride(0), K1, _p(a2), a2.stride(0) if a2 is not None else 0, K2, _p(wt), M,
-                                            N, _p(bias), ldb, bias_div, _p(residual),
-                                            residual.stride(0) if residual is not None else 0, _p(out), out.stride(0), flags,
-                                            _stream())
-    _lib.check(rc, f"gemm_bf16(M={M},N={N},K={K1}+{K2})")
+        if residual.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("residual must be fp32 or bf16")
+        _req(residual, residual.dtype, "residual", 2)
+        if residual.shape[0] != M or residual.shape[1] != n_out:
+            raise ValueError("residual shape != out shape")
+        d.residual, d.ldr, d.residual_bf16 = residual.data_ptr(), residual.stride(0), int(residual.dtype == torch.bfloat16)
+    d.geglu = int(geglu)
+    cs = rs = None
+    if col_stats:
+        cs = torch.empty(((M + 31) // 32, N, 2), device=dev, dtype=torch.float32)
+        d.col_stats = cs.data_ptr()
+    if ln is not None:
+        st, colsum, eps = ln
+        _req(st, torch.float32, "ln row_stats", 3); _req(colsum, torch.float32, "ln colsum", 1)
+        if st.shape[1] != M or st.shape[2] != 2 or not st.is_contiguous() or colsum.numel() != N:
+            raise ValueError("ln: row_stats must be [parts, M, 2] contiguous and colsum [N]")
+        d.row_stats_in, d.row_parts_in, d.ln_eps, d.ln_colsum = st.data_ptr(), st.shape[0], float(eps), colsum.data_ptr()
+    L = _lib.lib()
+    if row_stats:
+        parts = L.seer_b200_gemm_row_parts(ctypes.byref(d))
+        if parts <= 0:
+            _lib.check(parts if parts < 0 else -2, "gemm_row_parts")
+        rs = torch.empty((parts, M, 2), device=dev, dtype=torch.float32)
+        d.row_stats_out = rs.data_ptr()
+    name = f"{'conv3x3' if x_img is not None else 'gemm'} M={M} N={N} K={K1 + K2}"
+    with _Timed(name, 2.0 * M * N * (K1 + K2)):
+        rc = L.seer_b200_gemm_ex(ctypes.byref(d), _stream())
+    if rc == -2 and x_img is not None:
+        return None          # geometry not tileable by TMA boxes: caller falls back to explicit im2col
+    _lib.check(rc, name)
     _count()
-    return out
+    return GemmOut(out, out16, cs, rs)
+
+
+def gemm(a: torch.Tensor, wt: torch.Tensor, *, a2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+         bias_div: int = 0, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         out_dtype: torch.dtype = torch.float32, geglu: bool = False) -> torch.Tensor:
+    """out = [a | a2] @ wt.T + bias (+ residual).  a:[M,K1] bf16, a2:[M,K2] bf16, wt:[N,K1+K2] bf16."""
+    return gemm_ex(a, wt, a2=a2, bias=bias, bias_div=bias_div, residual=residual, out=out, out_dtype=out_dtype, geglu=geglu).out
+
+
+def conv3x3_ex(x: torch.Tensor, wt: torch.Tensor, **kw) -> GemmOut:
+    """Frame-wise 3x3 conv (stride 1, pad 1).  x:[n_img,H,W,Cin] bf16 contiguous; wt:[Cout, 9*Cin (+K2)] bf16 with
+    K order [ky][kx][Cin]; result rows [n_img*H*W, Cout].  Falls back to im2col + GEMM (still seer_b200 kernels) for
+    image sizes the TMA-box tiling does not cover."""
+    r = gemm_ex(None, wt, x_img=x, **kw)
+    if r is None:
+        cols = im2col3x3(x, stride=1)
+        a2 = kw.pop("a2", None)
+        a_full = cols if a2 is None else torch.cat([cols, a2], dim=1)
+        r = gemm_ex(a_full, wt, **kw)
+    return r
 
 
 def conv3x3(x: torch.Tensor, wt: torch.Tensor, *, a2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
             bias_div: int = 0, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
             out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
-    """Frame-wise 3x3 conv (stride 1, pad 1).  x:[n_img,H,W,Cin] bf16 contiguous; wt:[Cout, 9*Cin (+K2)] bf16 with
-    K order [ky][kx][Cin]; returns [n_img*H*W, Cout].  Falls back to im2col + GEMM (still seer_b200 kernels) for
-    image sizes the TMA-box tiling does not cover."""
-    _req(x, torch.bfloat16, "x", 4); _req(wt, torch.bfloat16, "wt", 2)
-    if not x.is_contiguous() or not wt.is_contiguous():
-        raise ValueError("x and wt must be contiguous")
-    n_img, H, W, Cin = x.shape
-    Cout = wt.shape[0]
-    M = n_img * H * W
-    K2 = 0
-    if a2 is not None:
-        _req(a2, torch.bfloat16, "a2", 2)
-        K2 = a2.shape[1]
-    if wt.shape[1] != 9 * Cin + K2:
-        raise ValueError(f"wt must be [Cout, {9 * Cin + K2}], got {tuple(wt.shape)}")
-    if out is None:
-        out = torch.empty((M, Cout), device=x.device, dtype=out_dtype)
-    flags = GEMM_OUT_BF16 if out.dtype == torch.bfloat16 else 0
-    ldb = 0
-    if bias is not None:
-        _req(bias, torch.float32, "bias")
-        ldb = bias.stride(0) if bias.dim() == 2 else Cout
-    if residual is not None:
-        _req(residual, torch.float32, "residual", 2)
-    with _Timed(f"conv3x3 M={M} N={Cout} K={9 * Cin + K2}", 2.0 * M * Cout * (9 * Cin + K2)):
-        rc = _lib.lib().seer_b200_conv3x3_bf16(_p(x), n_img, H, W, Cin, _p(a2), a2.stride(0) if a2 is not None else 0, K2,
-                                               _p(wt), Cout, _p(bias), ldb, bias_div, _p(residual),
-                                               residual.stride(0) if residual is not None else 0, _p(out), out.stride(0),
-                                               flags, _stream())
-    if rc == -2:      # geometry not tileable by TMA boxes: explicit im2col, same GEMM kernel
-        cols = im2col3x3(x, stride=1)
-        a_full = cols if a2 is None else torch.cat([cols, a2], dim=1)
-        return gemm(a_full, wt, bias=bias, bias_div=bias_div, residual=residual, out=out)
-    _lib.check(rc, f"conv3x3_bf16(n={n_img},H={H},W={W},Cin={Cin},Cout={Cout})")
-    _count()
-    return out
+    return conv3x3_ex(x, wt, a2=a2, bias=bias, bias_div=bias_div, residual=residual, out=out, out_dtype=out_dtype).out
 
 
 def groupnorm(x1: torch.Tensor, x2: Optional[torch.Tensor], B: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
-              silu: bool, out_dtype: torch.dtype = torch.bfloat16, want_raw: bool = False):
-    """GroupNorm(32) over (C/32, T) per sample on the virtual concat [x1 | x2] (token-major fp32) (+SiLU)."""
+              silu: bool, out_dtype: torch.dtype = torch.bfloat16, want_raw: bool = False,
+              stats1: Optional[torch.Tensor] = None, stats2: Optional[torch.Tensor] = None):
+    """GroupNorm(32) over (C/32, T) per sample on the virtual concat [x1 | x2] (token-major fp32) (+SiLU).
+    With `stats1` (and `stats2` when x2 is given) — the col_stats a gemm_ex launch emitted while producing the
+    tensor — the statistics pass over the activation is skipped."""
     _req(x1, torch.float32, "x1", 2)
     M, C1 = x1.shape
     C2 = 0
@@ -170,14 +228,27 @@ def groupnorm(x1: torch.Tensor, x2: Optional[torch.Tensor], B: int, gamma: torch
     if gamma.numel() != C or beta.numel() != C:
         raise ValueError("gamma/beta size != C1 + C2")
     L = _lib.lib()
-    ws = torch.empty(L.seer_b200_groupnorm_workspace_floats(B, T), device=x1.device, dtype=torch.float32)
     ss = torch.empty(2 * B * C, device=x1.device, dtype=torch.float32)
     y = torch.empty((M, C), device=x1.device, dtype=out_dtype)
     raw = torch.empty((M, C), device=x1.device, dtype=torch.bfloat16) if want_raw else None
-    rc = L.seer_b200_groupnorm(_p(x1), C1, _p(x2), C2, B, T, _p(gamma), _p(beta), float(eps), int(silu), _p(ws), _p(ss), _p(y),
-                               int(out_dtype == torch.float32), _p(raw), _stream())
-    _lib.check(rc, f"groupnorm(B={B},T={T},C={C1}+{C2})")
-    _count(3)
+    use_stats = stats1 is not None and (x2 is None or stats2 is not None) and T % 32 == 0
+    if use_stats:
+        for nm, st, Ci in (("stats1", stats1, C1), ("stats2", stats2, C2)):
+            if st is not None:
+                _req(st, torch.float32, nm, 3)
+                if tuple(st.shape) != (M // 32, Ci, 2) or not st.is_contiguous():
+                    raise ValueError(f"{nm} must be contiguous [{M // 32}, {Ci}, 2]")
+        rc = L.seer_b200_groupnorm_from_stats(_p(x1), C1, _p(stats1), _p(x2), C2, _p(stats2) if x2 is not None else None, B, T,
+                                              _p(gamma), _p(beta), float(eps), int(silu), _p(ss), _p(y),
+                                              int(out_dtype == torch.float32), _p(raw), _stream())
+        _lib.check(rc, f"groupnorm_from_stats(B={B},T={T},C={C1}+{C2})")
+        _count(2)
+    else:
+        ws = torch.empty(L.seer_b200_groupnorm_workspace_floats(B, T), device=x1.device, dtype=torch.float32)
+        rc = L.seer_b200_groupnorm(_p(x1), C1, _p(x2), C2, B, T, _p(gamma), _p(beta), float(eps), int(silu), _p(ws), _p(ss),
+                                   _p(y), int(out_dtype == torch.float32), _p(raw), _stream())
+        _lib.check(rc, f"groupnorm(B={B},T={T},C={C1}+{C2})")
+        _count(3)
     return (y, raw) if want_raw else y
 
 
