@@ -44,7 +44,7 @@ int seer_b200_gemm_bf16(const void* A, int lda, int K1, const void* A2, int lda2
 /* Full descriptor of one tcgen05 GEMM / implicit-GEMM conv launch (superset of the two entry points around it):
  *
  *   acc[M,N]  = [A | A2] * Wt^T                       A: plain A[M,K1] bf16, or (X != NULL) the 3x3/pad-1 im2col of
- *                                                      X[n_img,H,W,Cin] bf16 (K1 = 9*Cin, K order [ky][kx][Cin])
+ *                                                      X[n_img,H,W,Cin] bf16 (K1 = 9*Cin, K order [Cin/64][ky][kx][64])
  *   v         = ln ? rstd_r * (acc - mean_r * ln_colsum[n]) : acc        (LayerNorm folded into the GEMM: Wt holds
  *                                                      W*gamma, bias holds beta*W^T (+b); mean/rstd of row r come from
  *                                                      row_stats_in = `row_parts_in` partial (sum, sumsq) pairs)
@@ -78,7 +78,7 @@ int seer_b200_gemm_desc_size(void);
 int seer_b200_gemm_row_parts(const SeerGemmDesc* desc);
 
 /* Frame-wise 3x3 conv, stride 1, pad 1, as implicit GEMM over 9 shifted TMA boxes of X[n_img,H,W,Cin] (bf16),
- * optional fused 1x1 tail A2[M,K2] (ResNet shortcut).  Wt[Cout, 9*Cin + K2] with K order [ky][kx][Cin] then tail.
+ * optional fused 1x1 tail A2[M,K2] (ResNet shortcut).  Wt[Cout, 9*Cin + K2] with K order [Cin/64][ky][kx][64] then tail.
  * Replaces InflatedConv3d(k=3): seer/models/resnet.py:8-16,147,155 and Upsample3D's conv :39.
  * Requires Cin % 64 == 0, W | 128, and (128/W) | H or H | (128/W). */
 int seer_b200_conv3x3_bf16(const void* X, int n_img, int H, int W, int Cin, const void* A2, int lda2, int K2, const void* Wt,
@@ -138,7 +138,7 @@ int seer_b200_conv_out(const float* x, const float* w_packed, const float* bias,
 
 /* nearest 2x upsample fp32 [n,H,W,C] -> bf16 [n,2H,2W,C] (resnet.py:52). */
 int seer_b200_upsample2x_to_bf16(const float* x, void* y, int n_img, int H, int W, int C, void* stream);
-/* pad-1 3x3 im2col, stride 1 or 2: [n,H,W,C] (fp32, or bf16 if in_is_bf16) -> bf16 [n*(H/s)*(W/s), 9*C], K order [tap][C].
+/* pad-1 3x3 im2col, stride 1 or 2: [n,H,W,C] (fp32, or bf16 if in_is_bf16) -> bf16 [n*(H/s)*(W/s), 9*C], K order [C/64][tap][64]; C % 64 == 0.
  * Stride 2 = Downsample3D (resnet.py:95-104); stride 1 = fallback for image sizes the TMA-box conv does not tile. */
 int seer_b200_im2col3x3_to_bf16(const void* x, int in_is_bf16, void* y, int n_img, int H, int W, int C, int stride, void* stream);
 int seer_b200_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);

@@ -209,18 +209,20 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __
 
 // ---------------------------------------------------------------------------------------------------
 // im2col for pad-1 3x3 convs, stride 1 or 2: [n_img, H, W, C] (fp32 or bf16) -> bf16 [n_img*Ho*Wo, 9*C],
-// K order = [tap][C] (matches the packed conv weight).  Stride 2: Downsample3D (resnet.py:95-104).
+// K order = [C/64][tap][64] (matches the packed conv weight, packing.pack_conv3x3).  Stride 2: Downsample3D (resnet.py:95-104).
 // ---------------------------------------------------------------------------------------------------
 template <bool IN_BF16>
 __global__ void im2col3x3_kernel(const void* __restrict__ xin, __nv_bfloat16* __restrict__ y, int n_img, int H, int W, int C,
                                  int stride) {
-  const int c8n = C / 8;
+  const int nchunk = C / 64;
   const int Ho = H / stride, Wo = W / stride;
-  const size_t total = (size_t)n_img * Ho * Wo * 9 * c8n;
+  const size_t total = (size_t)n_img * Ho * Wo * nchunk * 72;     // 72 = 9 taps x 8 groups of 8 channels
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c8n) * 8;
-    size_t r = i / c8n;
+    size_t r = i;
+    const int g8 = (int)(r % 8); r /= 8;
     const int tap = (int)(r % 9); r /= 9;
+    const int chunk = (int)(r % nchunk); r /= nchunk;
+    const int c = chunk * 64 + g8 * 8;
     const int ox = (int)(r % Wo); r /= Wo;
     const int oy = (int)(r % Ho);
     const int img = (int)(r / Ho);
@@ -352,7 +354,7 @@ extern "C" int seer_b200_upsample2x_to_bf16(const float* x, void* y, int n_img, 
 
 extern "C" int seer_b200_im2col3x3_to_bf16(const void* x, int in_is_bf16, void* y, int n_img, int H, int W, int C, int stride,
                                            void* stream) {
-  SEER_CHECK_ARG(x && y && C % 8 == 0 && (stride == 1 || stride == 2) && H % stride == 0 && W % stride == 0);
+  SEER_CHECK_ARG(x && y && C % 64 == 0 && (stride == 1 || stride == 2) && H % stride == 0 && W % stride == 0);
   const size_t total = (size_t)n_img * (H / stride) * (W / stride) * 9 * (C / 8);
   if (in_is_bf16)
     im2col3x3_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n_img, H, W, C, stride);

@@ -63,9 +63,12 @@ struct GemmParams {
   const float* ln_colsum;
 };
 
-template <int BN>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile — each
+// CTA stages its own 128 A rows and only HALF of the Wt rows, so the L2 -> SM operand traffic per FLOP drops by
+// 64*(128+BN)/BN -> 64*(128+BN/2)/BN bytes per MMA cycle (the measured limiter of the 1-CTA kernel, profiles/).
+template <int BN, int CG>
 struct GemmCfg {
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TBUF = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // TMEM column stride between the 2 buffers
   static constexpr int TMEM_COLS = 2 * TBUF;
@@ -75,12 +78,12 @@ struct GemmCfg {
 __device__ __forceinline__ int sw128(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
 __device__ __forceinline__ int sw64(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_MAX_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmRes,
                const __grid_constant__ CUtensorMap tmOutF, const __grid_constant__ CUtensorMap tmOutH, const GemmParams p) {
-  using C = GemmCfg<BN>;
+  using C = GemmCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring_base = smem + p.stages * C::STAGE_BYTES;
@@ -93,6 +96,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA pair bookkeeping: `unit` = this CTA (CG 1) or this pair (CG 2) in the persistent tile loop
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nunits = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -107,28 +114,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], p.nepi);
+      mbar_init(&tmem_empty_bar[b], p.nepi * CG);     // CG 2: the epilogue warps of BOTH CTAs arrive on the leader's
     }
     for (int i = 0; i < MAX_EPI_WARPS * MAX_RING; ++i) mbar_init(&res_full_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_cg2(tmem_slot, C::TMEM_COLS); tmem_relinquish_cg2(); }
+    else { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();                                            // reconverge (barrier.cluster is .aligned)
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // barrier inits visible (cluster-wide) before any arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp loops — uniform control flow; one elected lane issues) ==========
+    {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const uint32_t full0 = CG == 2 ? mapa_shared(smem_u32(full_bar), 0) : 0;   // the pair leader's full barriers
+      for (int tile = unit; tile < p.num_tiles; tile += nunits) {
         const int mb = tile / p.tiles_n, nb = tile - mb * p.tiles_n;
-        const int m0 = mb * BM, n0 = nb * BN;
+        const int m0 = (mb * CG + rank) * BM, n0 = nb * BN + rank * (BN / CG);
         int img0 = 0, y0 = 0;
         if (p.mode == 1) {
           const int hw = p.H * p.W;
@@ -139,32 +148,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sA = smem + s * C::STAGE_BYTES;
           uint8_t* sB = sA + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-          if (kb < p.kb_main) {
-            if (p.mode == 0) {
-              tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m0);
+          if (elect_one()) {
+          if (CG == 1) {
+            mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+            if (kb < p.kb_main) {
+              if (p.mode == 0) {
+                tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m0);
+              } else {
+                // K order [Cin/64][tap][64]: the 9 shifted views of one 64-channel slab are fetched back to back, so
+                // the slab (and its halo) is served from L2 while it is hot instead of being re-read 9 x Cin/64 k-blocks apart
+                const int chunk = kb / 9;
+                const int tap = kb - chunk * 9;
+                const int c0 = chunk * BK;
+                const int ky = tap / 3, kx = tap - ky * 3;
+                tma_load_4d(sA, &tmA, &full_bar[s], c0, kx - 1, y0 + ky - 1, img0);
+              }
             } else {
-              const int tap = kb / p.cblk;
-              const int c0 = (kb - tap * p.cblk) * BK;
-              const int ky = tap / 3, kx = tap - ky * 3;
-              tma_load_4d(sA, &tmA, &full_bar[s], c0, kx - 1, y0 + ky - 1, img0);
+              tma_load_2d(sA, &tmA2, &full_bar[s], (kb - p.kb_main) * BK, m0);
             }
+            tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
           } else {
-            tma_load_2d(sA, &tmA2, &full_bar[s], (kb - p.kb_main) * BK, m0);
+            // both CTAs of the pair fill their own stage; all bytes are counted on the LEADER's full barrier
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+            const uint32_t fb = full0 + (uint32_t)s * 8u;
+            if (kb < p.kb_main) {
+              if (p.mode == 0) {
+                tma_load_2d_cg2(sA, &tmA, fb, kb * BK, m0);
+              } else {
+                // K order [Cin/64][tap][64]: the 9 shifted views of one 64-channel slab are fetched back to back, so
+                // the slab (and its halo) is served from L2 while it is hot instead of being re-read 9 x Cin/64 k-blocks apart
+                const int chunk = kb / 9;
+                const int tap = kb - chunk * 9;
+                const int c0 = chunk * BK;
+                const int ky = tap / 3, kx = tap - ky * 3;
+                tma_load_4d_cg2(sA, &tmA, fb, c0, kx - 1, y0 + ky - 1, img0);
+              }
+            } else {
+              tma_load_2d_cg2(sA, &tmA2, fb, (kb - p.kb_main) * BK, m0);
+            }
+            tma_load_2d_cg2(sB, &tmB, fb, kb * BK, n0);
           }
-          tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
+          }
+          __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    // ===== whole warp loops (uniform control flow, descriptors in uniform registers); one elected lane issues =====
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
         const int buf = it & 1;
         mbar_wait(&tmem_empty_bar[buf], (((uint32_t)it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
@@ -175,15 +213,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t a_addr = smem_u32(smem + s * C::STAGE_BYTES);
           const uint64_t a_desc = umma_desc_sw128(a_addr);
           const uint64_t b_desc = umma_desc_sw128(a_addr + A_BYTES);
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            if (CG == 2) umma_bf16_cg2(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[s]);   // frees this smem stage once the MMAs above have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+          if (CG == 2) umma_commit_cg2(&empty_bar[s], 3); else umma_commit(&empty_bar[s]);
+          if (kb == p.kb_total - 1) {          // accumulator complete
+            if (CG == 2) umma_commit_cg2(&tmem_full_bar[buf], 3); else umma_commit(&tmem_full_bar[buf]);
+          }
+          }
+          __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tmem_full_bar[buf]);   // accumulator complete
       }
     }
     __syncwarp();
@@ -196,7 +241,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int cw = p.geglu ? 64 : 32;        // accumulator columns per chunk (always 32 output columns)
     const int nch = BN / cw;
     const int my_nch = (nch - half + nhalf - 1) / nhalf;
-    const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my_tiles = (p.num_tiles - unit + nunits - 1) / nunits;
+    const uint32_t tempty0 = CG == 2 ? mapa_shared(smem_u32(tmem_empty_bar), 0) : 0;   // the leader's tmem_empty barriers
     const int total = my_tiles * my_nch;
     const int R = p.ring, P = p.ring - 2;
     uint8_t* ring = ring_base + (size_t)ew * R * p.slot_bytes;
@@ -205,21 +251,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     auto issue_res = [&](int step) {         // lane 0: TMA-prefetch the residual chunk of a future step
       const int it2 = step / my_nch, j2 = step - it2 * my_nch;
-      const int tile2 = blockIdx.x + it2 * gridDim.x;
+      const int tile2 = unit + it2 * nunits;
       const int mb2 = tile2 / p.tiles_n, nb2 = tile2 - mb2 * p.tiles_n;
       const int s2 = step % R;
       mbar_arrive_expect_tx(&rfull[s2], res_bytes);
       tma_load_2d(ring + s2 * p.slot_bytes + p.res_off, &tmRes, &rfull[s2], nb2 * BN + (half + j2 * nhalf) * 32,
-                  mb2 * BM + q * 32);
+                  (mb2 * CG + rank) * BM + q * 32);
     };
-    if (p.res_mode && lane == 0)
-      for (int st = 0; st < P && st < total; ++st) issue_res(st);
+    if (p.res_mode) {
+      for (int st = 0; st < P && st < total; ++st)
+        if (elect_one()) issue_res(st);
+      __syncwarp();
+    }
 
     const bool want_stats = p.col_stats != nullptr || p.row_stats_out != nullptr;
     int g = 0, it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
       const int mb = tile / p.tiles_n, nb = tile - mb * p.tiles_n;
-      const int m0 = mb * BM, n0 = nb * BN;
+      const int m0 = (mb * CG + rank) * BM, n0 = nb * BN;
       const int buf = it & 1;
       const int row0 = m0 + q * 32;
       const int row = row0 + lane;
@@ -243,11 +292,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int c = half + j * nhalf;
         const int s = g % R;
         uint8_t* slot = ring + s * p.slot_bytes;
-        if (lane == 0) {
-          bulk_wait_read<1>();               // the store that last used slot (g+P)%R (and (g-R)%R) has read its smem
-          if (p.res_mode && g + P < total) issue_res(g + P);
-        }
+        if (lane == 0) bulk_wait_read<1>();  // the store that last used slot (g+P)%R (and (g-R)%R) has read its smem
         __syncwarp();
+        if (p.res_mode && g + P < total) {
+          if (lane == 0) issue_res(g + P);   // (same lane as the stores: bulk groups are tracked per thread)
+          __syncwarp();
+        }
         if (j == 0) {
           mbar_wait(&tmem_full_bar[buf], ((uint32_t)it >> 1) & 1);
           tc_fence_after();
@@ -262,7 +312,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (j == my_nch - 1) {           // last TMEM read of this tile by this warp: hand the buffer back
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+              if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(tempty0 + (uint32_t)buf * 8u); else mbar_arrive(&tmem_empty_bar[buf]);
+              }
             }
 #pragma unroll
             for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
@@ -293,32 +345,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (j == my_nch - 1) {
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+              if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(tempty0 + (uint32_t)buf * 8u); else mbar_arrive(&tmem_empty_bar[buf]);
+              }
             }
             // GEGLU: accumulator columns [c*64, +32) are "value", [c*64+32, +64) the matching "gate"
             const int col0 = n0 + c * 64;
+            if (p.row_stats_in) {            // folded LayerNorm (own pass under a uniform branch: no predicated filler)
+              const float4* sa = reinterpret_cast<const float4*>(p.ln_colsum + col0);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float4 t1 = __ldg(sa + k), t2 = __ldg(sa + 8 + k);
+                v[4 * k] = __float_as_uint(fmaf(__uint_as_float(v[4 * k]), rstd, nmr * t1.x));
+                v[4 * k + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * k + 1]), rstd, nmr * t1.y));
+                v[4 * k + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * k + 2]), rstd, nmr * t1.z));
+                v[4 * k + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * k + 3]), rstd, nmr * t1.w));
+                vg[4 * k] = __float_as_uint(fmaf(__uint_as_float(vg[4 * k]), rstd, nmr * t2.x));
+                vg[4 * k + 1] = __float_as_uint(fmaf(__uint_as_float(vg[4 * k + 1]), rstd, nmr * t2.y));
+                vg[4 * k + 2] = __float_as_uint(fmaf(__uint_as_float(vg[4 * k + 2]), rstd, nmr * t2.z));
+                vg[4 * k + 3] = __float_as_uint(fmaf(__uint_as_float(vg[4 * k + 3]), rstd, nmr * t2.w));
+              }
+            }
             const float4* ba = reinterpret_cast<const float4*>(bias_row + col0);
-            const float4* bg = reinterpret_cast<const float4*>(bias_row + col0 + 32);
-            const float4* sa = reinterpret_cast<const float4*>(p.ln_colsum + col0);
-            const float4* sg = reinterpret_cast<const float4*>(p.ln_colsum + col0 + 32);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              float a[4] = {__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
-                            __uint_as_float(v[4 * k + 3])};
-              float gt[4] = {__uint_as_float(vg[4 * k]), __uint_as_float(vg[4 * k + 1]), __uint_as_float(vg[4 * k + 2]),
-                             __uint_as_float(vg[4 * k + 3])};
-              if (p.row_stats_in) {
-                const float4 t1 = __ldg(sa + k), t2 = __ldg(sg + k);
-                a[0] = fmaf(a[0], rstd, nmr * t1.x); a[1] = fmaf(a[1], rstd, nmr * t1.y);
-                a[2] = fmaf(a[2], rstd, nmr * t1.z); a[3] = fmaf(a[3], rstd, nmr * t1.w);
-                gt[0] = fmaf(gt[0], rstd, nmr * t2.x); gt[1] = fmaf(gt[1], rstd, nmr * t2.y);
-                gt[2] = fmaf(gt[2], rstd, nmr * t2.z); gt[3] = fmaf(gt[3], rstd, nmr * t2.w);
-              }
-              const float4 b1 = __ldg(ba + k), b2 = __ldg(bg + k);
-              f[4 * k] = (a[0] + b1.x) * gelu_erf_fast(gt[0] + b2.x);
-              f[4 * k + 1] = (a[1] + b1.y) * gelu_erf_fast(gt[1] + b2.y);
-              f[4 * k + 2] = (a[2] + b1.z) * gelu_erf_fast(gt[2] + b2.z);
-              f[4 * k + 3] = (a[3] + b1.w) * gelu_erf_fast(gt[3] + b2.w);
+              const float4 b1 = __ldg(ba + k), b2 = __ldg(ba + 8 + k);
+              f[4 * k] = (__uint_as_float(v[4 * k]) + b1.x) * gelu_erf_fast(__uint_as_float(vg[4 * k]) + b2.x);
+              f[4 * k + 1] = (__uint_as_float(v[4 * k + 1]) + b1.y) * gelu_erf_fast(__uint_as_float(vg[4 * k + 1]) + b2.y);
+              f[4 * k + 2] = (__uint_as_float(v[4 * k + 2]) + b1.z) * gelu_erf_fast(__uint_as_float(vg[4 * k + 2]) + b2.z);
+              f[4 * k + 3] = (__uint_as_float(v[4 * k + 3]) + b1.w) * gelu_erf_fast(__uint_as_float(vg[4 * k + 3]) + b2.w);
             }
           }
         }
@@ -390,7 +445,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             cq = fmaf(t, t, cq);
           }
           if (row0 < p.M)
-            reinterpret_cast<float2*>(p.col_stats)[(size_t)(mb * 4 + q) * p.N + ocol + lane] = make_float2(cs, cq);
+            reinterpret_cast<float2*>(p.col_stats)[(size_t)(row0 >> 5) * p.N + ocol + lane] = make_float2(cs, cq);
         }
       }
       if (p.row_stats_out && row_ok)
@@ -400,10 +455,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: the peer may still arrive on / read this CTA's smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -480,7 +536,7 @@ static int num_sms() {
 }
 
 struct Plan {
-  int bn, stages, nepi, ring, slot_bytes, res_off, outf_off, outh_off, tiles_n, num_tiles, grid, smem_bytes;
+  int bn, cg, stages, nepi, ring, slot_bytes, res_off, outf_off, outh_off, tiles_n, num_tiles, grid, smem_bytes;
 };
 
 static int env_int(const char* name, int dflt) {
@@ -490,8 +546,20 @@ static int env_int(const char* name, int dflt) {
 
 static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   const int N = d.N;
-  const int tiles_m = ceil_div(d.M, BM);
-  const int nsm = num_sms();
+  // CTA pairs (cta_group::2, 256-row tiles) for tensor-bound launches: they halve the Wt bytes each SM pulls from L2
+  // per FLOP (measured +15..25 % on K >= 1280 GEMMs); HBM-bound launches (small K, fp32 residual + output) run a
+  // little better as independent 128-row CTAs.  Crude roofline estimate with the measured peaks (profiles/).
+  const double Kd = d.X ? 9.0 * d.Cin + d.K2 : (double)d.K1 + d.K2;
+  const double n_out = d.geglu ? N / 2 : N;
+  const double bytes = (double)d.M * (d.X ? d.Cin + d.K2 : Kd) * 2 + (double)N * Kd * 2 +
+                       (double)d.M * n_out * ((d.out_f32 ? 4 : 0) + (d.out_bf16 ? 2 : 0) + (d.residual ? (d.residual_bf16 ? 2 : 4) : 0));
+  const double t_mem = bytes / 5.5e12, t_mma = 2.0 * d.M * N * Kd / 1.6e15;
+  int cg = (d.M > BM && t_mma > t_mem) ? 2 : 1;
+  const int fcg = env_int("SEER_GEMM_CG", 0);      // tuning hook
+  if (fcg == 1 || fcg == 2) cg = fcg;
+  pl.cg = cg;
+  const int tiles_m = ceil_div(d.M, BM * cg);
+  const int nsm = num_sms() / cg;                  // scheduling units: CTAs or CTA pairs
   // tile width: the widest BN that divides N, unless a narrower one fills the SMs with fewer rounds of tiles
   static const int cand_plain[] = {256, 192, 160, 128, 64};
   static const int cand_geglu[] = {256, 128};
@@ -517,7 +585,7 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   pl.bn = best;
   pl.tiles_n = N / best;
   pl.num_tiles = tiles_m * pl.tiles_n;
-  pl.grid = pl.num_tiles < nsm ? pl.num_tiles : nsm;
+  pl.grid = (pl.num_tiles < nsm ? pl.num_tiles : nsm) * cg;
   // slot layout
   const bool of = d.out_f32 != nullptr, oh = d.out_bf16 != nullptr;
   const int rm = d.residual ? (d.residual_bf16 ? 2 : 1) : 0;
@@ -537,7 +605,7 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   pl.nepi = env_int("SEER_GEMM_NEPI", d.geglu ? 8 : 4);
   if (pl.nepi != 4 && pl.nepi != 8) pl.nepi = 4;
   if (best / (d.geglu ? 64 : 32) < 2) pl.nepi = 4;   // every epilogue warp needs at least one chunk
-  const int stage_bytes = A_BYTES + best * BK * 2;
+  const int stage_bytes = A_BYTES + (best / cg) * BK * 2;
   const int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - BAR_BYTES;
   pl.ring = 4;
   pl.stages = (avail - pl.nepi * pl.ring * pl.slot_bytes) / stage_bytes;
@@ -559,17 +627,35 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   return SEER_OK;
 }
 
-template <int BN>
+template <int BN, int CG>
 static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, const Plan& pl, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  gemm_tc_kernel<BN><<<pl.grid, 64 + 32 * pl.nepi, pl.smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(pl.grid);
+  cfg.blockDim = dim3(64 + 32 * pl.nepi);
+  cfg.dynamicSmemBytes = pl.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  if (e != cudaSuccess) return (int)e;
   SEER_LAUNCH_CHECK();
   return SEER_OK;
+}
+
+template <int BN>
+static int launch_gemm_cg(const CUtensorMap* maps, const GemmParams& p, const Plan& pl, cudaStream_t stream) {
+  return pl.cg == 2 ? launch_gemm<BN, 2>(maps, p, pl, stream) : launch_gemm<BN, 1>(maps, p, pl, stream);
 }
 
 static int check_desc(const SeerGemmDesc& d) {
@@ -656,7 +742,7 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   p.kb_total = Ktot / 64;
   p.ln_inv_dim = 1.0f / (float)(d.X ? 1 : d.K1);
   if (d.K2) { if ((rc = make_map_bf16_k64(&maps[1], d.A2, d.M, d.K2, d.lda2, BM))) return rc; } else maps[1] = maps[0];
-  if ((rc = make_map_bf16_k64(&maps[2], d.Wt, d.N, Ktot, Ktot, pl.bn))) return rc;
+  if ((rc = make_map_bf16_k64(&maps[2], d.Wt, d.N, Ktot, Ktot, pl.bn / pl.cg))) return rc;
   const int n_out = d.geglu ? d.N / 2 : d.N;
   maps[3] = maps[0]; maps[4] = maps[0]; maps[5] = maps[0];
   if (d.residual) {
@@ -675,11 +761,11 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
 
   cudaStream_t st = (cudaStream_t)stream;
   switch (pl.bn) {
-    case 64: return launch_gemm<64>(maps, p, pl, st);
-    case 128: return launch_gemm<128>(maps, p, pl, st);
-    case 160: return launch_gemm<160>(maps, p, pl, st);
-    case 192: return launch_gemm<192>(maps, p, pl, st);
-    case 256: return launch_gemm<256>(maps, p, pl, st);
+    case 64: return launch_gemm_cg<64>(maps, p, pl, st);
+    case 128: return launch_gemm_cg<128>(maps, p, pl, st);
+    case 160: return launch_gemm_cg<160>(maps, p, pl, st);
+    case 192: return launch_gemm_cg<192>(maps, p, pl, st);
+    case 256: return launch_gemm_cg<256>(maps, p, pl, st);
     default: return SEER_EUNSUPPORTED;
   }
 }

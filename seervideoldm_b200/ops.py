@@ -41,6 +41,19 @@ class _Timed:
         return False
 
 
+def _timed_op(fn):
+    """Decorator: CUDA-event timing of a (non-GEMM) op while ops.PROFILE is a list (bench / tools only)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        if PROFILE is None:
+            return fn(*a, **k)
+        with _Timed(fn.__name__, 0.0):
+            return fn(*a, **k)
+    return wrapper
+
+
 def _count(n: int = 1) -> None:
     global LAUNCHES
     LAUNCHES += n
@@ -189,7 +202,7 @@ def gemm(a: torch.Tensor, wt: torch.Tensor, *, a2: Optional[torch.Tensor] = None
 
 def conv3x3_ex(x: torch.Tensor, wt: torch.Tensor, **kw) -> GemmOut:
     """Frame-wise 3x3 conv (stride 1, pad 1).  x:[n_img,H,W,Cin] bf16 contiguous; wt:[Cout, 9*Cin (+K2)] bf16 with
-    K order [ky][kx][Cin]; result rows [n_img*H*W, Cout].  Falls back to im2col + GEMM (still seer_b200 kernels) for
+    K order [Cin/64][ky][kx][64] (packing.pack_conv3x3); result rows [n_img*H*W, Cout].  Falls back to im2col + GEMM (still seer_b200 kernels) for
     image sizes the TMA-box tiling does not cover."""
     r = gemm_ex(None, wt, x_img=x, **kw)
     if r is None:
@@ -206,6 +219,7 @@ def conv3x3(x: torch.Tensor, wt: torch.Tensor, *, a2: Optional[torch.Tensor] = N
     return conv3x3_ex(x, wt, a2=a2, bias=bias, bias_div=bias_div, residual=residual, out=out, out_dtype=out_dtype).out
 
 
+@_timed_op
 def groupnorm(x1: torch.Tensor, x2: Optional[torch.Tensor], B: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
               silu: bool, out_dtype: torch.dtype = torch.bfloat16, want_raw: bool = False,
               stats1: Optional[torch.Tensor] = None, stats2: Optional[torch.Tensor] = None):
@@ -252,6 +266,7 @@ def groupnorm(x1: torch.Tensor, x2: Optional[torch.Tensor], B: int, gamma: torch
     return (y, raw) if want_raw else y
 
 
+@_timed_op
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _req(x, torch.float32, "x", 2)
@@ -264,6 +279,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
+@_timed_op
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, mode: int, heads: int, n_outer: int, Lq: int = 0,
               Lk: int = 0, F: int = 0, H: int = 0, W: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q/k/v: 2-D bf16 token-major views [rows, heads*d] (column slices of wider buffers are fine)."""
@@ -290,6 +306,7 @@ def scta_row_index(B: int, F: int, H: int, W: int, device="cuda") -> torch.Tenso
     return out
 
 
+@_timed_op
 def rope_inplace(qkv: torch.Tensor, tokens_per_clip: int, heads: int, head_dim: int, q_col: int, k_col: int,
                  freqs: torch.Tensor) -> None:
     _req(qkv, torch.bfloat16, "qkv", 2); _req(freqs, torch.float32, "freqs", 1)
@@ -299,6 +316,7 @@ def rope_inplace(qkv: torch.Tensor, tokens_per_clip: int, heads: int, head_dim: 
     _count()
 
 
+@_timed_op
 def timestep_embedding(t: torch.Tensor, dim: int, shift: float, flip_sin_to_cos: bool) -> torch.Tensor:
     _req(t, torch.float32, "t", 1)
     out = torch.empty((t.numel(), dim), device=t.device, dtype=torch.float32)
@@ -308,6 +326,7 @@ def timestep_embedding(t: torch.Tensor, dim: int, shift: float, flip_sin_to_cos:
     return out
 
 
+@_timed_op
 def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], add: Optional[torch.Tensor] = None,
                  silu_in: bool = False, silu_out: bool = False) -> torch.Tensor:
     _req(x, torch.float32, "x", 2); _req(w, torch.float32, "w", 2)
@@ -321,6 +340,7 @@ def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
     return out
 
 
+@_timed_op
 def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """x:(B,4,F,H,W) fp32 -> [B*F*H*W, Cout] fp32."""
     _req(x, torch.float32, "x", 5)
@@ -335,6 +355,7 @@ def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tenso
     return out
 
 
+@_timed_op
 def conv_out(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, B: int, F: int, H: int, W: int) -> torch.Tensor:
     """x:[B*F*H*W, Cin] fp32 -> (B,Cout,F,H,W) fp32."""
     _req(x, torch.float32, "x", 2)
@@ -347,6 +368,7 @@ def conv_out(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, B: int
     return out
 
 
+@_timed_op
 def upsample2x(x: torch.Tensor, n_img: int, H: int, W: int) -> torch.Tensor:
     """x:[n_img*H*W, C] fp32 -> [n_img, 2H, 2W, C] bf16."""
     _req(x, torch.float32, "x", 2)
@@ -358,6 +380,7 @@ def upsample2x(x: torch.Tensor, n_img: int, H: int, W: int) -> torch.Tensor:
     return y
 
 
+@_timed_op
 def im2col3x3(x: torch.Tensor, stride: int) -> torch.Tensor:
     """x:[n_img,H,W,C] fp32 or bf16 -> [n_img*(H/s)*(W/s), 9*C] bf16."""
     if x.dim() != 4 or not x.is_contiguous() or not x.is_cuda:
@@ -370,6 +393,7 @@ def im2col3x3(x: torch.Tensor, stride: int) -> torch.Tensor:
     return y
 
 
+@_timed_op
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     _req(x, torch.float32, "x")
     if not x.is_contiguous():
@@ -381,6 +405,7 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+@_timed_op
 def cfg_ddim_update(eps: torch.Tensor, x: torch.Tensor, cond_f: int, use_cfg: bool, scale: float, sqrt_one_minus_at: float,
                     sqrt_at: float, sqrt_a_prev: float, dir_coef: float, x_prev: Optional[torch.Tensor] = None,
                     pred_x0: Optional[torch.Tensor] = None):

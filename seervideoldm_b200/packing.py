@@ -23,10 +23,13 @@ def pack_conv1x1(w: torch.Tensor) -> torch.Tensor:
 
 
 def pack_conv3x3(w: torch.Tensor, shortcut: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """[Cout, Cin, 3, 3] -> [Cout, 9*Cin] bf16 with K order [ky][kx][Cin] (one K-block per (tap, 64 channels));
-    an optional 1x1 shortcut weight [Cout, Csc, 1, 1] is appended along K (fused ResNet shortcut)."""
+    """[Cout, Cin, 3, 3] -> [Cout, 9*Cin] bf16 with K order [Cin/64][ky][kx][64] (one K-block per (64-channel slab, tap),
+    the 9 taps of a slab adjacent so the implicit-GEMM conv re-reads a slab while it is hot in L2); an optional 1x1
+    shortcut weight [Cout, Csc, 1, 1] is appended along K (fused ResNet shortcut)."""
     cout, cin = w.shape[:2]
-    p = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    if cin % 64:
+        raise ValueError("pack_conv3x3: Cin must be a multiple of 64")
+    p = w.permute(0, 2, 3, 1).reshape(cout, 9, cin // 64, 64).permute(0, 2, 1, 3).reshape(cout, 9 * cin)
     if shortcut is not None:
         p = torch.cat([p, shortcut.reshape(cout, -1)], dim=1)
     return p.to(torch.bfloat16).contiguous()
@@ -58,3 +61,24 @@ def pack_qkv(wq: torch.Tensor, wk: torch.Tensor, wv: torch.Tensor) -> torch.Tens
 
 def pack_kv(wk: torch.Tensor, wv: torch.Tensor) -> torch.Tensor:
     return torch.cat([wk, wv], dim=0).to(torch.bfloat16).contiguous()
+
+
+def fold_layernorm(w: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
+                   geglu: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Fold LayerNorm(gamma, beta) into the Linear(w [N, C], b) that consumes it:
+
+        Linear(LN(x)) = rstd * (x @ (w*gamma).T - mean * colsum) + (w @ beta + b),   colsum[n] = sum_k (w*gamma)[n, k]
+
+    so the GEMM runs on the RAW activations and applies the per-row (mean, rstd) in its epilogue (SeerGemmDesc LN fold;
+    reference: attention.py:237,244,311,322-323 apply nn.LayerNorm in front of attn1 / attn2 / ff).  Returns
+    (w*gamma as bf16, colsum fp32 of the ROUNDED weights, folded bias fp32); rows in GEGLU block order if `geglu`."""
+    w = w.float()
+    wf = w * gamma.float()[None, :]
+    bias = w @ beta.float()
+    if b is not None:
+        bias = bias + b.float()
+    if geglu:
+        perm = geglu_permutation(w.shape[0] // 2, device=w.device)
+        wf, bias = wf[perm], bias[perm]
+    w16 = wf.to(torch.bfloat16).contiguous()
+    return w16, w16.float().sum(1).contiguous(), bias.contiguous()

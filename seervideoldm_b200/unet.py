@@ -10,7 +10,7 @@ whole forward runs on hand-written sm_100a kernels in one canonical channels-las
 Data layout in HBM (per evaluation, B = UNet batch after CFG):
   * residual stream   fp32 [B*F*h*w, C]            (GroupNorm/LayerNorm inputs, skip connections)
   * GEMM/conv operands bf16, same token-major shape (normalised activations, q/k/v, FF hidden)
-  * packed weights    bf16 [N, K] K-major           (conv3x3: K = [ky][kx][Cin] (+ fused 1x1 shortcut))
+  * packed weights    bf16 [N, K] K-major           (conv3x3: K = [Cin/64][ky][kx][64] (+ fused 1x1 shortcut))
   * text K/V          bf16 [B*F*77, 2C] per cross-attention layer, cached across the 31 DDIM steps
 """
 from __future__ import annotations
@@ -201,17 +201,19 @@ class SeerUNet(nn.Module):
             t["gn_g"], t["gn_b"] = f32(prefix + "norm.weight"), f32(prefix + "norm.bias")
             t["pin_w"], t["pin_b"] = packing.pack_conv1x1(P(prefix + "proj_in.weight")), f32(prefix + "proj_in.bias")
             t["pout_w"], t["pout_b"] = packing.pack_conv1x1(P(prefix + "proj_out.weight")), f32(prefix + "proj_out.bias")
-            t["ln1_g"], t["ln1_b"] = f32(b + "norm1.weight"), f32(b + "norm1.bias")
-            t["ln3_g"], t["ln3_b"] = f32(b + "norm3.weight"), f32(b + "norm3.bias")
-            t["qkv_w"] = packing.pack_qkv(P(b + "attn1.to_q.weight"), P(b + "attn1.to_k.weight"), P(b + "attn1.to_v.weight"))
+            # LayerNorms are folded into the GEMM that consumes them (packing.fold_layernorm): weights carry gamma,
+            # the bias carries beta @ W.T and the epilogue applies the per-row mean / rstd (SeerGemmDesc, LN fold).
+            wqkv = torch.cat([P(b + "attn1.to_q.weight"), P(b + "attn1.to_k.weight"), P(b + "attn1.to_v.weight")], 0)
+            t["qkv_w"], t["qkv_cs"], t["qkv_b"] = packing.fold_layernorm(wqkv, None, P(b + "norm1.weight"), P(b + "norm1.bias"))
             t["o1_w"], t["o1_b"] = packing.pack_linear(P(b + "attn1.to_out.0.weight")), f32(b + "attn1.to_out.0.bias")
-            t["ff1_w"], t["ff1_b"] = packing.pack_geglu(P(b + "ff.net.0.proj.weight"), P(b + "ff.net.0.proj.bias"))
+            t["ff1_w"], t["ff1_cs"], t["ff1_b"] = packing.fold_layernorm(P(b + "ff.net.0.proj.weight"), P(b + "ff.net.0.proj.bias"),
+                                                                         P(b + "norm3.weight"), P(b + "norm3.bias"), geglu=True)
             t["ff2_w"], t["ff2_b"] = packing.pack_linear(P(b + "ff.net.2.weight")), f32(b + "ff.net.2.bias")
             if temporal:
                 t["freqs"] = f32(b + "attn1.rotary_emb.freqs")
             else:
-                t["ln2_g"], t["ln2_b"] = f32(b + "norm2.weight"), f32(b + "norm2.bias")
-                t["q2_w"] = packing.pack_linear(P(b + "attn2.to_q.weight"))
+                t["q2_w"], t["q2_cs"], t["q2_b"] = packing.fold_layernorm(P(b + "attn2.to_q.weight"), None, P(b + "norm2.weight"),
+                                                                          P(b + "norm2.bias"))
                 t["kv2_w"] = packing.pack_kv(P(b + "attn2.to_k.weight"), P(b + "attn2.to_v.weight"))
                 t["o2_w"], t["o2_b"] = packing.pack_linear(P(b + "attn2.to_out.0.weight")), f32(b + "attn2.to_out.0.bias")
             return t
@@ -251,39 +253,46 @@ class SeerUNet(nn.Module):
 
     # ------------------------------------------------------------------ operators
     def _resnet(self, r: dict, x1, x2, B, F, H, W, temb_all):
-        """ResnetBlock3D.forward (resnet.py:174-208) on the virtual concat [x1 | x2]."""
+        """ResnetBlock3D.forward (resnet.py:174-208) on the virtual concat [x1 | x2].  Activations travel as
+        (tensor, col_stats) pairs: the GEMM that produced a tensor also emitted the per-channel partial sums the next
+        GroupNorm needs, so no statistics pass re-reads the activation."""
         T = F * H * W
         eps = self.cfg.norm_eps
         cin, cout = r["cin"], r["cout"]
+        (t1, s1), (t2, s2) = x1, (x2 if x2 is not None else (None, None))
         if r["sc"]:
-            h, raw = ops.groupnorm(x1, x2, B, r["g1"], r["b1"], eps, True, want_raw=True)
+            h, raw = ops.groupnorm(t1, t2, B, r["g1"], r["b1"], eps, True, want_raw=True, stats1=s1, stats2=s2)
         else:
-            if x2 is not None:
+            if t2 is not None:
                 raise RuntimeError("concat input without a shortcut conv cannot occur in this architecture")
-            h, raw = ops.groupnorm(x1, None, B, r["g1"], r["b1"], eps, True), None
+            h, raw = ops.groupnorm(t1, None, B, r["g1"], r["b1"], eps, True, stats1=s1), None
         tb = temb_all[:, r["off"]: r["off"] + cout]
-        h1 = ops.conv3x3(h.view(B * F, H, W, cin), r["w1"], bias=tb, bias_div=T)
-        h2 = ops.groupnorm(h1, None, B, r["g2"], r["b2"], eps, True)
+        c1 = ops.conv3x3_ex(h.view(B * F, H, W, cin), r["w1"], bias=tb, bias_div=T, col_stats=True)
+        h2 = ops.groupnorm(c1.out, None, B, r["g2"], r["b2"], eps, True, stats1=c1.col_stats)
         if r["sc"]:
-            return ops.conv3x3(h2.view(B * F, H, W, cout), r["w2"], a2=raw, bias=r["bias2"])
-        return ops.conv3x3(h2.view(B * F, H, W, cout), r["w2"], bias=r["bias2"], residual=x1)
+            c2 = ops.conv3x3_ex(h2.view(B * F, H, W, cout), r["w2"], a2=raw, bias=r["bias2"], col_stats=True)
+        else:
+            c2 = ops.conv3x3_ex(h2.view(B * F, H, W, cout), r["w2"], bias=r["bias2"], residual=t1, col_stats=True)
+        return c2.out, c2.col_stats
 
-    def _ff(self, t: dict, tok, out_rows=None):
-        """x + FF(LN3(x)) -> bf16 (feeds proj_out only).  attention.py:244,323 + 744-747,791-793."""
-        n3 = ops.layernorm(tok, t["ln3_g"], t["ln3_b"])
-        hid = ops.gemm(n3, t["ff1_w"], bias=t["ff1_b"], geglu=True)
-        return ops.gemm(hid, t["ff2_w"], bias=t["ff2_b"], residual=tok, out=out_rows, out_dtype=torch.bfloat16)
+    def _ff(self, t: dict, tok, tok16, rstats, out_rows=None):
+        """x + FF(LN3(x)) -> bf16 (feeds proj_out only).  attention.py:244,323 + 744-747,791-793.  LN3 is folded into
+        the GEGLU projection, which reads the raw bf16 copy of the token stream."""
+        hid = ops.gemm_ex(tok16, t["ff1_w"], bias=t["ff1_b"], geglu=True, ln=(rstats, t["ff1_cs"], 1e-5)).out
+        return ops.gemm_ex(hid, t["ff2_w"], bias=t["ff2_b"], residual=tok, out=out_rows, out_dtype=torch.bfloat16).out
 
     def _transformer(self, t: dict, x, B, F, H, W, kv, cond_frame):
-        """SpatialTransformer3D.forward (attention.py:129-145) with its text (:308-327) or temporal (:231-248) block."""
+        """SpatialTransformer3D.forward (attention.py:129-145) with its text (:308-327) or temporal (:231-248) block.
+        Token stream: fp32 master copy + bf16 copy + per-row (sum, sumsq), all written by the producing GEMM's epilogue."""
         C, heads = t["C"], self.cfg.heads
         d = C // heads
         hw, T = H * W, F * H * W
         M = B * T
-        hn = ops.groupnorm(x, None, B, t["gn_g"], t["gn_b"], 1e-6, False)
-        tok = ops.gemm(hn, t["pin_w"], bias=t["pin_b"])                                   # fp32 token stream
-        n1 = ops.layernorm(tok, t["ln1_g"], t["ln1_b"])
-        qkv = ops.gemm(n1, t["qkv_w"], out_dtype=torch.bfloat16)                          # [M, 3C]
+        xt, xs = x
+        hn = ops.groupnorm(xt, None, B, t["gn_g"], t["gn_b"], 1e-6, False, stats1=xs)
+        r = ops.gemm_ex(hn, t["pin_w"], bias=t["pin_b"], also_bf16=True, row_stats=True)          # fp32 token stream
+        qkv = ops.gemm_ex(r.out16, t["qkv_w"], bias=t["qkv_b"], out_dtype=torch.bfloat16,
+                          ln=(r.row_stats, t["qkv_cs"], 1e-5)).out                                 # [M, 3C]
         if t["temporal"]:
             ops.rope_inplace(qkv, T, heads, d, 0, C, t["freqs"])
             att = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], mode=ops.ATTN_SCTA, heads=heads, n_outer=B,
@@ -291,25 +300,26 @@ class SeerUNet(nn.Module):
         else:
             att = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], mode=ops.ATTN_SPATIAL, heads=heads,
                                 n_outer=B * F, Lq=hw, Lk=hw)
-        tok = ops.gemm(att, t["o1_w"], bias=t["o1_b"], residual=tok)
+        r = ops.gemm_ex(att, t["o1_w"], bias=t["o1_b"], residual=r.out, also_bf16=True, row_stats=True)
         if not t["temporal"]:
-            n2 = ops.layernorm(tok, t["ln2_g"], t["ln2_b"])
-            q2 = ops.gemm(n2, t["q2_w"], out_dtype=torch.bfloat16)
+            q2 = ops.gemm_ex(r.out16, t["q2_w"], bias=t["q2_b"], out_dtype=torch.bfloat16, ln=(r.row_stats, t["q2_cs"], 1e-5)).out
             Lk = kv.shape[0] // (B * F)
             att2 = ops.attention(q2, kv[:, :C], kv[:, C:], mode=ops.ATTN_CROSS, heads=heads, n_outer=B * F, Lq=hw, Lk=Lk)
-            tok = ops.gemm(att2, t["o2_w"], bias=t["o2_b"], residual=tok)
+            r = ops.gemm_ex(att2, t["o2_w"], bias=t["o2_b"], residual=r.out, also_bf16=True, row_stats=True)
+        tok, tok16, rstats = r.out, r.out16, r.row_stats
         if t["temporal"] and cond_frame > 0:
             # the first cond_frame frames of every clip bypass the feed-forward (attention.py:240-246)
-            y = torch.empty((M, C), device=x.device, dtype=torch.bfloat16)
+            y = torch.empty((M, C), device=xt.device, dtype=torch.bfloat16)
             c0 = min(cond_frame, F) * hw
             for b in range(B):
                 lo, mid, hi = b * T, b * T + c0, (b + 1) * T
-                y[lo:mid] = ops.cast_bf16(tok[lo:mid].contiguous())
+                y[lo:mid] = tok16[lo:mid]
                 if mid < hi:
-                    self._ff(t, tok[mid:hi], out_rows=y[mid:hi])
+                    self._ff(t, tok[mid:hi], tok16[mid:hi], rstats[:, mid:hi].contiguous(), out_rows=y[mid:hi])
         else:
-            y = self._ff(t, tok)
-        return ops.gemm(y, t["pout_w"], bias=t["pout_b"], residual=x)
+            y = self._ff(t, tok, tok16, rstats)
+        o = ops.gemm_ex(y, t["pout_w"], bias=t["pout_b"], residual=xt, col_stats=True)
+        return o.out, o.col_stats
 
     def _cross_layers(self, pk: dict) -> List[dict]:
         return [a for blk in pk["down"] for a in blk["attn"]] + [pk["mid"]["attn"]] + [a for blk in pk["up"] for a in blk["attn"]]
@@ -374,9 +384,9 @@ class SeerUNet(nn.Module):
         kvs = iter(self._context_kv(pk, context.to(dev)))
 
         # 2. conv_in -> token-major fp32 stream
-        x = ops.conv_in(sample.contiguous(), pk["conv_in_w"], pk["conv_in_b"])
+        x = (ops.conv_in(sample.contiguous(), pk["conv_in_w"], pk["conv_in_b"]), None)     # (tensor, GroupNorm col_stats)
         h, w = H, W
-        skips: List[torch.Tensor] = [x]
+        skips: List[tuple] = [x]
         n = len(cfg.block_out_channels)
         # 3. down
         for i, blk in enumerate(pk["down"]):
@@ -388,8 +398,9 @@ class SeerUNet(nn.Module):
                 skips.append(x)
             if blk["down"] is not None:
                 wd, bd = blk["down"]
-                cols = ops.im2col3x3(x.view(B * F, h, w, x.shape[1]), stride=2)
-                x = ops.gemm(cols, wd, bias=bd)
+                cols = ops.im2col3x3(x[0].view(B * F, h, w, x[0].shape[1]), stride=2)
+                dn = ops.gemm_ex(cols, wd, bias=bd, col_stats=True)
+                x = (dn.out, dn.col_stats)
                 h, w = h // 2, w // 2
                 skips.append(x)
         # 4. mid
@@ -407,9 +418,10 @@ class SeerUNet(nn.Module):
                     x = self._transformer(blk["tattn"][j], x, B, F, h, w, None, cond_frame)
             if blk["up"] is not None:
                 wu, bu = blk["up"]
-                up = ops.upsample2x(x, B * F, h, w)
+                up = ops.upsample2x(x[0], B * F, h, w)
                 h, w = 2 * h, 2 * w
-                x = ops.conv3x3(up, wu, bias=bu)
+                uc = ops.conv3x3_ex(up, wu, bias=bu, col_stats=True)
+                x = (uc.out, uc.col_stats)
         # 6. out: GN -> SiLU -> conv_out, fp32, back to (B, C, F, H, W)
-        y = ops.groupnorm(x, None, B, pk["gno_g"], pk["gno_b"], cfg.norm_eps, True, out_dtype=torch.float32)
+        y = ops.groupnorm(x[0], None, B, pk["gno_g"], pk["gno_b"], cfg.norm_eps, True, out_dtype=torch.float32, stats1=x[1])
         return ops.conv_out(y, pk["conv_out_w"], pk["conv_out_b"], B, F, h, w)

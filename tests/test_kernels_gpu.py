@@ -236,11 +236,13 @@ def test_conv3x3_generic_fallback_and_stride2():
     out = ops.conv3x3(x, pack_conv3x3(w).to(DEV))
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), None, padding=1).permute(0, 2, 3, 1).reshape(-1, 160)
     assert rel(out, ref) < 2e-5
-    xf = rn(30, 3, 16, 16, 64)
-    cols = ops.im2col3x3(xf.reshape(3, 16, 16, 64), stride=2)
-    out = ops.gemm(cols, pack_conv3x3(w).to(DEV))
-    ref = F.conv2d(xf.bfloat16().float().permute(0, 3, 1, 2), w.bfloat16().float(), None, stride=2, padding=1)
-    assert rel(out, ref.permute(0, 2, 3, 1).reshape(-1, 160)) < 2e-5
+    for C in (64, 192):                            # stride-2 im2col (Downsample3D); 192 = three 64-channel K slabs
+        xf = rn(30, 3, 16, 16, C)
+        w2 = rn(31, 160, C, 3, 3, scale=(9 * C) ** -0.5)
+        cols = ops.im2col3x3(xf.reshape(3, 16, 16, C), stride=2)
+        out = ops.gemm(cols, pack_conv3x3(w2).to(DEV))
+        ref = F.conv2d(xf.bfloat16().float().permute(0, 3, 1, 2), w2.bfloat16().float(), None, stride=2, padding=1)
+        assert rel(out, ref.permute(0, 2, 3, 1).reshape(-1, 160)) < 2e-5
 
 
 # ------------------------------------------------------------------------------------------------ norms

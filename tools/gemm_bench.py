@@ -89,7 +89,10 @@ def main():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--out", default=None)
     ap.add_argument("--only", default=None, help="comma-separated substrings: run only the shapes whose name contains one")
+    ap.add_argument("--cg", type=int, default=0, help="force CTA-group size 1 or 2 (tuning hook SEER_GEMM_CG)")
     args = ap.parse_args()
+    if args.cg:
+        os.environ["SEER_GEMM_CG"] = str(args.cg)
     flush = torch.empty(256 * 1024 * 1024, device=DEV, dtype=torch.uint8)
     rows = []
     for name, cfg in shapes():
