@@ -34,10 +34,12 @@ constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_EPI_WARPS = 8;
-constexpr int MAX_RING = 4;
+constexpr int MAX_RING = 8;
 constexpr int GEMM_MAX_THREADS = 64 + 32 * MAX_EPI_WARPS;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 1024;
+constexpr int EVEC_FLOATS = 256;                       // per-warp staging of the tile's bias / LN column-sum slices (BN <= 256)
+constexpr int EVEC_BYTES_PER_WARP = 2 * EVEC_FLOATS * 4;
 
 struct GemmParams {
   int M, N;            // N = accumulator columns (GEGLU: twice the output columns)
@@ -47,7 +49,8 @@ struct GemmParams {
   int cblk;            // conv: Cin / 64
   int H, W;            // conv image geometry
   int tiles_n, num_tiles;
-  int stages, nepi, ring, slot_bytes;
+  int stages, nepi, ring, prefetch, slot_bytes;
+  int alias_sync;
   int res_off, outf_off, outh_off;   // byte offsets of the residual / fp32-out / bf16-out regions inside a slot
   const float* bias;
   int ldb;
@@ -78,6 +81,40 @@ struct GemmCfg {
 __device__ __forceinline__ int sw128(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
 __device__ __forceinline__ int sw64(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
 
+// v = rstd * (v - mean * colsum[col]) + bias[col]   (folded LayerNorm and/or bias) on one 32-column accumulator chunk.
+// `cs` / `b` point at this chunk's slices (shared memory on the fast path).
+template <bool LN, bool BIAS, bool SMEM>
+__device__ __forceinline__ void epi_affine32(uint32_t (&v)[32], const float* cs, const float* b, float rstd, float neg_mean) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (LN) c4 = lds128(cs + 4 * k);
+    if (BIAS) b4 = SMEM ? lds128(b + 4 * k) : __ldg(reinterpret_cast<const float4*>(b) + k);
+    float x0 = __uint_as_float(v[4 * k]), x1 = __uint_as_float(v[4 * k + 1]), x2 = __uint_as_float(v[4 * k + 2]),
+          x3 = __uint_as_float(v[4 * k + 3]);
+    if (LN) {
+      x0 = fmaf(rstd, fmaf(neg_mean, c4.x, x0), b4.x); x1 = fmaf(rstd, fmaf(neg_mean, c4.y, x1), b4.y);
+      x2 = fmaf(rstd, fmaf(neg_mean, c4.z, x2), b4.z); x3 = fmaf(rstd, fmaf(neg_mean, c4.w, x3), b4.w);
+    } else if (BIAS) {
+      x0 += b4.x; x1 += b4.y; x2 += b4.z; x3 += b4.w;
+    }
+    v[4 * k] = __float_as_uint(x0); v[4 * k + 1] = __float_as_uint(x1);
+    v[4 * k + 2] = __float_as_uint(x2); v[4 * k + 3] = __float_as_uint(x3);
+  }
+}
+// cs always points into shared memory; b into shared memory (smem_bias) or at a global bias row
+__device__ __forceinline__ void epi_affine32_dispatch(uint32_t (&v)[32], bool ln, bool bias, bool smem_bias, const float* cs,
+                                                      const float* b, float rstd, float neg_mean) {
+  if (ln) {
+    if (!bias) epi_affine32<true, false, true>(v, cs, b, rstd, neg_mean);
+    else if (smem_bias) epi_affine32<true, true, true>(v, cs, b, rstd, neg_mean);
+    else epi_affine32<true, true, false>(v, cs, b, rstd, neg_mean);
+  } else if (bias) {
+    if (smem_bias) epi_affine32<false, true, true>(v, cs, b, rstd, neg_mean);
+    else epi_affine32<false, true, false>(v, cs, b, rstd, neg_mean);
+  }
+}
+
 template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_MAX_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
@@ -93,6 +130,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
   uint64_t* res_full_bar = tmem_empty_bar + 2;          // [MAX_EPI_WARPS][MAX_RING]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full_bar + MAX_EPI_WARPS * MAX_RING);
+  float* evec_base = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -244,7 +282,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int my_tiles = (p.num_tiles - unit + nunits - 1) / nunits;
     const uint32_t tempty0 = CG == 2 ? mapa_shared(smem_u32(tmem_empty_bar), 0) : 0;   // the leader's tmem_empty barriers
     const int total = my_tiles * my_nch;
-    const int R = p.ring, P = p.ring - 2;
+    // ring of R slots per warp; residual chunks are prefetched P steps ahead; up to W = R - P - 1 (no residual:
+    // R - 1) TMA stores may still be reading their slot when the warp moves on.  The stores share the SM's TMA
+    // queue with the producer's big operand loads, so W must be deep enough to ride out that queueing delay.
+    const int R = p.ring, P = p.prefetch;
+    const int W = p.res_mode ? R - P - 1 : R - 1;
     uint8_t* ring = ring_base + (size_t)ew * R * p.slot_bytes;
     uint64_t* rfull = res_full_bar + ew * MAX_RING;
     const uint32_t res_bytes = p.res_mode == 1 ? 4096u : 2048u;
@@ -274,6 +316,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const float* bias_row = p.bias ? p.bias + (size_t)(row_ok ? row / p.bias_div : 0) * p.ldb : nullptr;
+      // Nearly all of the SM's L1/shared array is carved as shared memory, so per-chunk __ldg's of the bias / LN
+      // column-sum vectors would each pay an L2 round trip.  Stage this tile's slices in shared memory once, before
+      // waiting for the accumulator (the load latency hides behind the main loop).
+      float* vb = evec_base + ew * (2 * EVEC_FLOATS);
+      float* vc = vb + EVEC_FLOATS;
+      const int rlast = min(row0 + 31, p.M - 1);
+      const bool bias_smem = p.bias && row0 < p.M && (row0 / p.bias_div == rlast / p.bias_div);   // one bias row for the warp
+      __syncwarp();
+      if (bias_smem) {
+        const float* src = p.bias + (size_t)(row0 / p.bias_div) * p.ldb + n0;
+        for (int i = lane; i < BN; i += 32) sts32(vb + i, __ldg(src + i));
+      }
+      if (p.row_stats_in)
+        for (int i = lane; i < BN; i += 32) sts32(vc + i, __ldg(p.ln_colsum + n0 + i));
+      __syncwarp();
       float mean = 0.f, rstd = 1.f;
       if (p.row_stats_in && row_ok) {        // folded LayerNorm: combine the producer's per-row partial sums
         float s1 = 0.f, s2 = 0.f;
@@ -285,14 +342,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mean = s1 * p.ln_inv_dim;
         rstd = rsqrtf(fmaxf(s2 * p.ln_inv_dim - mean * mean, 0.f) + p.ln_eps);
       }
-      const float nmr = -mean * rstd;
       float rs = 0.f, rq = 0.f;
 
       for (int j = 0; j < my_nch; ++j, ++g) {
         const int c = half + j * nhalf;
         const int s = g % R;
         uint8_t* slot = ring + s * p.slot_bytes;
-        if (lane == 0) bulk_wait_read<1>();  // the store that last used slot (g+P)%R (and (g-R)%R) has read its smem
+        if (lane == 0) {                     // the store that last used slot (g+P)%R (no residual: g%R) has read its smem
+          switch (W) {
+            case 0: bulk_wait_read<0>(); break;
+            case 1: bulk_wait_read<1>(); break;
+            case 2: bulk_wait_read<2>(); break;
+            case 3: bulk_wait_read<3>(); break;
+            case 4: bulk_wait_read<4>(); break;
+            case 5: bulk_wait_read<5>(); break;
+            default: bulk_wait_read<6>(); break;
+          }
+        }
         __syncwarp();
         if (p.res_mode && g + P < total) {
           if (lane == 0) issue_res(g + P);   // (same lane as the stores: bulk groups are tracked per thread)
@@ -305,6 +371,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * C::TBUF + c * cw);
         float f[32];
         {
+          const bool ln = p.row_stats_in != nullptr;
           uint32_t v[32];
           tmem_ld_32x32(taddr, v);
           if (!p.geglu) {
@@ -316,28 +383,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (CG == 2) mbar_arrive_cluster(tempty0 + (uint32_t)buf * 8u); else mbar_arrive(&tmem_empty_bar[buf]);
               }
             }
+            epi_affine32_dispatch(v, ln, p.bias != nullptr, bias_smem, vc + c * 32, bias_smem ? vb + c * 32 : bias_row + n0 + c * 32,
+                                  rstd, -mean);
 #pragma unroll
             for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
-            const int col0 = n0 + c * 32;
-            if (p.row_stats_in) {
-              const float4* s4 = reinterpret_cast<const float4*>(p.ln_colsum + col0);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const float4 t = __ldg(s4 + k);
-                f[4 * k] = fmaf(f[4 * k], rstd, nmr * t.x);
-                f[4 * k + 1] = fmaf(f[4 * k + 1], rstd, nmr * t.y);
-                f[4 * k + 2] = fmaf(f[4 * k + 2], rstd, nmr * t.z);
-                f[4 * k + 3] = fmaf(f[4 * k + 3], rstd, nmr * t.w);
-              }
-            }
-            if (bias_row) {
-              const float4* b4 = reinterpret_cast<const float4*>(bias_row + col0);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const float4 t = __ldg(b4 + k);
-                f[4 * k] += t.x; f[4 * k + 1] += t.y; f[4 * k + 2] += t.z; f[4 * k + 3] += t.w;
-              }
-            }
           } else {
             uint32_t vg[32];
             tmem_ld_32x32(taddr + 32, vg);
@@ -349,32 +398,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (CG == 2) mbar_arrive_cluster(tempty0 + (uint32_t)buf * 8u); else mbar_arrive(&tmem_empty_bar[buf]);
               }
             }
-            // GEGLU: accumulator columns [c*64, +32) are "value", [c*64+32, +64) the matching "gate"
-            const int col0 = n0 + c * 64;
-            if (p.row_stats_in) {            // folded LayerNorm (own pass under a uniform branch: no predicated filler)
-              const float4* sa = reinterpret_cast<const float4*>(p.ln_colsum + col0);
+            // GEGLU: accumulator columns [c*64, +32) are "value", [c*64+32, +64) the matching "gate" (bias is staged)
+            epi_affine32_dispatch(v, ln, true, true, vc + c * 64, vb + c * 64, rstd, -mean);
+            epi_affine32_dispatch(vg, ln, true, true, vc + c * 64 + 32, vb + c * 64 + 32, rstd, -mean);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const float4 t1 = __ldg(sa + k), t2 = __ldg(sa + 8 + k);
-                v[4 * k] = __float_as_uint(fmaf(__uint_as_float(v[4 * k]), rstd, nmr * t1.x));
-                v[4 * k + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * k + 1]), rstd, nmr * t1.y));
-                v[4 * k + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * k + 2]), rstd, nmr * t1.z));
-                v[4 * k + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * k + 3]), rstd, nmr * t1.w));
-                vg[4 * k] = __float_as_uint(fmaf(__uint_as_float(vg[4 * k]), rstd, nmr * t2.x));
-                vg[4 * k + 1] = __float_as_uint(fmaf(__uint_as_float(vg[4 * k + 1]), rstd, nmr * t2.y));
-                vg[4 * k + 2] = __float_as_uint(fmaf(__uint_as_float(vg[4 * k + 2]), rstd, nmr * t2.z));
-                vg[4 * k + 3] = __float_as_uint(fmaf(__uint_as_float(vg[4 * k + 3]), rstd, nmr * t2.w));
-              }
-            }
-            const float4* ba = reinterpret_cast<const float4*>(bias_row + col0);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float4 b1 = __ldg(ba + k), b2 = __ldg(ba + 8 + k);
-              f[4 * k] = (__uint_as_float(v[4 * k]) + b1.x) * gelu_erf_fast(__uint_as_float(vg[4 * k]) + b2.x);
-              f[4 * k + 1] = (__uint_as_float(v[4 * k + 1]) + b1.y) * gelu_erf_fast(__uint_as_float(vg[4 * k + 1]) + b2.y);
-              f[4 * k + 2] = (__uint_as_float(v[4 * k + 2]) + b1.z) * gelu_erf_fast(__uint_as_float(vg[4 * k + 2]) + b2.z);
-              f[4 * k + 3] = (__uint_as_float(v[4 * k + 3]) + b1.w) * gelu_erf_fast(__uint_as_float(vg[4 * k + 3]) + b2.w);
-            }
+            for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]) * gelu_erf_tanhfit(__uint_as_float(vg[k]));
           }
         }
         // ---- residual (prefetched into the slot by TMA) ----
@@ -384,13 +412,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.res_mode == 1) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const float4 t = *reinterpret_cast<const float4*>(rsrc + sw128(lane, k));
+              const float4 t = lds128(rsrc + sw128(lane, k));
               f[4 * k] += t.x; f[4 * k + 1] += t.y; f[4 * k + 2] += t.z; f[4 * k + 3] += t.w;
             }
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint4 t = *reinterpret_cast<const uint4*>(rsrc + sw64(lane, k));
+              const uint4 t = lds128u(rsrc + sw64(lane, k));
               const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), cc = unpack_bf16(t.z), d = unpack_bf16(t.w);
               f[8 * k] += a.x; f[8 * k + 1] += a.y; f[8 * k + 2] += b.x; f[8 * k + 3] += b.y;
               f[8 * k + 4] += cc.x; f[8 * k + 5] += cc.y; f[8 * k + 6] += d.x; f[8 * k + 7] += d.y;
@@ -412,9 +440,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* dst = slot + p.outf_off;
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<float4*>(dst + sw128(lane, k)) = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+            sts128(dst + sw128(lane, k), make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]));
         }
         if (p.out_bf16) {
+          if (p.alias_sync) __syncwarp();      // the bf16 tile overwrites the (fully read) fp32 residual tile
           uint8_t* dst = slot + p.outh_off;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -423,7 +452,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             o.y = pack_bf16(f[8 * k + 2], f[8 * k + 3]);
             o.z = pack_bf16(f[8 * k + 4], f[8 * k + 5]);
             o.w = pack_bf16(f[8 * k + 6], f[8 * k + 7]);
-            *reinterpret_cast<uint4*>(dst + sw64(lane, k)) = o;
+            sts128u(dst + sw64(lane, k), o);
           }
         }
         fence_proxy_async_smem();
@@ -440,7 +469,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float cs = 0.f, cq = 0.f;
 #pragma unroll
           for (int r = 0; r < 32; ++r) {
-            const float t = *reinterpret_cast<const float*>(src + sw128(r, lane >> 2));
+            const float t = lds32(src + sw128(r, lane >> 2));
             cs += t;
             cq = fmaf(t, t, cq);
           }
@@ -536,7 +565,7 @@ static int num_sms() {
 }
 
 struct Plan {
-  int bn, cg, stages, nepi, ring, slot_bytes, res_off, outf_off, outh_off, tiles_n, num_tiles, grid, smem_bytes;
+  int bn, cg, stages, nepi, ring, prefetch, alias_sync, slot_bytes, res_off, outf_off, outh_off, tiles_n, num_tiles, grid, smem_bytes;
 };
 
 static int env_int(const char* name, int dflt) {
@@ -591,9 +620,10 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   const int rm = d.residual ? (d.residual_bf16 ? 2 : 1) : 0;
   pl.res_off = 0; pl.outf_off = 0; pl.outh_off = 0;
   int extent;
-  if (rm == 1) {            // fp32 residual at 0 (fp32 output in place), bf16 output behind it
-    pl.outh_off = 4096;
-    extent = oh ? 6144 : 4096;
+  pl.alias_sync = 0;
+  if (rm == 1) {            // fp32 residual at 0 (fp32 output in place); a bf16 copy goes behind it, a bf16-ONLY output
+    if (of) { pl.outh_off = 4096; extent = oh ? 6144 : 4096; }      // reuses the residual's bytes after a warp sync
+    else { pl.outh_off = 0; extent = 4096; pl.alias_sync = 1; }
   } else if (rm == 2) {
     if (of) { pl.res_off = 4096; pl.outh_off = 4096; extent = 6144; }
     else { extent = 2048; }
@@ -602,26 +632,34 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
     extent = of ? (oh ? 6144 : 4096) : 2048;
   }
   pl.slot_bytes = extent;
-  pl.nepi = env_int("SEER_GEMM_NEPI", d.geglu ? 8 : 4);
+  pl.nepi = env_int("SEER_GEMM_NEPI", (d.geglu || !of) ? 8 : 4);   // bf16-only outputs: small slots, latency-bound epilogue
   if (pl.nepi != 4 && pl.nepi != 8) pl.nepi = 4;
   if (best / (d.geglu ? 64 : 32) < 2) pl.nepi = 4;   // every epilogue warp needs at least one chunk
   const int stage_bytes = A_BYTES + (best / cg) * BK * 2;
-  const int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - BAR_BYTES;
-  pl.ring = 4;
-  pl.stages = (avail - pl.nepi * pl.ring * pl.slot_bytes) / stage_bytes;
-  if (pl.stages < 4) {
-    pl.ring = 3;
-    pl.stages = (avail - pl.nepi * pl.ring * pl.slot_bytes) / stage_bytes;
+  const int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - BAR_BYTES - MAX_EPI_WARPS * EVEC_BYTES_PER_WARP;
+  // (epilogue warps, ring depth, operand stages) by score: operand stages matter most (up to 5), then 8 epilogue warps
+  // for the latency-bound bf16-only / GEGLU epilogues, then ring depth
+  const int want_nepi = pl.nepi;
+  const int want_ring = env_int("SEER_EPI_RING", rm ? 6 : 4);
+  int best_score = -1;
+  for (int ne = want_nepi; ne >= 4; ne -= 4) {
+    for (int rg = want_ring; rg >= 3; --rg) {
+      int st = (avail - ne * rg * pl.slot_bytes) / stage_bytes;
+      if (st < 2) continue;
+      if (st > 6) st = 6;
+      const int score = (st > 5 ? 5 : st) * 100 + (ne == 8 ? 30 : 0) + rg * 5;
+      if (score > best_score) { best_score = score; pl.nepi = ne; pl.ring = rg; pl.stages = st; }
+    }
   }
-  if (pl.stages < 3 && pl.nepi == 8) {
-    pl.nepi = 4; pl.ring = 4;
-    pl.stages = (avail - pl.nepi * pl.ring * pl.slot_bytes) / stage_bytes;
-  }
+  if (best_score < 0) return SEER_EUNSUPPORTED;
+  pl.prefetch = env_int("SEER_EPI_PREFETCH", pl.ring >= 6 ? 2 : pl.ring - 2);
+  if (pl.prefetch < 1) pl.prefetch = 1;
+  if (pl.prefetch > pl.ring - 1) pl.prefetch = pl.ring - 1;
   if (pl.stages < 2) return SEER_EUNSUPPORTED;
   if (pl.stages > 6) pl.stages = 6;
   const int fs = env_int("SEER_GEMM_STAGES", 0);
   if (fs >= 2 && fs <= pl.stages) pl.stages = fs;
-  pl.smem_bytes = pl.stages * stage_bytes + pl.nepi * pl.ring * pl.slot_bytes + BAR_BYTES + 1024;
+  pl.smem_bytes = pl.stages * stage_bytes + pl.nepi * pl.ring * pl.slot_bytes + BAR_BYTES + pl.nepi * EVEC_BYTES_PER_WARP + 1024;
   // > half of the SM's shared memory, so two CTAs (2 x TMEM_COLS could exceed 512 columns) never share an SM
   if (pl.smem_bytes < 120 * 1024) pl.smem_bytes = 120 * 1024;
   return SEER_OK;
@@ -672,7 +710,7 @@ static int check_desc(const SeerGemmDesc& d) {
   SEER_CHECK_ARG(!d.out_bf16 || d.ldo_bf16 % 8 == 0);
   SEER_CHECK_ARG(!d.residual || (d.residual_bf16 ? d.ldr % 8 == 0 : d.ldr % 4 == 0));
   SEER_CHECK_ARG(d.ldb <= 0 || d.ldb % 4 == 0);
-  if (d.geglu) SEER_CHECK_ARG(d.N % 128 == 0 && d.out_bf16 && !d.out_f32 && d.bias && !d.residual && !d.col_stats && !d.row_stats_out);
+  if (d.geglu) SEER_CHECK_ARG(d.bias_div <= 0 && d.N % 128 == 0 && d.out_bf16 && !d.out_f32 && d.bias && !d.residual && !d.col_stats && !d.row_stats_out);
   SEER_CHECK_ARG(!d.col_stats || d.out_f32);
   if (d.row_stats_in) SEER_CHECK_ARG(d.row_parts_in > 0 && d.ln_colsum && !d.X);
   return SEER_OK;
@@ -701,7 +739,7 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   GemmParams p{};
   p.M = d.M; p.N = d.N;
   p.tiles_n = pl.tiles_n; p.num_tiles = pl.num_tiles;
-  p.stages = pl.stages; p.nepi = pl.nepi; p.ring = pl.ring; p.slot_bytes = pl.slot_bytes;
+  p.stages = pl.stages; p.nepi = pl.nepi; p.ring = pl.ring; p.prefetch = pl.prefetch; p.alias_sync = pl.alias_sync; p.slot_bytes = pl.slot_bytes;
   p.res_off = pl.res_off; p.outf_off = pl.outf_off; p.outh_off = pl.outh_off;
   p.bias = d.bias; p.ldb = d.ldb > 0 ? d.ldb : d.N; p.bias_div = d.bias_div > 0 ? d.bias_div : 0x7fffffff;
   p.res_mode = d.residual ? (d.residual_bf16 ? 2 : 1) : 0;
