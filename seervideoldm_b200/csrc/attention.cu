@@ -286,9 +286,11 @@ static void fill_scta_geometry(AttnParams& p, int F, int H, int W) {
 
 using namespace seer;
 
-extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
-                                   int mode, int heads, int head_dim, int n_outer, int Lq, int Lk, int F, int H, int W,
-                                   void* stream) {
+// mma.sync path: every head dim / geometry.  The d = 40 level-0 problems are routed to the tcgen05 kernel in
+// attention_tc.cu by the C entry point defined there.
+int seer::attention_mma_launch(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
+                               int mode, int heads, int head_dim, int n_outer, int Lq, int Lk, int F, int H, int W,
+                               void* stream) {
   SEER_CHECK_ARG(q && k && v && o && heads > 0 && n_outer > 0);
   SEER_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0);
   AttnParams p{};

@@ -1,0 +1,414 @@
+// tcgen05 flash attention for the d = 40 level of the Seer UNet (32x32 latents: 84 % of the attention-core FLOPs), and
+// the C entry point seer_b200_attention that routes every other shape to the mma.sync kernel in attention.cu.
+//
+//   mode SPATIAL : per-frame self attention, L = h*w tokens            (reference attention.py:310-311, 512-554)
+//   mode CROSS   : per-frame cross attention against Lk (= 77) text tokens                     (attention.py:313-322)
+//   mode SCTA    : spatial-causal temporal attention over one 8x8 window of every frame, sequence order
+//                  (frame, wy, wx), lower-triangular causal          (attention.py:632-703, window order :42-53)
+//
+// One CTA = 128 queries of one (problem, head); two CTAs share an SM (80 KB smem, 256 TMEM columns each) so one CTA's
+// softmax overlaps the other's MMAs.  Per 128-key tile:
+//   warp 0  TMA: K and V tiles [128 rows x 64 columns] straight from the token-major projection buffers.  The head
+//           split (column offset head*40) and the window partition (a 4-D box {64 ch, 8, 8, 2 frames} of the
+//           [B*F, H, W, C] view) are TMA coordinates — no gather, no copies.  Columns 40..63 of a box belong to the next
+//           head; Q's are zeroed in smem once, so they contribute nothing to Q K^T, and the matching O columns are dropped.
+//   warp 1  tcgen05.mma: S[128x128] = Q K^T into TMEM; then O_j[128x64] = P V (P from smem, V as MN-major B operand).
+//   warps 2-5  softmax, thread = query row = TMEM lane: two passes over S (max, then exp2 / sum / bf16 P -> smem in the
+//           UMMA K-major swizzled layout), then O_acc = O_acc * corr + O_j from TMEM, all fp32 in registers.
+// The kernel is MUFU-bound by design (128x128 exp2 per tile = 1024 SM cycles vs 512 tensor cycles).
+#include "common.cuh"
+#include "seer_b200.h"
+
+namespace seer {
+
+constexpr int AT_BM = 128;     // queries per CTA
+constexpr int AT_BN = 128;     // keys per tile
+constexpr int AT_DP = 64;      // padded head dim (one 128-byte swizzle atom)
+constexpr int AT_TILE = AT_BM * AT_DP * 2;           // 16 KB: Q / K / V tile
+constexpr int AT_P_BYTES = AT_BM * AT_BN * 2;        // 32 KB: P tile (two 64-key atoms)
+constexpr int AT_SMEM = 3 * AT_TILE + AT_P_BYTES + 256 + 1024;
+constexpr int AT_THREADS = 192;
+
+struct AttnTcParams {
+  __nv_bfloat16* o;
+  int ldo;
+  int mode, heads;
+  int Lq, Lk;
+  int F, H, W, nwx, nwin;      // SCTA geometry (window side fixed at 8)
+  float scale_log2;            // d^-0.5 * log2(e)
+  int causal;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn at_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + AT_TILE;
+  uint8_t* sV = sK + AT_TILE;
+  uint8_t* sP = sV + AT_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_P_BYTES);
+  uint64_t* q_full = bars + 0;     // TMA: Q landed
+  uint64_t* q_ready = bars + 1;    // softmax warps zeroed Q's pad columns (count 4)
+  uint64_t* k_full = bars + 2;
+  uint64_t* k_empty = bars + 3;    // S MMA has read K
+  uint64_t* v_full = bars + 4;
+  uint64_t* v_empty = bars + 5;    // P V MMA has read V (and P)
+  uint64_t* s_full = bars + 6;     // S in TMEM
+  uint64_t* s_free = bars + 7;     // softmax finished reading S (count 4)
+  uint64_t* p_full = bars + 8;     // P in smem (count 4)
+  uint64_t* o_full = bars + 9;     // O_j in TMEM
+  uint64_t* o_free = bars + 10;    // softmax finished reading O_j (count 4)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x;
+  const int head = blockIdx.y % p.heads;
+  const int outer = blockIdx.y / p.heads;       // spatial/cross: frame; scta: b * nwin + win
+  const int col0 = head * D;
+  int b = 0, wy = 0, wx = 0;
+  if (p.mode == SEER_ATTN_SCTA) {
+    b = outer / p.nwin;
+    const int win = outer - b * p.nwin;
+    wy = win / p.nwx;
+    wx = win - wy * p.nwx;
+  }
+  int n_kv = ceil_div(p.Lk, AT_BN);
+  if (p.causal) n_kv = min(n_kv, qt + 1);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_ready, 4);
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 4);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;           // 128 columns
+  const uint32_t tO = tmem_base + 128;     // 64 columns
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    auto load_tile = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tile) {
+      if (p.mode == SEER_ATTN_SCTA) tma_load_4d(dst, tm, bar, col0, wx * 8, wy * 8, b * p.F + tile * 2);
+      else tma_load_2d(dst, tm, bar, col0, outer * (tm == &tmQ ? p.Lq : p.Lk) + tile * AT_BN);
+    };
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, AT_TILE);
+      load_tile(sQ, &tmQ, q_full, qt);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(k_empty, (j & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(k_full, AT_TILE);
+        load_tile(sK, &tmK, k_full, j);
+      }
+      __syncwarp();
+      mbar_wait(v_empty, (j & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(v_full, AT_TILE);
+        load_tile(sV, &tmV, v_full, j);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN);          // S = Q K^T : N = 128 keys, K = 64 (padded d)
+    constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(AT_BM, AT_DP);      // O = P V   : N = 64 (padded d), K = 128 keys, V MN-major
+    const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
+    const uint64_t k_desc = umma_desc_sw128(smem_u32(sK));
+    const uint64_t v_desc = umma_desc_sw128_mn(smem_u32(sV));
+    const uint64_t p_desc0 = umma_desc_sw128(smem_u32(sP));
+    const uint64_t p_desc1 = umma_desc_sw128(smem_u32(sP + AT_BM * 128));
+    mbar_wait(q_ready, 0);
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = j & 1;
+      mbar_wait(k_full, ph);
+      mbar_wait(s_free, ph ^ 1);               // softmax has drained S of tile j-1
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < AT_DP / 16; ++k)
+          umma_bf16(tS, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
+        umma_commit(s_full);
+        umma_commit(k_empty);
+      }
+      __syncwarp();
+      mbar_wait(v_full, ph);
+      mbar_wait(p_full, ph);
+      mbar_wait(o_free, ph ^ 1);               // softmax has drained O of tile j-1
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < AT_BN / 16; ++k) {
+          // A: 16 keys = 32 B inside the 64-key atom (two atoms 16 KB apart); B: 16 keys = two 8-row groups = 2048 B
+          const uint64_t a = (k < 4 ? p_desc0 : p_desc1) + (uint64_t)((k & 3) * 2);
+          umma_bf16(tO, a, v_desc + (uint64_t)(k * 128), idesc_o, k != 0);
+        }
+        umma_commit(o_full);
+        umma_commit(v_empty);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax warps (thread = query row) =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;               // row inside the tile = TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    // zero Q's pad columns D..63 (they hold the next head's channels), then hand Q to the MMA warp
+    mbar_wait(q_full, 0);
+#pragma unroll
+    for (int c = D / 8; c < 8; ++c) sts128u(sQ + r * 128 + ((c ^ (r & 7)) << 4), make_uint4(0, 0, 0, 0));
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(q_ready);
+
+    float o_acc[48];
+#pragma unroll
+    for (int i = 0; i < 48; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    const float sl2 = p.scale_log2;
+    const int qi = qt * AT_BM + r;             // query index in the sequence
+
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = j & 1;
+      const int kv0 = j * AT_BN;
+      const bool need_mask = (kv0 + AT_BN > p.Lk) || (p.causal && j == qt);
+      const int k_hi = min(p.Lk - kv0, p.causal && j == qt ? r + 1 : AT_BN);   // keys [0, k_hi) of this tile are visible
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      // ---- pass 1: row maximum ----
+      float mx = m_run;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (need_mask) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (c * 32 + k < k_hi) mx = fmaxf(mx, __uint_as_float(v[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
+        }
+      }
+      // ---- pass 2: p = exp2((s - max) * scale), row sum, bf16 P into the swizzled K-major A tile ----
+      const float msc = mx * sl2;
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        float e[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[k]) : "f"(fmaf(__uint_as_float(v[k]), sl2, -msc)));
+          if (need_mask && c * 32 + k >= k_hi) e[k] = 0.f;
+          sum += e[k];
+        }
+        uint8_t* prow = sP + (c >> 1) * (AT_BM * 128) + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16(e[8 * g], e[8 * g + 1]);
+          o.y = pack_bf16(e[8 * g + 2], e[8 * g + 3]);
+          o.z = pack_bf16(e[8 * g + 4], e[8 * g + 5]);
+          o.w = pack_bf16(e[8 * g + 6], e[8 * g + 7]);
+          sts128u(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4), o);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(s_free);
+        mbar_arrive(p_full);
+      }
+      const float corr = exp2f((m_run - mx) * sl2);      // first tile: exp2(-inf) = 0
+      l_run = l_run * corr + sum;
+      m_run = mx;
+      // ---- O_acc = O_acc * corr + O_j ----
+      mbar_wait(o_full, ph);
+      tc_fence_after();
+      {
+        uint32_t v0[32], v1[16];
+        tmem_ld_32x32(tO + lane_addr, v0);
+        tmem_ld_32x16(tO + lane_addr + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], corr, __uint_as_float(v0[i]));
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o_acc[32 + i] = fmaf(o_acc[32 + i], corr, __uint_as_float(v1[i]));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+    }
+
+    // ---- finalize: O / l -> bf16, token-major row ----
+    size_t grow;
+    if (p.mode == SEER_ATTN_SCTA) {
+      const int f = qt * 2 + (r >> 6), iy = (r >> 3) & 7, ix = r & 7;
+      grow = ((size_t)(b * p.F + f) * p.H + wy * 8 + iy) * p.W + wx * 8 + ix;
+    } else {
+      grow = (size_t)outer * p.Lq + qi;
+    }
+    if (qi < p.Lq) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* dst = p.o + grow * p.ldo + col0;
+#pragma unroll
+      for (int g = 0; g < D / 8; ++g) {
+        uint4 o;
+        o.x = pack_bf16(o_acc[8 * g] * inv, o_acc[8 * g + 1] * inv);
+        o.y = pack_bf16(o_acc[8 * g + 2] * inv, o_acc[8 * g + 3] * inv);
+        o.z = pack_bf16(o_acc[8 * g + 4] * inv, o_acc[8 * g + 5] * inv);
+        o.w = pack_bf16(o_acc[8 * g + 6] * inv, o_acc[8 * g + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + 8 * g) = o;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncwarp();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// 2-D map over a token-major buffer [rows, ld] restricted to its first `cols` columns; box {64, 128}
+static int at_map_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  EncodeTiledFn enc = at_encode_fn();
+  if (!enc) return SEER_ENODRIVER;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {AT_DP, AT_BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SEER_OK : SEER_EINVAL;
+}
+// 4-D map [n_frames, H, W, cols] (row pitch ld); box {64 ch, 8, 8, 2 frames} = one 8x8 window of two frames
+static int at_map_4d(CUtensorMap* tm, const void* base, uint64_t n_frames, uint64_t H, uint64_t W, uint64_t cols, uint64_t ld) {
+  EncodeTiledFn enc = at_encode_fn();
+  if (!enc) return SEER_ENODRIVER;
+  cuuint64_t dims[4] = {cols, W, H, n_frames};
+  cuuint64_t strides[3] = {ld * 2, W * ld * 2, H * W * ld * 2};
+  cuuint32_t box[4] = {AT_DP, 8, 8, 2};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SEER_OK : SEER_EINVAL;
+}
+
+static int env_flag(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+}  // namespace seer
+
+using namespace seer;
+
+extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
+                                   int mode, int heads, int head_dim, int n_outer, int Lq, int Lk, int F, int H, int W,
+                                   void* stream) {
+  SEER_CHECK_ARG(q && k && v && o && heads > 0 && n_outer > 0);
+  // tcgen05 path: d = 40, 128-row query tiles; SCTA needs 8x8 windows (H/8 >= 4) and an even frame count
+  bool tc = head_dim == 40 && env_flag("SEER_ATTN_TC", 1) && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 &&
+            ((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) && ((uintptr_t)o % 16 == 0);
+  AttnTcParams p{};
+  int n_problems = 0, nq_tiles = 0;
+  if (tc) {
+    if (mode == SEER_ATTN_SCTA) {
+      tc = F > 0 && H >= 32 && H % 8 == 0 && W % 8 == 0 && F % 2 == 0;
+      if (tc) {
+        p.F = F; p.H = H; p.W = W; p.nwx = W / 8; p.nwin = (H / 8) * p.nwx;
+        p.Lq = p.Lk = F * 64; p.causal = 1;
+        n_problems = n_outer * p.nwin * heads;
+        nq_tiles = p.Lq / AT_BM;
+      }
+    } else if (mode == SEER_ATTN_SPATIAL || mode == SEER_ATTN_CROSS) {
+      tc = Lq > 0 && Lk > 0 && Lq % AT_BM == 0;
+      if (tc) {
+        p.Lq = Lq; p.Lk = Lk; p.causal = 0; p.nwin = 1; p.nwx = 1;
+        n_problems = n_outer * heads;
+        nq_tiles = Lq / AT_BM;
+      }
+    } else {
+      return SEER_EINVAL;
+    }
+    if (n_problems > 65535) tc = false;
+  }
+  if (!tc) return attention_mma_launch(q, ldq, k, ldk, v, ldv, o, ldo, mode, heads, head_dim, n_outer, Lq, Lk, F, H, W, stream);
+
+  p.o = (__nv_bfloat16*)o; p.ldo = ldo;
+  p.mode = mode; p.heads = heads;
+  p.scale_log2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
+  const uint64_t C = (uint64_t)heads * head_dim;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if (mode == SEER_ATTN_SCTA) {
+    const uint64_t nf = (uint64_t)n_outer * F;
+    if ((rc = at_map_4d(&tq, q, nf, H, W, C, ldq))) return rc;
+    if ((rc = at_map_4d(&tk, k, nf, H, W, C, ldk))) return rc;
+    if ((rc = at_map_4d(&tv, v, nf, H, W, C, ldv))) return rc;
+  } else {
+    if ((rc = at_map_2d(&tq, q, (uint64_t)n_outer * Lq, C, ldq))) return rc;
+    if ((rc = at_map_2d(&tk, k, (uint64_t)n_outer * Lk, C, ldk))) return rc;
+    if ((rc = at_map_2d(&tv, v, (uint64_t)n_outer * Lk, C, ldv))) return rc;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  dim3 grid(nq_tiles, n_problems);
+  attention_tc_kernel<40><<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}

@@ -28,6 +28,10 @@ enum : int { SEER_OK = 0, SEER_EINVAL = -1, SEER_EUNSUPPORTED = -2, SEER_ENODRIV
 
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// attention.cu (mma.sync flash attention, any head dim) — called by the dispatcher in attention_tc.cu
+int attention_mma_launch(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int mode,
+                         int heads, int head_dim, int n_outer, int Lq, int Lk, int F, int H, int W, void* stream);
+
 // ---- generic -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -323,7 +327,32 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// MN-major, 128-byte-swizzled B operand (rows = K index, 64 contiguous N elements = 128 B per row; 8-row groups
+// 1024 B apart): the V tile of attention as TMA lands it.  SBO = 1024 B between 8-row K groups, LBO (stride between
+// 64-wide N atoms) unused for N <= 64.  Layout per cute UMMA::make_umma_desc<Major::MN> (mma_traits_sm100.hpp).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 16;       // LBO (not exercised)
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// as umma_idesc_bf16, with B taken MN-major (bit 16)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // ---- Ampere-style async copy + ldmatrix + mma.sync (attention v1) ----------------------------------------
 __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem, bool valid) {

@@ -49,14 +49,17 @@ struct GemmParams {
   int cblk;            // conv: Cin / 64
   int H, W;            // conv image geometry
   int tiles_n, num_tiles;
-  int stages, nepi, ring, prefetch, slot_bytes;
-  int alias_sync;
-  int res_off, outf_off, outh_off;   // byte offsets of the residual / fp32-out / bf16-out regions inside a slot
+  int stages, nepi, ring, slot_bytes;
+  int bstat;           // 1: the whole Wt panel of this CTA's (fixed) n-block is resident in smem; only A is streamed
+  int debug;           // tuning hook SEER_GEMM_DEBUG: 1 = skip the global stores, 2 = skip staging + stores (timing experiments only)
   const float* bias;
   int ldb;
   int bias_div;
   int res_mode;        // 0 none, 1 fp32, 2 bf16
-  int out_f32, out_bf16;
+  float* out_f32;      // fp32 output (or null), leading dim ldo_f32 elements
+  int ldo_f32;
+  __nv_bfloat16* out_bf16;
+  int ldo_bf16;
   int geglu;
   float* col_stats;
   float* row_stats_out;
@@ -118,18 +121,21 @@ __device__ __forceinline__ void epi_affine32_dispatch(uint32_t (&v)[32], bool ln
 template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_MAX_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmRes,
-               const __grid_constant__ CUtensorMap tmOutF, const __grid_constant__ CUtensorMap tmOutH, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmRes, const GemmParams p) {
   using C = GemmCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring_base = smem + p.stages * C::STAGE_BYTES;
+  // B-stationary mode (small K): [Wt panel: kb_total x B_BYTES][A stages: stages x A_BYTES]; else [stages x (A | B)]
+  const int stage_stride = p.bstat ? A_BYTES : C::STAGE_BYTES;
+  uint8_t* stage_base = smem + (p.bstat ? p.kb_total * C::B_BYTES : 0);
+  uint8_t* ring_base = stage_base + p.stages * stage_stride;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring_base + p.nepi * p.ring * p.slot_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
   uint64_t* res_full_bar = tmem_empty_bar + 2;          // [MAX_EPI_WARPS][MAX_RING]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full_bar + MAX_EPI_WARPS * MAX_RING);
+  uint64_t* bpanel_bar = res_full_bar + MAX_EPI_WARPS * MAX_RING;   // [1] B-stationary: the Wt panel has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bpanel_bar + 1);
   float* evec_base = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
@@ -144,8 +150,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     if (p.kb_total > p.kb_main) tma_prefetch_desc(&tmA2);
     if (p.res_mode) tma_prefetch_desc(&tmRes);
-    if (p.out_f32) tma_prefetch_desc(&tmOutF);
-    if (p.out_bf16) tma_prefetch_desc(&tmOutH);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -155,6 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tmem_empty_bar[b], p.nepi * CG);     // CG 2: the epilogue warps of BOTH CTAs arrive on the leader's
     }
     for (int i = 0; i < MAX_EPI_WARPS * MAX_RING; ++i) mbar_init(&res_full_bar[i], 1);
+    mbar_init(bpanel_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -173,6 +178,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       const uint32_t full0 = CG == 2 ? mapa_shared(smem_u32(full_bar), 0) : 0;   // the pair leader's full barriers
+      if (p.bstat) {
+        // this CTA's n-block never changes (grid is a multiple of tiles_n): fetch its whole Wt panel once
+        const int nb0 = unit % p.tiles_n;
+        if (elect_one()) {
+          if (CG == 1) {
+            mbar_arrive_expect_tx(bpanel_bar, p.kb_total * C::B_BYTES);
+            for (int kb = 0; kb < p.kb_total; ++kb) tma_load_2d(smem + kb * C::B_BYTES, &tmB, bpanel_bar, kb * BK, nb0 * BN);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(bpanel_bar, 2 * p.kb_total * C::B_BYTES);
+            const uint32_t bb = mapa_shared(smem_u32(bpanel_bar), 0);
+            for (int kb = 0; kb < p.kb_total; ++kb)
+              tma_load_2d_cg2(smem + kb * C::B_BYTES, &tmB, bb, kb * BK, nb0 * BN + rank * (BN / CG));
+          }
+        }
+        __syncwarp();
+      }
+      const uint32_t stage_tx = p.bstat ? A_BYTES : C::STAGE_BYTES;
       for (int tile = unit; tile < p.num_tiles; tile += nunits) {
         const int mb = tile / p.tiles_n, nb = tile - mb * p.tiles_n;
         const int m0 = (mb * CG + rank) * BM, n0 = nb * BN + rank * (BN / CG);
@@ -184,11 +206,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int kb = 0; kb < p.kb_total; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sA = smem + s * C::STAGE_BYTES;
+          uint8_t* sA = stage_base + s * stage_stride;
           uint8_t* sB = sA + A_BYTES;
           if (elect_one()) {
           if (CG == 1) {
-            mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+            mbar_arrive_expect_tx(&full_bar[s], stage_tx);
             if (kb < p.kb_main) {
               if (p.mode == 0) {
                 tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m0);
@@ -204,10 +226,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               tma_load_2d(sA, &tmA2, &full_bar[s], (kb - p.kb_main) * BK, m0);
             }
-            tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
+            if (!p.bstat) tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
           } else {
             // both CTAs of the pair fill their own stage; all bytes are counted on the LEADER's full barrier
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_tx);
             const uint32_t fb = full0 + (uint32_t)s * 8u;
             if (kb < p.kb_main) {
               if (p.mode == 0) {
@@ -224,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               tma_load_2d_cg2(sA, &tmA2, fb, (kb - p.kb_main) * BK, m0);
             }
-            tma_load_2d_cg2(sB, &tmB, fb, kb * BK, n0);
+            if (!p.bstat) tma_load_2d_cg2(sB, &tmB, fb, kb * BK, n0);
           }
           }
           __syncwarp();
@@ -240,6 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
+      if (p.bstat) mbar_wait(bpanel_bar, 0);
       for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
         const int buf = it & 1;
         mbar_wait(&tmem_empty_bar[buf], (((uint32_t)it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
@@ -248,9 +271,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < p.kb_total; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t a_addr = smem_u32(stage_base + s * stage_stride);
           const uint64_t a_desc = umma_desc_sw128(a_addr);
-          const uint64_t b_desc = umma_desc_sw128(a_addr + A_BYTES);
+          const uint64_t b_desc = umma_desc_sw128(p.bstat ? smem_u32(smem + kb * C::B_BYTES) : a_addr + A_BYTES);
           if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -282,27 +305,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int my_tiles = (p.num_tiles - unit + nunits - 1) / nunits;
     const uint32_t tempty0 = CG == 2 ? mapa_shared(smem_u32(tmem_empty_bar), 0) : 0;   // the leader's tmem_empty barriers
     const int total = my_tiles * my_nch;
-    // ring of R slots per warp; residual chunks are prefetched P steps ahead; up to W = R - P - 1 (no residual:
-    // R - 1) TMA stores may still be reading their slot when the warp moves on.  The stores share the SM's TMA
-    // queue with the producer's big operand loads, so W must be deep enough to ride out that queueing delay.
-    const int R = p.ring, P = p.prefetch;
-    const int W = p.res_mode ? R - P - 1 : R - 1;
+    // Ring of R smem slots per warp.  A slot first receives the TMA-prefetched residual chunk (32 rows x 32 cols),
+    // then stages the output chunk for the coalesced copy-out; it is free again as soon as the warp has read it back,
+    // so the residual for step g + R - 1 can be requested at the top of step g.
+    const int R = p.ring, P = p.ring - 1;
     uint8_t* ring = ring_base + (size_t)ew * R * p.slot_bytes;
     uint64_t* rfull = res_full_bar + ew * MAX_RING;
     const uint32_t res_bytes = p.res_mode == 1 ? 4096u : 2048u;
 
-    auto issue_res = [&](int step) {         // lane 0: TMA-prefetch the residual chunk of a future step
-      const int it2 = step / my_nch, j2 = step - it2 * my_nch;
-      const int tile2 = unit + it2 * nunits;
-      const int mb2 = tile2 / p.tiles_n, nb2 = tile2 - mb2 * p.tiles_n;
-      const int s2 = step % R;
+    // residual prefetch cursor (tile / chunk of step g + P), advanced incrementally: no divisions in the chunk loop
+    int pf_step = 0, pf_tile = unit, pf_j = 0;
+    auto issue_res = [&]() {                 // lane 0: TMA-prefetch the residual chunk of step pf_step, then advance
+      const int mb2 = pf_tile / p.tiles_n, nb2 = pf_tile - mb2 * p.tiles_n;
+      const int s2 = pf_step % R;
       mbar_arrive_expect_tx(&rfull[s2], res_bytes);
-      tma_load_2d(ring + s2 * p.slot_bytes + p.res_off, &tmRes, &rfull[s2], nb2 * BN + (half + j2 * nhalf) * 32,
+      tma_load_2d(ring + s2 * p.slot_bytes, &tmRes, &rfull[s2], nb2 * BN + (half + pf_j * nhalf) * 32,
                   (mb2 * CG + rank) * BM + q * 32);
     };
+    auto advance_pf = [&]() {
+      ++pf_step;
+      if (++pf_j == my_nch) { pf_j = 0; pf_tile += nunits; }
+    };
     if (p.res_mode) {
-      for (int st = 0; st < P && st < total; ++st)
-        if (elect_one()) issue_res(st);
+      for (int st = 0; st < P && st < total; ++st) {
+        if (lane == 0) issue_res();
+        advance_pf();
+      }
       __syncwarp();
     }
 
@@ -348,20 +376,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int c = half + j * nhalf;
         const int s = g % R;
         uint8_t* slot = ring + s * p.slot_bytes;
-        if (lane == 0) {                     // the store that last used slot (g+P)%R (no residual: g%R) has read its smem
-          switch (W) {
-            case 0: bulk_wait_read<0>(); break;
-            case 1: bulk_wait_read<1>(); break;
-            case 2: bulk_wait_read<2>(); break;
-            case 3: bulk_wait_read<3>(); break;
-            case 4: bulk_wait_read<4>(); break;
-            case 5: bulk_wait_read<5>(); break;
-            default: bulk_wait_read<6>(); break;
-          }
-        }
-        __syncwarp();
-        if (p.res_mode && g + P < total) {
-          if (lane == 0) issue_res(g + P);   // (same lane as the stores: bulk groups are tracked per thread)
+        if (p.res_mode && pf_step < total) { // slot (g+P)%R = (g-1)%R was fully consumed in the previous step
+          if (lane == 0) issue_res();
+          advance_pf();
           __syncwarp();
         }
         if (j == 0) {
@@ -408,7 +425,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ---- residual (prefetched into the slot by TMA) ----
         if (p.res_mode) {
           mbar_wait(&rfull[s], ((uint32_t)(g / R)) & 1);
-          const uint8_t* rsrc = slot + p.res_off;
+          const uint8_t* rsrc = slot;
           if (p.res_mode == 1) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -435,16 +452,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int k = 0; k < 32; ++k) { rs += f[k]; rq = fmaf(f[k], f[k], rq); }
           }
         }
-        // ---- stage the outputs in the slot (thread = row, swizzled 16-byte chunks) and TMA-store them ----
-        if (p.out_f32) {
-          uint8_t* dst = slot + p.outf_off;
+        // ---- outputs: stage the chunk in the slot (thread = row, XOR-swizzled 16-byte pieces: conflict-free), then
+        // copy it out with coalesced 128-bit global stores (each warp store covers 4 full 128-byte lines).  This stays
+        // in the generic proxy: a TMA store would need fence.proxy.async + a bulk-group round trip per chunk, measured
+        // at ~1000 cycles of serial latency per warp (tools/tma_store_bench.cu) — the L0 epilogues were bound by it.
+        const int ocol = (p.geglu ? (n0 >> 1) : n0) + c * 32;
+        __syncwarp();                          // every lane has read its residual row: the slot may be overwritten
+        if (p.out_f32 && !(p.debug & 2)) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            sts128(dst + sw128(lane, k), make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]));
+            sts128(slot + sw128(lane, k), make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]));
+          __syncwarp();
+          float* dst = p.out_f32 + (size_t)row0 * p.ldo_f32 + ocol;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            const float4 t = lds128(slot + sw128(r, lane & 7));
+            if (row0 + r < p.M && !(p.debug & 1)) *reinterpret_cast<float4*>(dst + (size_t)r * p.ldo_f32 + (lane & 7) * 4) = t;
+          }
+          if (p.col_stats) {
+            // lane = column: (sum, sumsq) over this warp's 32 rows, read back from the staged fp32 tile
+            const uint8_t* src = slot + (lane & 3) * 4;
+            float cs = 0.f, cq = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const float t = lds32(src + sw128(r, lane >> 2));
+              cs += t;
+              cq = fmaf(t, t, cq);
+            }
+            if (row0 < p.M)
+              reinterpret_cast<float2*>(p.col_stats)[(size_t)(row0 >> 5) * p.N + ocol + lane] = make_float2(cs, cq);
+          }
+          __syncwarp();
         }
-        if (p.out_bf16) {
-          if (p.alias_sync) __syncwarp();      // the bf16 tile overwrites the (fully read) fp32 residual tile
-          uint8_t* dst = slot + p.outh_off;
+        if (p.out_bf16 && !(p.debug & 2)) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             uint4 o;
@@ -452,35 +493,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             o.y = pack_bf16(f[8 * k + 2], f[8 * k + 3]);
             o.z = pack_bf16(f[8 * k + 4], f[8 * k + 5]);
             o.w = pack_bf16(f[8 * k + 6], f[8 * k + 7]);
-            sts128u(dst + sw64(lane, k), o);
+            sts128u(slot + sw64(lane, k), o);
           }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        const int ocol = (p.geglu ? (n0 >> 1) : n0) + c * 32;
-        if (lane == 0) {
-          if (p.out_f32) tma_store_2d(&tmOutF, slot + p.outf_off, ocol, row0);
-          if (p.out_bf16) tma_store_2d(&tmOutH, slot + p.outh_off, ocol, row0);
-          bulk_commit();
-        }
-        if (p.col_stats) {
-          // lane = column: (sum, sumsq) over this warp's 32 rows, read back from the staged fp32 tile
-          const uint8_t* src = slot + p.outf_off + (lane & 3) * 4;
-          float cs = 0.f, cq = 0.f;
+          __syncwarp();
+          __nv_bfloat16* dst = p.out_bf16 + (size_t)row0 * p.ldo_bf16 + ocol;
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const float t = lds32(src + sw128(r, lane >> 2));
-            cs += t;
-            cq = fmaf(t, t, cq);
+          for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + (lane >> 2);
+            const uint4 t = lds128u(slot + sw64(r, lane & 3));
+            if (row0 + r < p.M && !(p.debug & 1)) *reinterpret_cast<uint4*>(dst + (size_t)r * p.ldo_bf16 + (lane & 3) * 8) = t;
           }
-          if (row0 < p.M)
-            reinterpret_cast<float2*>(p.col_stats)[(size_t)(row0 >> 5) * p.N + ocol + lane] = make_float2(cs, cq);
+          __syncwarp();
         }
       }
       if (p.row_stats_out && row_ok)
         reinterpret_cast<float2*>(p.row_stats_out)[(size_t)(nb * nhalf + half) * p.M + row] = make_float2(rs, rq);
     }
-    if (lane == 0) bulk_wait_all();          // smem must outlive the last TMA stores
   }
 
   tc_fence_before();
@@ -565,7 +593,7 @@ static int num_sms() {
 }
 
 struct Plan {
-  int bn, cg, stages, nepi, ring, prefetch, alias_sync, slot_bytes, res_off, outf_off, outh_off, tiles_n, num_tiles, grid, smem_bytes;
+  int bn, cg, stages, nepi, ring, slot_bytes, bstat, tiles_n, num_tiles, grid, smem_bytes;
 };
 
 static int env_int(const char* name, int dflt) {
@@ -584,6 +612,10 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
                        (double)d.M * n_out * ((d.out_f32 ? 4 : 0) + (d.out_bf16 ? 2 : 0) + (d.residual ? (d.residual_bf16 ? 2 : 4) : 0));
   const double t_mem = bytes / 5.5e12, t_mma = 2.0 * d.M * N * Kd / 1.6e15;
   int cg = (d.M > BM && t_mma > t_mem) ? 2 : 1;
+  // B-stationary candidates (K <= 320, measured: proj_in 168 -> 118 us, qkv 412 -> 286 us at M = 262144; K = 640 and the
+  // epilogue-bound GEGLU launches ran slower with it): a pair halves the resident panel
+  const bool bstat_ok = d.M > BM && Kd <= 320.0 && !d.geglu && env_int("SEER_GEMM_BSTAT", 1);
+  if (bstat_ok) cg = 2;
   const int fcg = env_int("SEER_GEMM_CG", 0);      // tuning hook
   if (fcg == 1 || fcg == 2) cg = fcg;
   pl.cg = cg;
@@ -615,35 +647,33 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   pl.tiles_n = N / best;
   pl.num_tiles = tiles_m * pl.tiles_n;
   pl.grid = (pl.num_tiles < nsm ? pl.num_tiles : nsm) * cg;
-  // slot layout
-  const bool of = d.out_f32 != nullptr, oh = d.out_bf16 != nullptr;
+  // slot: residual chunk and staged output chunk share the bytes (fp32: 32 x 128 B, bf16: 32 x 64 B)
+  const bool of = d.out_f32 != nullptr;
   const int rm = d.residual ? (d.residual_bf16 ? 2 : 1) : 0;
-  pl.res_off = 0; pl.outf_off = 0; pl.outh_off = 0;
-  int extent;
-  pl.alias_sync = 0;
-  if (rm == 1) {            // fp32 residual at 0 (fp32 output in place); a bf16 copy goes behind it, a bf16-ONLY output
-    if (of) { pl.outh_off = 4096; extent = oh ? 6144 : 4096; }      // reuses the residual's bytes after a warp sync
-    else { pl.outh_off = 0; extent = 4096; pl.alias_sync = 1; }
-  } else if (rm == 2) {
-    if (of) { pl.res_off = 4096; pl.outh_off = 4096; extent = 6144; }
-    else { extent = 2048; }
-  } else {
-    pl.outh_off = of ? 4096 : 0;
-    extent = of ? (oh ? 6144 : 4096) : 2048;
-  }
-  pl.slot_bytes = extent;
-  pl.nepi = env_int("SEER_GEMM_NEPI", (d.geglu || !of) ? 8 : 4);   // bf16-only outputs: small slots, latency-bound epilogue
+  pl.slot_bytes = (of || rm == 1) ? 4096 : 2048;
+  // 8 epilogue warps (two per scheduler, so one warp's dependent-issue latency hides behind the other's) unless a long
+  // main loop (big K) hides the epilogue anyway and the smem is better spent on operand stages
+  pl.nepi = env_int("SEER_GEMM_NEPI", (d.geglu || !of || Kd <= 1280.0) ? 8 : 4);
   if (pl.nepi != 4 && pl.nepi != 8) pl.nepi = 4;
   if (best / (d.geglu ? 64 : 32) < 2) pl.nepi = 4;   // every epilogue warp needs at least one chunk
-  const int stage_bytes = A_BYTES + (best / cg) * BK * 2;
-  const int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - BAR_BYTES - MAX_EPI_WARPS * EVEC_BYTES_PER_WARP;
+  // B-stationary: the CTA keeps the Wt panel of ONE n-block resident (needs grid % tiles_n == 0) and streams only A —
+  // for K <= 640 the per-tile re-read of the panel from L2 (all SMs hammering the same ~100 KB) dominated the operand
+  // traffic and capped these launches at ~25 B/cycle/SM (profiles/)
+  const int Ktot_i = (int)Kd;
+  const int panel_bytes = (Ktot_i / BK) * (best / cg) * BK * 2;
+  const int units_bs = (nsm / pl.tiles_n) * pl.tiles_n;
+  pl.bstat = bstat_ok && panel_bytes <= 120 * 1024 && units_bs > 0 && pl.num_tiles >= 2 * units_bs;
+  if (pl.bstat) pl.grid = units_bs * cg;
+  const int stage_bytes = pl.bstat ? A_BYTES : A_BYTES + (best / cg) * BK * 2;
+  const int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - BAR_BYTES - MAX_EPI_WARPS * EVEC_BYTES_PER_WARP -
+                    (pl.bstat ? panel_bytes : 0);
   // (epilogue warps, ring depth, operand stages) by score: operand stages matter most (up to 5), then 8 epilogue warps
   // for the latency-bound bf16-only / GEGLU epilogues, then ring depth
   const int want_nepi = pl.nepi;
-  const int want_ring = env_int("SEER_EPI_RING", rm ? 6 : 4);
+  const int want_ring = rm ? env_int("SEER_EPI_RING", 4) : 1;    // no residual: the slot is only a staging buffer
   int best_score = -1;
   for (int ne = want_nepi; ne >= 4; ne -= 4) {
-    for (int rg = want_ring; rg >= 3; --rg) {
+    for (int rg = want_ring; rg >= (rm ? 2 : 1); --rg) {
       int st = (avail - ne * rg * pl.slot_bytes) / stage_bytes;
       if (st < 2) continue;
       if (st > 6) st = 6;
@@ -652,14 +682,12 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
     }
   }
   if (best_score < 0) return SEER_EUNSUPPORTED;
-  pl.prefetch = env_int("SEER_EPI_PREFETCH", pl.ring >= 6 ? 2 : pl.ring - 2);
-  if (pl.prefetch < 1) pl.prefetch = 1;
-  if (pl.prefetch > pl.ring - 1) pl.prefetch = pl.ring - 1;
   if (pl.stages < 2) return SEER_EUNSUPPORTED;
   if (pl.stages > 6) pl.stages = 6;
   const int fs = env_int("SEER_GEMM_STAGES", 0);
   if (fs >= 2 && fs <= pl.stages) pl.stages = fs;
-  pl.smem_bytes = pl.stages * stage_bytes + pl.nepi * pl.ring * pl.slot_bytes + BAR_BYTES + pl.nepi * EVEC_BYTES_PER_WARP + 1024;
+  pl.smem_bytes = (pl.bstat ? panel_bytes : 0) + pl.stages * stage_bytes + pl.nepi * pl.ring * pl.slot_bytes + BAR_BYTES +
+                  pl.nepi * EVEC_BYTES_PER_WARP + 1024;
   // > half of the SM's shared memory, so two CTAs (2 x TMEM_COLS could exceed 512 columns) never share an SM
   if (pl.smem_bytes < 120 * 1024) pl.smem_bytes = 120 * 1024;
   return SEER_OK;
@@ -685,7 +713,7 @@ static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, const Plan&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, maps[0], maps[1], maps[2], maps[3], p);
   if (e != cudaSuccess) return (int)e;
   SEER_LAUNCH_CHECK();
   return SEER_OK;
@@ -739,16 +767,18 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   GemmParams p{};
   p.M = d.M; p.N = d.N;
   p.tiles_n = pl.tiles_n; p.num_tiles = pl.num_tiles;
-  p.stages = pl.stages; p.nepi = pl.nepi; p.ring = pl.ring; p.prefetch = pl.prefetch; p.alias_sync = pl.alias_sync; p.slot_bytes = pl.slot_bytes;
-  p.res_off = pl.res_off; p.outf_off = pl.outf_off; p.outh_off = pl.outh_off;
+  p.debug = env_int("SEER_GEMM_DEBUG", 0);
+  p.bstat = pl.bstat;
+  p.stages = pl.stages; p.nepi = pl.nepi; p.ring = pl.ring; p.slot_bytes = pl.slot_bytes;
   p.bias = d.bias; p.ldb = d.ldb > 0 ? d.ldb : d.N; p.bias_div = d.bias_div > 0 ? d.bias_div : 0x7fffffff;
   p.res_mode = d.residual ? (d.residual_bf16 ? 2 : 1) : 0;
-  p.out_f32 = d.out_f32 ? 1 : 0; p.out_bf16 = d.out_bf16 ? 1 : 0;
+  p.out_f32 = (float*)d.out_f32; p.ldo_f32 = d.ldo_f32;
+  p.out_bf16 = (__nv_bfloat16*)d.out_bf16; p.ldo_bf16 = d.ldo_bf16;
   p.geglu = d.geglu ? 1 : 0;
   p.col_stats = d.col_stats; p.row_stats_out = d.row_stats_out;
   p.row_stats_in = d.row_stats_in; p.row_parts_in = d.row_parts_in; p.ln_eps = d.ln_eps; p.ln_colsum = d.ln_colsum;
 
-  CUtensorMap maps[6];
+  CUtensorMap maps[4];
   int Ktot;
   if (d.X) {
     // A 128-pixel M tile must be a whole number of image rows (or of images): W | 128 and the tile never
@@ -782,7 +812,7 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   if (d.K2) { if ((rc = make_map_bf16_k64(&maps[1], d.A2, d.M, d.K2, d.lda2, BM))) return rc; } else maps[1] = maps[0];
   if ((rc = make_map_bf16_k64(&maps[2], d.Wt, d.N, Ktot, Ktot, pl.bn / pl.cg))) return rc;
   const int n_out = d.geglu ? d.N / 2 : d.N;
-  maps[3] = maps[0]; maps[4] = maps[0]; maps[5] = maps[0];
+  maps[3] = maps[0];
   if (d.residual) {
     if (d.residual_bf16)
       rc = make_map_2d(&maps[3], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.residual, d.M, n_out, d.ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
@@ -790,13 +820,6 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
       rc = make_map_2d(&maps[3], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.residual, d.M, n_out, d.ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  if (d.out_f32 &&
-      (rc = make_map_2d(&maps[4], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out_f32, d.M, n_out, d.ldo_f32, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)))
-    return rc;
-  if (d.out_bf16 &&
-      (rc = make_map_2d(&maps[5], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out_bf16, d.M, n_out, d.ldo_bf16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
-    return rc;
-
   cudaStream_t st = (cudaStream_t)stream;
   switch (pl.bn) {
     case 64: return launch_gemm_cg<64>(maps, p, pl, st);

@@ -279,7 +279,6 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
-@_timed_op
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, mode: int, heads: int, n_outer: int, Lq: int = 0,
               Lk: int = 0, F: int = 0, H: int = 0, W: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q/k/v: 2-D bf16 token-major views [rows, heads*d] (column slices of wider buffers are fine)."""
@@ -289,8 +288,17 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, mode: int, h
     d = C // heads
     if out is None:
         out = torch.empty((q.shape[0], C), device=q.device, dtype=torch.bfloat16)
-    rc = _lib.lib().seer_b200_attention(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0), mode,
-                                        heads, d, n_outer, Lq, Lk, F, H, W, _stream())
+    if mode == ATTN_SCTA:
+        ws = 0 if H <= 4 else (8 if H // 8 >= 4 else 4)
+        L = F * (ws * ws if ws else H * W)
+        nprob = n_outer * heads * ((H // ws) * (W // ws) if ws else 1)
+        name, flops = f"attention scta d={d} L={L} x{nprob}", 4.0 * L * (L + 1) / 2 * d * nprob
+    else:
+        name = f"attention {'spatial' if mode == ATTN_SPATIAL else 'cross'} d={d} Lq={Lq} Lk={Lk} x{n_outer * heads}"
+        flops = 4.0 * Lq * Lk * d * n_outer * heads
+    with _Timed(name, flops):
+        rc = _lib.lib().seer_b200_attention(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+                                            mode, heads, d, n_outer, Lq, Lk, F, H, W, _stream())
     _lib.check(rc, f"attention(mode={mode},heads={heads},d={d},outer={n_outer},Lq={Lq},Lk={Lk},F={F},H={H},W={W})")
     _count()
     return out

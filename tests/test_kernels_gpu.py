@@ -283,7 +283,8 @@ def _attn_ref(q, k, v, causal):
     return (s.softmax(-1) @ v.double()).float()
 
 
-@pytest.mark.parametrize("d,frames,L", [(40, 3, 1024), (80, 2, 256), (160, 5, 64), (160, 3, 16), (40, 1, 100)])
+@pytest.mark.parametrize("d,frames,L", [(40, 3, 1024), (80, 2, 256), (160, 5, 64), (160, 3, 16), (40, 1, 100), (40, 5, 256),
+                                        (40, 2, 4096)])
 def test_attention_spatial(d, frames, L):
     heads = 8
     C = heads * d
@@ -308,7 +309,8 @@ def test_attention_cross_77(d, frames, L):
     assert rel(out.float(), ref) < 6e-3
 
 
-@pytest.mark.parametrize("d,B,Fr,H", [(40, 2, 3, 32), (80, 1, 4, 16), (160, 2, 3, 8), (160, 2, 5, 4), (40, 1, 2, 64)])
+@pytest.mark.parametrize("d,B,Fr,H", [(40, 2, 3, 32), (80, 1, 4, 16), (160, 2, 3, 8), (160, 2, 5, 4), (40, 1, 2, 64),
+                                      (40, 2, 4, 32), (40, 1, 16, 32)])
 def test_attention_scta(d, B, Fr, H):
     heads = 8
     C = heads * d
