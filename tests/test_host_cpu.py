@@ -65,18 +65,22 @@ def test_sampler_schedule_matches_reference_golden(golden_dir):
 
 
 def test_packing_layouts():
-    w = torch.arange(2 * 3 * 9, dtype=torch.float32).reshape(2, 3, 3, 3)
+    cin = 128
+    w = torch.arange(2 * cin * 9, dtype=torch.float32).reshape(2, cin, 3, 3) % 251   # exact in bf16
     p = packing.pack_conv3x3(w).float()
+    # K order [Cin/64][ky][kx][64]: one K block per (64-channel slab, tap)
     for co in range(2):
-        for ci in range(3):
+        for ci in range(0, cin, 7):
             for ky in range(3):
                 for kx in range(3):
-                    assert p[co, (ky * 3 + kx) * 3 + ci] == w[co, ci, ky, kx]
+                    assert p[co, (ci // 64) * 9 * 64 + (ky * 3 + kx) * 64 + ci % 64] == w[co, ci, ky, kx]
+    with pytest.raises(ValueError):
+        packing.pack_conv3x3(torch.zeros(2, 3, 3, 3))
     perm = packing.geglu_permutation(128)
     assert perm[:32].tolist() == list(range(32)) and perm[32:64].tolist() == list(range(128, 160))
     assert perm[64:96].tolist() == list(range(32, 64)) and sorted(perm.tolist()) == list(range(256))
-    sc = torch.ones(2, 5, 1, 1)
-    assert packing.pack_conv3x3(w, sc).shape == (2, 27 + 5)
+    sc = torch.ones(2, 64, 1, 1)
+    assert packing.pack_conv3x3(w, sc).shape == (2, 9 * cin + 64)
     assert packing.pack_conv_out(torch.zeros(4, 8, 3, 3)).shape == (4, 9, 8)
 
 
