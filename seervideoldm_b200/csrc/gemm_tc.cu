@@ -22,101 +22,12 @@
 //               transactions.  No epilogue global load/store is issued by the LSU except the bias vector.
 //
 // Epilogue options (all warp-uniform runtime branches): see SeerGemmDesc in include/seer_b200.h.
-#include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include "seer_b200.h"
 
 #include <stdlib.h>
 
 namespace seer {
-
-constexpr int BM = 128;
-constexpr int BK = 64;
-constexpr int A_BYTES = BM * BK * 2;
-constexpr int MAX_STAGES = 8;
-constexpr int MAX_EPI_WARPS = 8;
-constexpr int MAX_RING = 8;
-constexpr int GEMM_MAX_THREADS = 64 + 32 * MAX_EPI_WARPS;
-constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int BAR_BYTES = 1024;
-constexpr int EVEC_FLOATS = 256;                       // per-warp staging of the tile's bias / LN column-sum slices (BN <= 256)
-constexpr int EVEC_BYTES_PER_WARP = 2 * EVEC_FLOATS * 4;
-
-struct GemmParams {
-  int M, N;            // N = accumulator columns (GEGLU: twice the output columns)
-  int mode;            // 0 plain, 1 conv3x3
-  int kb_main;         // k-blocks (of 64) from the main source
-  int kb_total;        // + k-blocks from the tail source
-  int cblk;            // conv: Cin / 64
-  int H, W;            // conv image geometry
-  int tiles_n, num_tiles;
-  int stages, nepi, ring, slot_bytes;
-  int bstat;           // 1: the whole Wt panel of this CTA's (fixed) n-block is resident in smem; only A is streamed
-  int debug;           // tuning hook SEER_GEMM_DEBUG: 1 = skip the global stores, 2 = skip staging + stores (timing experiments only)
-  const float* bias;
-  int ldb;
-  int bias_div;
-  int res_mode;        // 0 none, 1 fp32, 2 bf16
-  float* out_f32;      // fp32 output (or null), leading dim ldo_f32 elements
-  int ldo_f32;
-  __nv_bfloat16* out_bf16;
-  int ldo_bf16;
-  int geglu;
-  float* col_stats;
-  float* row_stats_out;
-  const float* row_stats_in;
-  int row_parts_in;
-  float ln_inv_dim, ln_eps;
-  const float* ln_colsum;
-};
-
-// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile — each
-// CTA stages its own 128 A rows and only HALF of the Wt rows, so the L2 -> SM operand traffic per FLOP drops by
-// 64*(128+BN)/BN -> 64*(128+BN/2)/BN bytes per MMA cycle (the measured limiter of the 1-CTA kernel, profiles/).
-template <int BN, int CG>
-struct GemmCfg {
-  static constexpr int B_BYTES = (BN / CG) * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TBUF = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // TMEM column stride between the 2 buffers
-  static constexpr int TMEM_COLS = 2 * TBUF;
-};
-
-// byte offset of 16-byte chunk `j` of row `r` inside a TMA-swizzled box whose rows are 128 B / 64 B wide
-__device__ __forceinline__ int sw128(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
-__device__ __forceinline__ int sw64(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
-
-// v = rstd * (v - mean * colsum[col]) + bias[col]   (folded LayerNorm and/or bias) on one 32-column accumulator chunk.
-// `cs` / `b` point at this chunk's slices (shared memory on the fast path).
-template <bool LN, bool BIAS, bool SMEM>
-__device__ __forceinline__ void epi_affine32(uint32_t (&v)[32], const float* cs, const float* b, float rstd, float neg_mean) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (LN) c4 = lds128(cs + 4 * k);
-    if (BIAS) b4 = SMEM ? lds128(b + 4 * k) : __ldg(reinterpret_cast<const float4*>(b) + k);
-    float x0 = __uint_as_float(v[4 * k]), x1 = __uint_as_float(v[4 * k + 1]), x2 = __uint_as_float(v[4 * k + 2]),
-          x3 = __uint_as_float(v[4 * k + 3]);
-    if (LN) {
-      x0 = fmaf(rstd, fmaf(neg_mean, c4.x, x0), b4.x); x1 = fmaf(rstd, fmaf(neg_mean, c4.y, x1), b4.y);
-      x2 = fmaf(rstd, fmaf(neg_mean, c4.z, x2), b4.z); x3 = fmaf(rstd, fmaf(neg_mean, c4.w, x3), b4.w);
-    } else if (BIAS) {
-      x0 += b4.x; x1 += b4.y; x2 += b4.z; x3 += b4.w;
-    }
-    v[4 * k] = __float_as_uint(x0); v[4 * k + 1] = __float_as_uint(x1);
-    v[4 * k + 2] = __float_as_uint(x2); v[4 * k + 3] = __float_as_uint(x3);
-  }
-}
-// cs always points into shared memory; b into shared memory (smem_bias) or at a global bias row
-__device__ __forceinline__ void epi_affine32_dispatch(uint32_t (&v)[32], bool ln, bool bias, bool smem_bias, const float* cs,
-                                                      const float* b, float rstd, float neg_mean) {
-  if (ln) {
-    if (!bias) epi_affine32<true, false, true>(v, cs, b, rstd, neg_mean);
-    else if (smem_bias) epi_affine32<true, true, true>(v, cs, b, rstd, neg_mean);
-    else epi_affine32<true, true, false>(v, cs, b, rstd, neg_mean);
-  } else if (bias) {
-    if (smem_bias) epi_affine32<false, true, true>(v, cs, b, rstd, neg_mean);
-    else epi_affine32<false, true, false>(v, cs, b, rstd, neg_mean);
-  }
-}
 
 template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_MAX_THREADS, 1)
@@ -294,221 +205,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp < 2 + p.nepi) {
-    // ===================== epilogue warps =====================
-    const int ew = warp - 2;
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int nhalf = p.nepi >> 2;           // 1 or 2 warps per quarter; they interleave the column chunks
-    const int half = ew >> 2;
-    const int cw = p.geglu ? 64 : 32;        // accumulator columns per chunk (always 32 output columns)
-    const int nch = BN / cw;
-    const int my_nch = (nch - half + nhalf - 1) / nhalf;
-    const int my_tiles = (p.num_tiles - unit + nunits - 1) / nunits;
-    const uint32_t tempty0 = CG == 2 ? mapa_shared(smem_u32(tmem_empty_bar), 0) : 0;   // the leader's tmem_empty barriers
-    const int total = my_tiles * my_nch;
-    // Ring of R smem slots per warp.  A slot first receives the TMA-prefetched residual chunk (32 rows x 32 cols),
-    // then stages the output chunk for the coalesced copy-out; it is free again as soon as the warp has read it back,
-    // so the residual for step g + R - 1 can be requested at the top of step g.
-    const int R = p.ring, P = p.ring - 1;
-    uint8_t* ring = ring_base + (size_t)ew * R * p.slot_bytes;
-    uint64_t* rfull = res_full_bar + ew * MAX_RING;
-    const uint32_t res_bytes = p.res_mode == 1 ? 4096u : 2048u;
-
-    // residual prefetch cursor (tile / chunk of step g + P), advanced incrementally: no divisions in the chunk loop
-    int pf_step = 0, pf_tile = unit, pf_j = 0;
-    auto issue_res = [&]() {                 // lane 0: TMA-prefetch the residual chunk of step pf_step, then advance
-      const int mb2 = pf_tile / p.tiles_n, nb2 = pf_tile - mb2 * p.tiles_n;
-      const int s2 = pf_step % R;
-      mbar_arrive_expect_tx(&rfull[s2], res_bytes);
-      tma_load_2d(ring + s2 * p.slot_bytes, &tmRes, &rfull[s2], nb2 * BN + (half + pf_j * nhalf) * 32,
-                  (mb2 * CG + rank) * BM + q * 32);
-    };
-    auto advance_pf = [&]() {
-      ++pf_step;
-      if (++pf_j == my_nch) { pf_j = 0; pf_tile += nunits; }
-    };
-    if (p.res_mode) {
-      for (int st = 0; st < P && st < total; ++st) {
-        if (lane == 0) issue_res();
-        advance_pf();
-      }
-      __syncwarp();
+    // ===================== epilogue warps (gemm_epilogue.cuh) =====================
+#define SEER_EPI(SPEC)                                                                                                  \
+  gemm_epilogue_warp<BN, CG, SPEC>(p, &tmRes, ring_base, tmem_full_bar, tmem_empty_bar, res_full_bar, evec_base, tmem_base, \
+                                   warp, lane, rank, unit, nunits)
+    switch (p.epi_spec) {
+      case EK_PIN: SEER_EPI(EK_PIN); break;
+      case EK_QKV: SEER_EPI(EK_QKV); break;
+      case EK_ATTN_OUT: SEER_EPI(EK_ATTN_OUT); break;
+      case EK_FF2: SEER_EPI(EK_FF2); break;
+      case EK_POUT: SEER_EPI(EK_POUT); break;
+      case EK_CONV: SEER_EPI(EK_CONV); break;
+      case EK_BF16: SEER_EPI(EK_BF16); break;
+      case EK_FF1:
+        if constexpr (BN == 128 || BN == 256) SEER_EPI(EK_FF1);
+        break;
+      case EK_FF1_PLAIN:
+        if constexpr (BN == 128 || BN == 256) SEER_EPI(EK_FF1_PLAIN);
+        break;
+      default: SEER_EPI(-1); break;
     }
-
-    const bool want_stats = p.col_stats != nullptr || p.row_stats_out != nullptr;
-    int g = 0, it = 0;
-    for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
-      const int mb = tile / p.tiles_n, nb = tile - mb * p.tiles_n;
-      const int m0 = (mb * CG + rank) * BM, n0 = nb * BN;
-      const int buf = it & 1;
-      const int row0 = m0 + q * 32;
-      const int row = row0 + lane;
-      const bool row_ok = row < p.M;
-      const float* bias_row = p.bias ? p.bias + (size_t)(row_ok ? row / p.bias_div : 0) * p.ldb : nullptr;
-      // Nearly all of the SM's L1/shared array is carved as shared memory, so per-chunk __ldg's of the bias / LN
-      // column-sum vectors would each pay an L2 round trip.  Stage this tile's slices in shared memory once, before
-      // waiting for the accumulator (the load latency hides behind the main loop).
-      float* vb = evec_base + ew * (2 * EVEC_FLOATS);
-      float* vc = vb + EVEC_FLOATS;
-      const int rlast = min(row0 + 31, p.M - 1);
-      const bool bias_smem = p.bias && row0 < p.M && (row0 / p.bias_div == rlast / p.bias_div);   // one bias row for the warp
-      __syncwarp();
-      if (bias_smem) {
-        const float* src = p.bias + (size_t)(row0 / p.bias_div) * p.ldb + n0;
-        for (int i = lane; i < BN; i += 32) sts32(vb + i, __ldg(src + i));
-      }
-      if (p.row_stats_in)
-        for (int i = lane; i < BN; i += 32) sts32(vc + i, __ldg(p.ln_colsum + n0 + i));
-      __syncwarp();
-      float mean = 0.f, rstd = 1.f;
-      if (p.row_stats_in && row_ok) {        // folded LayerNorm: combine the producer's per-row partial sums
-        float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < p.row_parts_in; ++i) {
-          const float2 t = __ldg(reinterpret_cast<const float2*>(p.row_stats_in) + (size_t)i * p.M + row);
-          s1 += t.x;
-          s2 += t.y;
-        }
-        mean = s1 * p.ln_inv_dim;
-        rstd = rsqrtf(fmaxf(s2 * p.ln_inv_dim - mean * mean, 0.f) + p.ln_eps);
-      }
-      float rs = 0.f, rq = 0.f;
-
-      for (int j = 0; j < my_nch; ++j, ++g) {
-        const int c = half + j * nhalf;
-        const int s = g % R;
-        uint8_t* slot = ring + s * p.slot_bytes;
-        if (p.res_mode && pf_step < total) { // slot (g+P)%R = (g-1)%R was fully consumed in the previous step
-          if (lane == 0) issue_res();
-          advance_pf();
-          __syncwarp();
-        }
-        if (j == 0) {
-          mbar_wait(&tmem_full_bar[buf], ((uint32_t)it >> 1) & 1);
-          tc_fence_after();
-        }
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * C::TBUF + c * cw);
-        float f[32];
-        {
-          const bool ln = p.row_stats_in != nullptr;
-          uint32_t v[32];
-          tmem_ld_32x32(taddr, v);
-          if (!p.geglu) {
-            tmem_ld_wait();
-            if (j == my_nch - 1) {           // last TMEM read of this tile by this warp: hand the buffer back
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                if (CG == 2) mbar_arrive_cluster(tempty0 + (uint32_t)buf * 8u); else mbar_arrive(&tmem_empty_bar[buf]);
-              }
-            }
-            epi_affine32_dispatch(v, ln, p.bias != nullptr, bias_smem, vc + c * 32, bias_smem ? vb + c * 32 : bias_row + n0 + c * 32,
-                                  rstd, -mean);
-#pragma unroll
-            for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
-          } else {
-            uint32_t vg[32];
-            tmem_ld_32x32(taddr + 32, vg);
-            tmem_ld_wait();
-            if (j == my_nch - 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                if (CG == 2) mbar_arrive_cluster(tempty0 + (uint32_t)buf * 8u); else mbar_arrive(&tmem_empty_bar[buf]);
-              }
-            }
-            // GEGLU: accumulator columns [c*64, +32) are "value", [c*64+32, +64) the matching "gate" (bias is staged)
-            epi_affine32_dispatch(v, ln, true, true, vc + c * 64, vb + c * 64, rstd, -mean);
-            epi_affine32_dispatch(vg, ln, true, true, vc + c * 64 + 32, vb + c * 64 + 32, rstd, -mean);
-#pragma unroll
-            for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]) * gelu_erf_tanhfit(__uint_as_float(vg[k]));
-          }
-        }
-        // ---- residual (prefetched into the slot by TMA) ----
-        if (p.res_mode) {
-          mbar_wait(&rfull[s], ((uint32_t)(g / R)) & 1);
-          const uint8_t* rsrc = slot;
-          if (p.res_mode == 1) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float4 t = lds128(rsrc + sw128(lane, k));
-              f[4 * k] += t.x; f[4 * k + 1] += t.y; f[4 * k + 2] += t.z; f[4 * k + 3] += t.w;
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint4 t = lds128u(rsrc + sw64(lane, k));
-              const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), cc = unpack_bf16(t.z), d = unpack_bf16(t.w);
-              f[8 * k] += a.x; f[8 * k + 1] += a.y; f[8 * k + 2] += b.x; f[8 * k + 3] += b.y;
-              f[8 * k + 4] += cc.x; f[8 * k + 5] += cc.y; f[8 * k + 6] += d.x; f[8 * k + 7] += d.y;
-            }
-          }
-        }
-        if (want_stats) {
-          if (!row_ok) {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) f[k] = 0.f;
-          }
-          if (p.row_stats_out) {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) { rs += f[k]; rq = fmaf(f[k], f[k], rq); }
-          }
-        }
-        // ---- outputs: stage the chunk in the slot (thread = row, XOR-swizzled 16-byte pieces: conflict-free), then
-        // copy it out with coalesced 128-bit global stores (each warp store covers 4 full 128-byte lines).  This stays
-        // in the generic proxy: a TMA store would need fence.proxy.async + a bulk-group round trip per chunk, measured
-        // at ~1000 cycles of serial latency per warp (tools/tma_store_bench.cu) — the L0 epilogues were bound by it.
-        const int ocol = (p.geglu ? (n0 >> 1) : n0) + c * 32;
-        __syncwarp();                          // every lane has read its residual row: the slot may be overwritten
-        if (p.out_f32 && !(p.debug & 2)) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            sts128(slot + sw128(lane, k), make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]));
-          __syncwarp();
-          float* dst = p.out_f32 + (size_t)row0 * p.ldo_f32 + ocol;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + (lane >> 3);
-            const float4 t = lds128(slot + sw128(r, lane & 7));
-            if (row0 + r < p.M && !(p.debug & 1)) *reinterpret_cast<float4*>(dst + (size_t)r * p.ldo_f32 + (lane & 7) * 4) = t;
-          }
-          if (p.col_stats) {
-            // lane = column: (sum, sumsq) over this warp's 32 rows, read back from the staged fp32 tile
-            const uint8_t* src = slot + (lane & 3) * 4;
-            float cs = 0.f, cq = 0.f;
-#pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              const float t = lds32(src + sw128(r, lane >> 2));
-              cs += t;
-              cq = fmaf(t, t, cq);
-            }
-            if (row0 < p.M)
-              reinterpret_cast<float2*>(p.col_stats)[(size_t)(row0 >> 5) * p.N + ocol + lane] = make_float2(cs, cq);
-          }
-          __syncwarp();
-        }
-        if (p.out_bf16 && !(p.debug & 2)) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint4 o;
-            o.x = pack_bf16(f[8 * k], f[8 * k + 1]);
-            o.y = pack_bf16(f[8 * k + 2], f[8 * k + 3]);
-            o.z = pack_bf16(f[8 * k + 4], f[8 * k + 5]);
-            o.w = pack_bf16(f[8 * k + 6], f[8 * k + 7]);
-            sts128u(slot + sw64(lane, k), o);
-          }
-          __syncwarp();
-          __nv_bfloat16* dst = p.out_bf16 + (size_t)row0 * p.ldo_bf16 + ocol;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = 8 * i + (lane >> 2);
-            const uint4 t = lds128u(slot + sw64(r, lane & 3));
-            if (row0 + r < p.M && !(p.debug & 1)) *reinterpret_cast<uint4*>(dst + (size_t)r * p.ldo_bf16 + (lane & 3) * 8) = t;
-          }
-          __syncwarp();
-        }
-      }
-      if (p.row_stats_out && row_ok)
-        reinterpret_cast<float2*>(p.row_stats_out)[(size_t)(nb * nhalf + half) * p.M + row] = make_float2(rs, rq);
-    }
+#undef SEER_EPI
   }
 
   tc_fence_before();
@@ -767,10 +484,22 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   GemmParams p{};
   p.M = d.M; p.N = d.N;
   p.tiles_n = pl.tiles_n; p.num_tiles = pl.num_tiles;
-  p.debug = env_int("SEER_GEMM_DEBUG", 0);
+  {
+    // epilogue specialisation: the option combinations of the UNet's hot launches are compiled as straight-line code
+    const int flags = (d.row_stats_in ? EF_LN : 0) | (d.geglu ? EF_GEGLU : 0) | ((d.residual && !d.residual_bf16) ? EF_RES32 : 0) |
+                      (d.out_f32 ? EF_OUT32 : 0) | (d.out_bf16 ? EF_OUT16 : 0) | (d.col_stats ? EF_CSTAT : 0) |
+                      (d.row_stats_out ? EF_RSTAT : 0);
+    static const int kinds[] = {EK_PIN, EK_QKV, EK_ATTN_OUT, EK_FF1, EK_FF1_PLAIN, EK_FF2, EK_POUT, EK_CONV, EK_BF16};
+    p.epi_spec = -1;
+    const bool generic_forced = env_int("SEER_GEMM_GENERIC", 0) != 0 && !d.geglu;    // A/B hook
+    if (d.bias && !(d.residual && d.residual_bf16) && !generic_forced)
+      for (int k : kinds)
+        if (k == flags) p.epi_spec = k;
+    if (d.geglu && p.epi_spec < 0) return SEER_EUNSUPPORTED;
+  }
   p.bstat = pl.bstat;
   p.stages = pl.stages; p.nepi = pl.nepi; p.ring = pl.ring; p.slot_bytes = pl.slot_bytes;
-  p.bias = d.bias; p.ldb = d.ldb > 0 ? d.ldb : d.N; p.bias_div = d.bias_div > 0 ? d.bias_div : 0x7fffffff;
+  p.bias = d.bias; p.ldb = d.ldb > 0 ? d.ldb : d.N; p.bias_div = d.bias_div > 0 ? d.bias_div : BIAS_ONE_ROW;
   p.res_mode = d.residual ? (d.residual_bf16 ? 2 : 1) : 0;
   p.out_f32 = (float*)d.out_f32; p.ldo_f32 = d.ldo_f32;
   p.out_bf16 = (__nv_bfloat16*)d.out_bf16; p.ldo_bf16 = d.ldo_bf16;
