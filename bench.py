@@ -40,8 +40,9 @@ GFLOP_PER_EVAL = 3865.9
 TEXT_KV_GFLOP = 47.23          # cached across evaluations 2..31 -> subtracted, not credited
 # dram__bytes_read.sum + dram__bytes_write.sum per gemm_tc_kernel launch from the committed `ncu --set full` capture
 # (profiles/r1_gemm_full_v4.summary.txt: 8 level-1 launches, mean 418.5 MB against 454.0 MB algorithmic)
-NCU_TRAFFIC = {"bytes_per_launch": 418.5e6, "algorithmic_bytes_per_launch": 454.0e6,
-               "source": "profiles/r1_gemm_full_v4.summary.txt (8 level-1 GEMM launches of one evaluation)"}
+NCU_TRAFFIC = 418.5e6
+NCU_TRAFFIC_NOTE = ("bytes per launch, mean of 8 level-1 GEMM launches of one evaluation under ncu --set full "
+                    "(profiles/r1_gemm_full_v4.summary.txt); their algorithmic bytes: 454.0e6")
 
 
 def workload_name() -> str:
@@ -271,7 +272,7 @@ def run_ours(args):
         t_ms = sum(p[2].elapsed_time(p[3]) for p in prof)
         achieved = flops / (t_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["sustained"], "traffic": NCU_TRAFFIC, "kernel": "gemm_tc_kernel<BN> (tcgen05 GEMM + implicit-GEMM conv3x3)",
+                "frac": achieved / peaks["sustained"], "traffic": NCU_TRAFFIC, "traffic_note": NCU_TRAFFIC_NOTE, "kernel": "gemm_tc_kernel<BN> (tcgen05 GEMM + implicit-GEMM conv3x3)",
                 "launches_timed": len(prof), "avg_launch_ms": t_ms / max(1, len(prof)),
                 "flops_per_launch_avg": flops / max(1, len(prof)), "peak_source": peaks["source"] + ", sustained bf16",
                 "frac_of_burst_peak": achieved / peaks["burst"],

@@ -29,6 +29,7 @@ extern "C" {
 #define SEER_ATTN_SPATIAL 0
 #define SEER_ATTN_CROSS 1
 #define SEER_ATTN_SCTA 2
+#define SEER_ATTN_FRAME 3 /* causal attention along the frame axis, one sequence per (clip, token): FSText temporal blocks */
 
 const char* seer_b200_version(void);
 
@@ -107,7 +108,9 @@ int seer_b200_layernorm(const float* x, int M, int C, int ldx, const float* gamm
 
 /* softmax(Q K^T / sqrt(d)) V over token-major bf16 buffers; row gathers implement the reference's head split and window
  * partition.  SPATIAL/CROSS: n_outer = b*f frames, sequences Lq/Lk rows per frame.  SCTA: n_outer = b, geometry (F,H,W),
- * window rule and causal order of attention.py:632-703 (Lq/Lk ignored).  head_dim in {40, 80, 160}.
+ * window rule and causal order of attention.py:632-703 (Lq/Lk ignored).  FRAME: n_outer = clips, F = frames, H = tokens
+ * per frame (W ignored): causal over the F frames of each (clip, token) — the FSText temporal blocks, attention.py:393-396,
+ * 521-524.  head_dim in {40, 80, 96, 160}.
  * Replaces xformers.ops.memory_efficient_attention at attention.py:622-630. */
 int seer_b200_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int mode,
                         int heads, int head_dim, int n_outer, int Lq, int Lk, int F, int H, int W, void* stream);
@@ -148,6 +151,30 @@ int seer_b200_cast_f32_to_bf16(const float* x, void* y, long long n, void* strea
 int seer_b200_cfg_ddim_update(const float* eps, const float* x, float* x_prev, float* pred_x0, int b, int C, int F2, int cond_f,
                               int HW, int use_cfg, float scale, float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev,
                               float dir_coef, void* stream);
+
+/* ---- fp32-parity path (rel-L2 <= 1e-4 against the reference's fp32 PyTorch forward) --------------------------------
+ * Contractions run on seer_b200_gemm_ex with error-compensated bf16 operands: A' = [a_hi | a_hi | a_lo] (this split),
+ * W' = [w_hi | w_lo | w_hi] (host packing), so A'.W' = a_hi.w_hi + a_hi.w_lo + a_lo.w_hi with fp32 accumulation. */
+
+/* x fp32 [rows_in, C] (ldx) -> out bf16 [rows_out, ldo]: out[r, col0+c] = out[r, Ctot+col0+c] = bf16(x), out[r, 2*Ctot+col0+c]
+ * = bf16(x - bf16(x)).  col0 / Ctot place one part of a channel concat (torch.cat at unet_3d_blocks.py:596,712).
+ * up_H > 0: rows are pixels of [up_n_img, up_H, up_W] images and the output is the nearest 2x upsampling
+ * [up_n_img, 2 up_H, 2 up_W] (resnet.py:52), rows_out = 4 rows_in. */
+int seer_b200_split3_bf16(const float* x, int ldx, long long rows_in, int C, void* out, int ldo, int Ctot, int col0, int up_n_img,
+                          int up_H, int up_W, void* stream);
+/* LayerNorm fp32 -> fp32 (attention.py:198-200). */
+int seer_b200_layernorm_f32(const float* x, int M, int C, int ldx, const float* gamma, const float* beta, float eps, float* y,
+                            int ldy, void* stream);
+/* out[M, inner] = h[:, :inner] * gelu_erf(h[:, inner:])  (GEGLU, attention.py:791-793), exact erff. */
+int seer_b200_geglu_f32(const float* h, int ldh, float* out, int ldo, long long M, int inner, void* stream);
+/* RoPE in place on the Q / K column blocks of a fp32 (is_f32) or bf16 buffer; position = (row / pos_div) % pos_mod
+ * (UNet SCTA: pos_div 1, pos_mod F*h*w, attention.py:649-651; FSText frame axis: pos_div 77, pos_mod F, :529-530). */
+int seer_b200_rope_ex(void* qk, int is_f32, int ld, int M, int pos_div, int pos_mod, int heads, int head_dim, int q_col, int k_col,
+                      const float* freqs, int n_freqs, void* stream);
+/* fp32 softmax attention, same modes / row gathers as seer_b200_attention plus SEER_ATTN_FRAME (n_outer = clips,
+ * F = frames, H = tokens per frame); head_dim in {40, 80, 96, 160}. */
+int seer_b200_attention_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo, int mode,
+                            int heads, int head_dim, int n_outer, int Lq, int Lk, int F, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,12 @@ SIGNATURES = {
     "seer_b200_im2col3x3_to_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "seer_b200_cast_f32_to_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "seer_b200_cfg_ddim_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f, _vp]),
+    # fp32-parity path
+    "seer_b200_split3_bf16": (_i, [_vp, _i, _ll, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "seer_b200_layernorm_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp]),
+    "seer_b200_geglu_f32": (_i, [_vp, _i, _vp, _i, _ll, _i, _vp]),
+    "seer_b200_rope_ex": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "seer_b200_attention_f32": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

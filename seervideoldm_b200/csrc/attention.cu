@@ -307,6 +307,14 @@ int seer::attention_mma_launch(const void* q, int ldq, const void* k, int ldk, c
     if (p.ws) SEER_CHECK_ARG(H % p.ws == 0 && W % p.ws == 0);
     p.causal = 1;
     n_problems = n_outer * p.nwin * heads;
+  } else if (mode == SEER_ATTN_FRAME) {
+    // causal attention over the F frames of token l (H = tokens per frame) of clip b = SCTA geometry with a 1x1 window
+    // per token: row = (b*F + f)*H + l  (FSText temporal blocks, attention.py:393-396)
+    SEER_CHECK_ARG(F > 0 && H > 0);
+    p.mode = SEER_ATTN_SCTA;
+    p.F = F; p.H = H; p.W = 1; p.ws = 1; p.nwx = 1; p.nwin = H; p.Lq = p.Lk = F;
+    p.causal = 1;
+    n_problems = n_outer * p.nwin * heads;
   } else if (mode == SEER_ATTN_SPATIAL || mode == SEER_ATTN_CROSS) {
     SEER_CHECK_ARG(Lq > 0 && Lk > 0);
     p.Lq = Lq; p.Lk = Lk; p.causal = 0;
@@ -320,6 +328,7 @@ int seer::attention_mma_launch(const void* q, int ldq, const void* k, int ldk, c
   switch (head_dim) {
     case 40: return launch_attention<40>(p, n_problems, (cudaStream_t)stream);
     case 80: return launch_attention<80>(p, n_problems, (cudaStream_t)stream);
+    case 96: return launch_attention<96>(p, n_problems, (cudaStream_t)stream);
     case 160: return launch_attention<160>(p, n_problems, (cudaStream_t)stream);
     default: return SEER_EUNSUPPORTED;
   }

@@ -12,9 +12,14 @@
 //           split (column offset head*40) and the window partition (a 4-D box {64 ch, 8, 8, 2 frames} of the
 //           [B*F, H, W, C] view) are TMA coordinates — no gather, no copies.  Columns 40..63 of a box belong to the next
 //           head; Q's are zeroed in smem once, so they contribute nothing to Q K^T, and the matching O columns are dropped.
-//   warp 1  tcgen05.mma: S[128x128] = Q K^T into TMEM; then O_j[128x64] = P V (P from smem, V as MN-major B operand).
-//   warps 2-5  softmax, thread = query row = TMEM lane: two passes over S (max, then exp2 / sum / bf16 P -> smem in the
-//           UMMA K-major swizzled layout), then O_acc = O_acc * corr + O_j from TMEM, all fp32 in registers.
+//   warp 1  tcgen05.mma: S[128x128] = Q K^T into TMEM; then O[128x64] += P V (P from smem, V as MN-major B operand),
+//           accumulated IN TMEM across all key tiles.
+//   warps 2-5  softmax, thread = query row = TMEM lane: the 128 scores of the row are pulled into registers with four
+//           back-to-back tcgen05.ld (one wait), S is handed back to the MMA warp at once (so Q K^T of tile j+1 runs under
+//           the softmax of tile j), then max / exp2 / sum / bf16 P -> smem in the UMMA K-major swizzled layout.
+//           The running maximum is LAZY: it is raised (and O in TMEM rescaled by a tcgen05.ld / st round trip) only when
+//           some row of the warp would otherwise produce P > 2^8 — with the stale maximum P / l stay exact because both
+//           use the same reference, so the per-tile O correction of flash attention leaves the critical path.
 // The kernel is MUFU-bound by design (128x128 exp2 per tile = 1024 SM cycles vs 512 tensor cycles).
 #include "common.cuh"
 #include "seer_b200.h"
@@ -77,8 +82,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* s_full = bars + 6;     // S in TMEM
   uint64_t* s_free = bars + 7;     // softmax finished reading S (count 4)
   uint64_t* p_full = bars + 8;     // P in smem (count 4)
-  uint64_t* o_full = bars + 9;     // O_j in TMEM
-  uint64_t* o_free = bars + 10;    // softmax finished reading O_j (count 4)
+  uint64_t* o_full = bars + 9;     // P V of tile j has completed (O updated, P and V consumed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -110,7 +114,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(s_free, 4);
     mbar_init(p_full, 4);
     mbar_init(o_full, 1);
-    mbar_init(o_free, 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -159,10 +162,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint64_t p_desc0 = umma_desc_sw128(smem_u32(sP));
     const uint64_t p_desc1 = umma_desc_sw128(smem_u32(sP + AT_BM * 128));
     mbar_wait(q_ready, 0);
-    for (int j = 0; j < n_kv; ++j) {
-      const uint32_t ph = j & 1;
-      mbar_wait(k_full, ph);
-      mbar_wait(s_free, ph ^ 1);               // softmax has drained S of tile j-1
+    // S(j+1) = Q K(j+1)^T is issued BEFORE the P V of tile j: it only needs the softmax warps to have pulled S(j) into
+    // registers (s_free), so it runs under the exp pass of tile j and S is ready when the softmax warps come back.
+    auto issue_s = [&](int j) {
+      mbar_wait(k_full, j & 1);
+      mbar_wait(s_free, (j & 1) ^ 1);          // softmax has drained S of tile j-1
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -172,16 +176,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         umma_commit(k_empty);
       }
       __syncwarp();
+    };
+    issue_s(0);
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = j & 1;
+      if (j + 1 < n_kv) issue_s(j + 1);
       mbar_wait(v_full, ph);
-      mbar_wait(p_full, ph);
-      mbar_wait(o_free, ph ^ 1);               // softmax has drained O of tile j-1
+      mbar_wait(p_full, ph);                   // P of tile j in smem; any rescale of O by the softmax warps has retired
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AT_BN / 16; ++k) {
           // A: 16 keys = 32 B inside the 64-key atom (two atoms 16 KB apart); B: 16 keys = two 8-row groups = 2048 B
           const uint64_t a = (k < 4 ? p_desc0 : p_desc1) + (uint64_t)((k & 3) * 2);
-          umma_bf16(tO, a, v_desc + (uint64_t)(k * 128), idesc_o, k != 0);
+          umma_bf16(tO, a, v_desc + (uint64_t)(k * 128), idesc_o, (j | k) != 0);
         }
         umma_commit(o_full);
         umma_commit(v_empty);
@@ -201,10 +209,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncwarp();
     if (lane == 0) mbar_arrive(q_ready);
 
-    float o_acc[48];
-#pragma unroll
-    for (int i = 0; i < 48; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;      // m_run: the (lazily raised) reference maximum of this row
     const float sl2 = p.scale_log2;
     const int qi = qt * AT_BM + r;             // query index in the sequence
 
@@ -215,74 +220,125 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int k_hi = min(p.Lk - kv0, p.causal && j == qt ? r + 1 : AT_BN);   // keys [0, k_hi) of this tile are visible
       mbar_wait(s_full, ph);
       tc_fence_after();
-      // ---- pass 1: row maximum ----
-      float mx = m_run;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_addr + c * 32, v);
-        tmem_ld_wait();
-        if (need_mask) {
+      // ---- the whole score row into registers, S handed back to the MMA warp ----
+      uint32_t v[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + lane_addr + c * 32, v[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      // ---- row maximum of this tile (4 independent chains) ----
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (need_mask) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int k = 0; k < 32; ++k)
-            if (c * 32 + k < k_hi) mx = fmaxf(mx, __uint_as_float(v[k]));
-        } else {
+            if (c * 32 + k < k_hi) mx4[c] = fmaxf(mx4[c], __uint_as_float(v[c][k]));
+      } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int k = 0; k < 32; ++k) mx4[c] = fmaxf(mx4[c], __uint_as_float(v[c][k]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      if (j == 0) {
+        m_run = mx;                            // O is overwritten (not accumulated) by the first P V
+      } else {
+        // P V of tile j-1 must have completed before P is overwritten below (and before O may be rescaled)
+        mbar_wait(o_full, ph ^ 1);
+        // raise the reference maximum only if some row of this warp would exceed 2^8 with the stale one
+        if (__any_sync(0xffffffffu, (mx - m_run) * sl2 > 8.0f)) {
+          tc_fence_after();
+          const float m_new = fmaxf(m_run, mx);
+          const float corr = exp2f((m_run - m_new) * sl2);
+          l_run *= corr;
+          m_run = m_new;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {        // columns 0..47 hold the D = 40 live output channels
+            uint32_t o[16];
+            tmem_ld_32x16(tO + lane_addr + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+            tmem_st_32x16(tO + lane_addr + c * 16, o);
+          }
+          tmem_st_wait();
+          tc_fence_before();
         }
       }
-      // ---- pass 2: p = exp2((s - max) * scale), row sum, bf16 P into the swizzled K-major A tile ----
-      const float msc = mx * sl2;
+      // ---- p = exp2((s - m_run) * scale), row sum, bf16 P into the swizzled K-major A tile ----
+      const float msc = m_run * sl2;
       float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_addr + c * 32, v);
-        tmem_ld_wait();
-        float e[32];
+      if (need_mask) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[k]) : "f"(fmaf(__uint_as_float(v[k]), sl2, -msc)));
-          if (need_mask && c * 32 + k >= k_hi) e[k] = 0.f;
-          sum += e[k];
-        }
-        uint8_t* prow = sP + (c >> 1) * (AT_BM * 128) + r * 128;
+        for (int c = 0; c < 4; ++c) {
+          uint8_t* prow = sP + (c >> 1) * (AT_BM * 128) + r * 128;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o;
-          o.x = pack_bf16(e[8 * g], e[8 * g + 1]);
-          o.y = pack_bf16(e[8 * g + 2], e[8 * g + 3]);
-          o.z = pack_bf16(e[8 * g + 4], e[8 * g + 5]);
-          o.w = pack_bf16(e[8 * g + 6], e[8 * g + 7]);
-          sts128u(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4), o);
+          for (int g = 0; g < 4; ++g) {
+            float e[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[k]) : "f"(fmaf(__uint_as_float(v[c][8 * g + k]), sl2, -msc)));
+              if (c * 32 + 8 * g + k >= k_hi) e[k] = 0.f;
+            }
+            sum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+            uint4 o;
+            o.x = pack_bf16(e[0], e[1]);
+            o.y = pack_bf16(e[2], e[3]);
+            o.z = pack_bf16(e[4], e[5]);
+            o.w = pack_bf16(e[6], e[7]);
+            sts128u(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4), o);
+          }
         }
+      } else {
+        // unmasked tiles (all but the diagonal / tail tile): packed fp32x2 scale and sum, one issue slot per two scores
+        const f2_t sl22 = f2_pack(sl2, sl2), nmsc2 = f2_pack(-msc, -msc);
+        f2_t sum2[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint8_t* prow = sP + (c >> 1) * (AT_BM * 128) + r * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float x0, x1, e0, e1;
+              f2_unpack(f2_fma(f2_pack_u(v[c][8 * g + 2 * k], v[c][8 * g + 2 * k + 1]), sl22, nmsc2), x0, x1);
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+              sum2[k & 1] = f2_add(sum2[k & 1], f2_pack(e0, e1));
+              o[k] = pack_bf16(e0, e1);
+            }
+            sts128u(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+          }
+        }
+        float s0, s1;
+        f2_unpack(f2_add(sum2[0], sum2[1]), s0, s1);
+        sum = s0 + s1;
       }
+      l_run += sum;
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(s_free);
-        mbar_arrive(p_full);
-      }
-      const float corr = exp2f((m_run - mx) * sl2);      // first tile: exp2(-inf) = 0
-      l_run = l_run * corr + sum;
-      m_run = mx;
-      // ---- O_acc = O_acc * corr + O_j ----
-      mbar_wait(o_full, ph);
-      tc_fence_after();
-      {
-        uint32_t v0[32], v1[16];
-        tmem_ld_32x32(tO + lane_addr, v0);
-        tmem_ld_32x16(tO + lane_addr + 32, v1);
-        tmem_ld_wait();
-        tc_fence_before();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+
+    // ---- O (accumulated in TMEM) after the last P V ----
+    mbar_wait(o_full, (n_kv - 1) & 1);
+    tc_fence_after();
+    float o_acc[48];
+    {
+      uint32_t v0[32], v1[16];
+      tmem_ld_32x32(tO + lane_addr, v0);
+      tmem_ld_32x16(tO + lane_addr + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], corr, __uint_as_float(v0[i]));
+      for (int i = 0; i < 32; ++i) o_acc[i] = __uint_as_float(v0[i]);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o_acc[32 + i] = fmaf(o_acc[32 + i], corr, __uint_as_float(v1[i]));
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);
+      for (int i = 0; i < 16; ++i) o_acc[32 + i] = __uint_as_float(v1[i]);
     }
 
     // ---- finalize: O / l -> bf16, token-major row ----
@@ -378,6 +434,8 @@ extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ld
         n_problems = n_outer * heads;
         nq_tiles = Lq / AT_BM;
       }
+    } else if (mode == SEER_ATTN_FRAME) {
+      tc = false;
     } else {
       return SEER_EINVAL;
     }

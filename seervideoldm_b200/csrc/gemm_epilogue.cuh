@@ -87,34 +87,6 @@ struct GemmCfg {
 __device__ __forceinline__ int sw128(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
 __device__ __forceinline__ int sw64(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
 
-// ---- packed fp32x2 (sm_100 FFMA2 / FADD2 / FMUL2): one issue slot per two elements ----
-typedef unsigned long long f2_t;
-__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
-  f2_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ f2_t f2_pack_u(uint32_t lo, uint32_t hi) {
-  f2_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(f2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
-  f2_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
-  f2_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
-  f2_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 __device__ __forceinline__ uint32_t f2_to_bf16x2(f2_t v) {
   float lo, hi;
   f2_unpack(v, lo, hi);

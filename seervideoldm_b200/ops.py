@@ -16,7 +16,7 @@ from . import _lib
 
 GEMM_OUT_BF16 = 1
 GEMM_GEGLU = 2
-ATTN_SPATIAL, ATTN_CROSS, ATTN_SCTA = 0, 1, 2
+ATTN_SPATIAL, ATTN_CROSS, ATTN_SCTA, ATTN_FRAME = 0, 1, 2, 3
 
 LAUNCHES = 0           # kernels launched through this module (graph replays are counted by the caller)
 PROFILE = None         # bench.py sets this to a list: (name, algorithmic flops, start event, end event) per GEMM/conv launch
@@ -281,14 +281,21 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, mode: int, heads: int, n_outer: int, Lq: int = 0,
               Lk: int = 0, F: int = 0, H: int = 0, W: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q/k/v: 2-D bf16 token-major views [rows, heads*d] (column slices of wider buffers are fine)."""
+    """q/k/v: 2-D token-major views [rows, heads*d] (column slices of wider buffers are fine), all bf16 (product path:
+    tcgen05 / mma.sync kernels) or all fp32 (fp32-parity path: SIMT kernel, accurate exp2f)."""
+    dt = q.dtype
+    if dt not in (torch.bfloat16, torch.float32):
+        raise TypeError(f"attention: expected bf16 or fp32 q/k/v, got {dt}")
     for n, t in (("q", q), ("k", k), ("v", v)):
-        _req(t, torch.bfloat16, n, 2)
+        _req(t, dt, n, 2)
     C = q.shape[1]
     d = C // heads
     if out is None:
-        out = torch.empty((q.shape[0], C), device=q.device, dtype=torch.bfloat16)
-    if mode == ATTN_SCTA:
+        out = torch.empty((q.shape[0], C), device=q.device, dtype=dt)
+    _req(out, dt, "out", 2)
+    if mode == ATTN_FRAME:
+        name, flops = f"attention frame d={d} L={F} x{n_outer * H * heads}", 4.0 * F * (F + 1) / 2 * d * n_outer * H * heads
+    elif mode == ATTN_SCTA:
         ws = 0 if H <= 4 else (8 if H // 8 >= 4 else 4)
         L = F * (ws * ws if ws else H * W)
         nprob = n_outer * heads * ((H // ws) * (W // ws) if ws else 1)
@@ -296,9 +303,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, mode: int, h
     else:
         name = f"attention {'spatial' if mode == ATTN_SPATIAL else 'cross'} d={d} Lq={Lq} Lk={Lk} x{n_outer * heads}"
         flops = 4.0 * Lq * Lk * d * n_outer * heads
+    fn = _lib.lib().seer_b200_attention if dt == torch.bfloat16 else _lib.lib().seer_b200_attention_f32
     with _Timed(name, flops):
-        rc = _lib.lib().seer_b200_attention(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
-                                            mode, heads, d, n_outer, Lq, Lk, F, H, W, _stream())
+        rc = fn(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+                mode, heads, d, n_outer, Lq, Lk, F, H, W, _stream())
     _lib.check(rc, f"attention(mode={mode},heads={heads},d={d},outer={n_outer},Lq={Lq},Lk={Lk},F={F},H={H},W={W})")
     _count()
     return out
@@ -432,3 +440,63 @@ def cfg_ddim_update(eps: torch.Tensor, x: torch.Tensor, cond_f: int, use_cfg: bo
     _lib.check(rc, "cfg_ddim_update")
     _count()
     return x_prev, pred_x0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fp32-parity path (csrc/fp32_path.cu): error-compensated bf16 operands for the tcgen05 GEMM, fp32 everywhere else
+# ---------------------------------------------------------------------------------------------------------------------
+@_timed_op
+def split3(x: torch.Tensor, out: Optional[torch.Tensor] = None, col0: int = 0, ctot: Optional[int] = None,
+           upsample: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
+    """x fp32 [M, C] -> bf16 [M', 3*ctot] = [hi | hi | lo] (this part at columns col0.. of each third).
+    `upsample` = (n_img, H, W): nearest 2x upsampling of the [n_img, H, W] pixel rows while splitting (M' = 4 M)."""
+    _req(x, torch.float32, "x", 2)
+    M, C = x.shape
+    ctot = C if ctot is None else ctot
+    rows_out = 4 * M if upsample else M
+    if out is None:
+        out = torch.empty((rows_out, 3 * ctot), device=x.device, dtype=torch.bfloat16)
+    _req(out, torch.bfloat16, "out", 2)
+    if out.shape[0] != rows_out or out.shape[1] != 3 * ctot:
+        raise ValueError(f"split3: out shape {tuple(out.shape)} != ({rows_out}, {3 * ctot})")
+    n_img, H, W = upsample if upsample else (0, 0, 0)
+    rc = _lib.lib().seer_b200_split3_bf16(_p(x), x.stride(0), M, C, _p(out), out.stride(0), ctot, col0, n_img, H, W, _stream())
+    _lib.check(rc, f"split3(M={M},C={C})")
+    _count()
+    return out
+
+
+@_timed_op
+def layernorm_f32(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    _req(x, torch.float32, "x", 2)
+    M, C = x.shape
+    out = torch.empty((M, C), device=x.device, dtype=torch.float32)
+    rc = _lib.lib().seer_b200_layernorm_f32(_p(x), M, C, x.stride(0), _p(gamma), _p(beta), float(eps), _p(out), out.stride(0), _stream())
+    _lib.check(rc, f"layernorm_f32(M={M},C={C})")
+    _count()
+    return out
+
+
+@_timed_op
+def geglu_f32(h: torch.Tensor) -> torch.Tensor:
+    """h fp32 [M, 2I] -> [M, I] = h[:, :I] * gelu_erf(h[:, I:])."""
+    _req(h, torch.float32, "h", 2)
+    M, two_i = h.shape
+    out = torch.empty((M, two_i // 2), device=h.device, dtype=torch.float32)
+    rc = _lib.lib().seer_b200_geglu_f32(_p(h), h.stride(0), _p(out), out.stride(0), M, two_i // 2, _stream())
+    _lib.check(rc, "geglu_f32")
+    _count()
+    return out
+
+
+@_timed_op
+def rope_ex(qk: torch.Tensor, pos_div: int, pos_mod: int, heads: int, head_dim: int, q_col: int, k_col: int,
+            freqs: torch.Tensor) -> None:
+    """RoPE in place on a bf16 or fp32 [M, ld] buffer; position = (row // pos_div) % pos_mod."""
+    if qk.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("rope_ex: bf16 or fp32 buffer expected")
+    _req(qk, qk.dtype, "qk", 2); _req(freqs, torch.float32, "freqs", 1)
+    rc = _lib.lib().seer_b200_rope_ex(_p(qk), int(qk.dtype == torch.float32), qk.stride(0), qk.shape[0], pos_div, pos_mod, heads,
+                                      head_dim, q_col, k_col, _p(freqs), freqs.numel(), _stream())
+    _lib.check(rc, "rope_ex")
+    _count()

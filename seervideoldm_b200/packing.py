@@ -82,3 +82,14 @@ def fold_layernorm(w: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tens
         wf, bias = wf[perm], bias[perm]
     w16 = wf.to(torch.bfloat16).contiguous()
     return w16, w16.float().sum(1).contiguous(), bias.contiguous()
+
+
+# ---- fp32-parity path: error-compensated bf16 operand pairs (csrc/fp32_path.cu) ----
+def split3_weight(w: torch.Tensor) -> torch.Tensor:
+    """[N, K, ...] fp32 -> [N, 3K, ...] fp32 holding [w_hi | w_lo | w_hi] along dim 1 (both halves exactly representable in
+    bf16), the partner of the activation split [a_hi | a_hi | a_lo]: the 3K-long dot product is
+    a_hi.w_hi + a_hi.w_lo + a_lo.w_hi.  Feed the result to the ordinary pack_* functions."""
+    w = w.float()
+    hi = w.to(torch.bfloat16).float()
+    lo = (w - hi).to(torch.bfloat16).float()
+    return torch.cat([hi, lo, hi], dim=1)

@@ -295,6 +295,39 @@ def test_attention_spatial(d, frames, L):
     assert rel(out.float(), ref) < 6e-3
 
 
+@pytest.mark.parametrize("mode", ["spatial", "scta"])
+def test_attention_tc_lazy_rescale(mode):
+    """Scores whose row maximum keeps growing along the key axis (key norms ramp up 6x) and spans tens of log2 units:
+    exercises the tcgen05 kernel's lazy-maximum path (O rescaled in TMEM only when a row would exceed 2^8)."""
+    heads, d = 8, 40
+    C = heads * d
+    if mode == "spatial":
+        frames, L = 2, 1024
+        n = frames * L
+        ramp = (1.0 + 5.0 * (torch.arange(n, device=DEV) % L).float() / L)[:, None]
+    else:
+        B, Fr, H = 1, 8, 32
+        n = B * Fr * H * H
+        ramp = (1.0 + 5.0 * torch.arange(n, device=DEV).float() / n)[:, None]
+    qkv = rn(64, n, 3 * C)
+    qkv[:, :C] *= 3.0
+    qkv[:, C:2 * C] *= ramp
+    qkv = qkv.bfloat16()
+    if mode == "spatial":
+        out = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], mode=ops.ATTN_SPATIAL, heads=heads, n_outer=frames, Lq=L, Lk=L)
+        t = qkv.float().reshape(frames, L, 3, heads, d).permute(2, 0, 3, 1, 4)
+        ref = _attn_ref(t[0], t[1], t[2], False).permute(0, 2, 1, 3).reshape(n, C)
+    else:
+        out = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], mode=ops.ATTN_SCTA, heads=heads, n_outer=B, F=Fr, H=H, W=H)
+        t = qkv.float().reshape(B, n // B, 3, heads, d).permute(2, 0, 3, 1, 4)
+        ref = torch.empty(B, heads, n // B, d, device=DEV)
+        for seq in torch.from_numpy(so.scta_sequences(Fr, H, H)).to(DEV):
+            ref[:, :, seq] = _attn_ref(t[0][:, :, seq], t[1][:, :, seq], t[2][:, :, seq], True)
+        ref = ref.permute(0, 2, 1, 3).reshape(n, C)
+    assert torch.isfinite(out.float()).all()
+    assert rel(out.float(), ref) < 8e-3
+
+
 @pytest.mark.parametrize("d,frames,L", [(40, 3, 1024), (80, 2, 256), (160, 4, 16)])
 def test_attention_cross_77(d, frames, L):
     heads, Lk = 8, 77
