@@ -393,6 +393,45 @@ def ddim_sample_latents(unet_fn, x_T: Tensor, c: Tensor, x0_emb: Optional[Tensor
     return img, inter
 
 
+def fstext_forward(sd: Dict[str, Tensor], context: Tensor, num_frames: int, heads: int = 8) -> Tensor:
+    """FSTextTransformer.forward, seer/models/unet_3d_condition.py:470-484, with LinearTransformer3D /
+    BasicLinearTransformerBlock3D (attention.py:172-176, 385-427).  context:(b,L,768) CLIP text embedding ->
+    (b,F,L,768) per-frame sub-instruction embedding.  `sd` = the module's state dict.
+
+    Per layer: block 0 (temporal=False) = UNMASKED self-attention over the L tokens of each frame (the causal mask at
+    attention.py:521-524 is only built when temporal=True), cross-attention of all F*L queries to the L context tokens
+    (3-D context branch, :405-406), GEGLU FF; block 1 (temporal=True) = causal RoPE attention along the frame axis per
+    (clip, token) (:393,396,521-530; rot dim min(32, 96), position = frame index), GEGLU FF.  Final LayerNorm (:482)."""
+    b, l, c = context.shape
+    pos = sd["pos_embed"][:, :, :l, :]
+    if sd["pos_embed"].shape[1] != num_frames:      # nearest-neighbour resize along the frame axis (:477-478)
+        pos = F.interpolate(pos.permute(0, 3, 1, 2), size=(num_frames, l)).permute(0, 2, 3, 1)
+    x = sd["learnable_query"].expand(b, num_frames, l, -1) + pos
+    f = num_frames
+    n_layers = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("trf_blocks."))
+    for n in range(n_layers):
+        p0 = f"trf_blocks.{n}.transformer_blocks.0."
+        t = x.reshape(b * f, l, c)
+        t = t + cross_attention(sd, p0 + "attn1.", _ln(sd, p0 + "norm1.", t), None, heads)
+        t = t.reshape(b, f * l, c)
+        t = t + cross_attention(sd, p0 + "attn2.", _ln(sd, p0 + "norm2.", t), context, heads)
+        t = t + feed_forward(sd, p0 + "ff.", _ln(sd, p0 + "norm3.", t))
+        x = t.reshape(b, f, l, c)
+        p1 = f"trf_blocks.{n}.transformer_blocks.1."
+        t = x.permute(0, 2, 1, 3).reshape(b * l, f, c)
+        h = _ln(sd, p1 + "norm1.", t)
+        q = _heads(F.linear(h, sd[p1 + "attn1.to_q.weight"]), heads)
+        k = _heads(F.linear(h, sd[p1 + "attn1.to_k.weight"]), heads)
+        v = _heads(F.linear(h, sd[p1 + "attn1.to_v.weight"]), heads)
+        rot = min(32, c // heads)
+        q, k = rope_interleaved(q, torch.arange(f), rot), rope_interleaved(k, torch.arange(f), rot)
+        o = _unheads(softmax_attention(q, k, v, causal=True))
+        t = t + F.linear(o, sd[p1 + "attn1.to_out.0.weight"], sd[p1 + "attn1.to_out.0.bias"])
+        t = t + feed_forward(sd, p1 + "ff.", _ln(sd, p1 + "norm3.", t))
+        x = t.reshape(b, l, f, c).permute(0, 2, 1, 3)
+    return F.layer_norm(x, (c,), sd["norm.weight"], sd["norm.bias"], 1e-5)
+
+
 def rel_l2(a: Tensor, b: Tensor) -> float:
     a, b = a.double().flatten(), b.double().flatten()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))

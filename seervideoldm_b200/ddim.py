@@ -169,7 +169,7 @@ class DDIMSampler(object):
         """One UNet evaluation; replayed from a CUDA graph when the model is a seer_b200 SeerUNet."""
         if not (self.use_cuda_graph and isinstance(unet, SeerUNet) and x_in.is_cuda):
             return unet(x_in, t_in, c_in, cond_frame=cond_frame)
-        key = (id(unet), tuple(x_in.shape), tuple(c_in.shape), cond_frame)
+        key = (id(unet), tuple(x_in.shape), tuple(c_in.shape), cond_frame, unet.precision)
         g = self._graphs.get(key)
         if g is not None and not g.matches(unet, x_in, c_in, cond_frame):      # id() reuse after garbage collection
             g = None

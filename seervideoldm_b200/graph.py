@@ -19,6 +19,7 @@ class GraphedUNet:
         self.t = t_in.detach().clone()
         self.c = c_in.detach().clone().contiguous()
         self.cond_frame = cond_frame
+        self.precision = unet.precision
         self._src = (c_in, c_in._version)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -36,7 +37,7 @@ class GraphedUNet:
 
     def matches(self, unet, x_in, c_in, cond_frame) -> bool:
         return (self.unet is unet and tuple(self.x.shape) == tuple(x_in.shape) and tuple(self.c.shape) == tuple(c_in.shape)
-                and self.cond_frame == cond_frame)
+                and self.cond_frame == cond_frame and self.precision == unet.precision)
 
     def __call__(self, x_in: torch.Tensor, t_in: torch.Tensor, c_in: torch.Tensor) -> torch.Tensor:
         if self._src[0] is not c_in or self._src[1] != c_in._version:

@@ -70,8 +70,10 @@ class SeerUNet(nn.Module):
         self.config = _Config(**asdict(self.cfg))
         self.sample_size = sample_size
         self._packed: Optional[dict] = None
+        self._packed32: Optional[dict] = None
         self._kv_key = None
         self._kv: List[torch.Tensor] = []
+        self.precision = "bf16"
         self._build_tree()
         self.reset_parameters()
 
@@ -104,17 +106,17 @@ class SeerUNet(nn.Module):
                 ref = p if name.endswith("weight") else params[name[: -len("bias")] + "weight"]
                 bound = 1.0 / math.sqrt(max(1, ref[0].numel()))
                 p.uniform_(-bound, bound)
-        self._packed = None
+        self._packed = self._packed32 = None
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
-        self._packed = None
+        self._packed = self._packed32 = None
         self._kv_key = None
         return out
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
-        self._packed = None
+        self._packed = self._packed32 = None
         self._kv_key = None
         return out
 
@@ -125,6 +127,18 @@ class SeerUNet(nn.Module):
     @property
     def device(self) -> torch.device:
         return self.conv_in.weight.device
+
+    def set_precision(self, precision: str) -> "SeerUNet":
+        """"bf16" (default, the product path: bf16 tensor-core operands, fp32 accumulation / residual stream; what the
+        reference computes under accelerate's mixed precision) or "fp32" (parity mode, unet_fp32.py: error-compensated
+        bf16 operand pairs on the same tcgen05 kernels, everything else fp32; matches the reference's fp32 forward to
+        rel-L2 <= 1e-4)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        if precision != self.precision:
+            self.precision = precision
+            self._kv_key = None
+        return self
 
     # API parity no-ops (xformers / slicing are memory-saving switches of the reference's PyTorch path)
     def enable_xformers_memory_efficient_attention(self):
@@ -327,6 +341,11 @@ class SeerUNet(nn.Module):
     def compute_context_kv(self, context: torch.Tensor, out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
         """K/V projections of the text context for every cross-attention layer: [B*F*L, 2C] bf16 each
         (attention.py:517-518 with the per-frame context of :314-315).  `out` recomputes into existing buffers."""
+        if self.precision == "fp32":
+            from . import unet_fp32
+            if self._packed32 is None:
+                self._packed32 = unet_fp32.pack_fp32(self)
+            return unet_fp32.context_kv(self, self._packed32, context, out)
         pk = self._packed or self._pack()
         ctx = ops.cast_bf16(context.reshape(-1, context.shape[-1]).float().contiguous())
         layers = self._cross_layers(pk)
@@ -341,10 +360,11 @@ class SeerUNet(nn.Module):
         for all 31 DDIM evaluations (SURVEY §7.1 'exploitable redundancy' (i)).  The cache is keyed on tensor identity
         + version and holds a reference: a data_ptr()-only key would go stale when the caching allocator hands a
         freed context's address to a new tensor."""
-        if self._kv_key is not None and self._kv_key[0] is context and self._kv_key[1] == context._version:
+        if (self._kv_key is not None and self._kv_key[0] is context and self._kv_key[1] == context._version
+                and self._kv_key[2] == self.precision):
             return self._kv
         self._kv = self.compute_context_kv(context)
-        self._kv_key = (context, context._version)
+        self._kv_key = (context, context._version, self.precision)
         return self._kv
 
     # ------------------------------------------------------------------ forward
@@ -359,7 +379,15 @@ class SeerUNet(nn.Module):
             raise NotImplementedError("return_attn=True (pre-softmax score dump) is not on the sampling path")
         if sample.dim() != 5 or context.dim() != 4:
             raise ValueError("expected sample (B,C,F,H,W) and context (B,F,L,D)")
-        pk = self._packed or self._pack()
+        if self.precision == "fp32":
+            if self.device.type != "cuda" or self.dtype != torch.float32:
+                raise RuntimeError("SeerUNet (seer_b200) needs fp32 parameters on a CUDA device")
+            from . import unet_fp32
+            if self._packed32 is None:
+                self._packed32 = unet_fp32.pack_fp32(self)
+            pk = self._packed32
+        else:
+            pk = self._packed or self._pack()
         cfg = self.cfg
         dev = self.device
         B, Cin, F, H, W = sample.shape
@@ -377,6 +405,8 @@ class SeerUNet(nn.Module):
         elif t.dim() == 0:
             t = t[None].to(dev)
         t = t.to(dev).broadcast_to((B,)).to(torch.float32).contiguous()
+        if self.precision == "fp32":
+            return unet_fp32.forward(self, pk, sample, t, context, cond_frame, self._context_kv(pk, context.to(dev)))
         temb = ops.timestep_embedding(t, cfg.block_out_channels[0], float(cfg.freq_shift), cfg.flip_sin_to_cos)
         e1 = ops.small_linear(temb, pk["te1_w"], pk["te1_b"], silu_out=True)
         emb = ops.small_linear(e1, pk["te2_w"], pk["te2_b"])

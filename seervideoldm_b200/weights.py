@@ -165,3 +165,57 @@ def unet_schema_cache(cfg: UNetConfig):
     if cfg not in _SCHEMA_CACHE:
         _SCHEMA_CACHE[cfg] = unet_schema(cfg)
     return _SCHEMA_CACHE[cfg]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# FSTextTransformer (seer/models/unet_3d_condition.py:379-398; LinearTransformer3D attention.py:152-170, 328-362)
+# ---------------------------------------------------------------------------------------------------------------------
+MAX_TEXT_LENGTH = 77      # unet_3d_condition.py MAX_LENGTH
+
+
+def fstext_schema(num_frames: int = 16, num_layers: int = 2, channels: int = 768, heads: int = 8,
+                  cross_attention_dim: int = 768) -> "OrderedDict[str, Shape]":
+    """State-dict keys/shapes of the reference FSTextTransformer, in its registration order."""
+    s: "OrderedDict[str, Shape]" = OrderedDict()
+    c = channels
+    s["learnable_query"] = (1, 1, 1, c)
+    s["pos_embed"] = (1, num_frames, MAX_TEXT_LENGTH, c)
+    for n in range(num_layers):
+        b0 = f"trf_blocks.{n}.transformer_blocks.0."
+        _attn(s, b0 + "attn1.", c, c)
+        _ff(s, b0 + "ff.", c)
+        _attn(s, b0 + "attn2.", c, cross_attention_dim)
+        _ln(s, b0 + "norm2.", c)
+        _ln(s, b0 + "norm1.", c)
+        _ln(s, b0 + "norm3.", c)
+        b1 = f"trf_blocks.{n}.transformer_blocks.1."
+        _attn(s, b1 + "attn1.", c, c, rotary=min(32, c // heads))
+        _ff(s, b1 + "ff.", c)
+        _ln(s, b1 + "norm1.", c)
+        _ln(s, b1 + "norm3.", c)
+    _ln(s, "norm.", c)
+    return s
+
+
+def random_fstext_state_dict(num_frames: int = 16, num_layers: int = 2, seed: int = 0, **kw) -> Dict[str, torch.Tensor]:
+    """Deterministic synthetic FSText weights (fp32, CPU): linear layers at PyTorch's default scale, norms 1+N(0,0.1) /
+    N(0,0.1), learnable_query and pos_embed N(0, 1) / N(0, 0.5) (the reference zero-initialises them; zeros would make
+    every token identical and the attention paths degenerate)."""
+    schema = fstext_schema(num_frames, num_layers, **kw)
+    out: Dict[str, torch.Tensor] = OrderedDict()
+    for key, shape in schema.items():
+        g = _gen(seed, "fstext." + key)
+        if key.endswith("rotary_emb.freqs"):
+            dim = 2 * shape[0]
+            out[key] = 1.0 / (10000.0 ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+        elif key == "learnable_query":
+            out[key] = torch.randn(shape, generator=g)
+        elif key == "pos_embed":
+            out[key] = 0.5 * torch.randn(shape, generator=g)
+        elif key.split(".")[-2].startswith("norm"):
+            out[key] = (1.0 if key.endswith("weight") else 0.0) + 0.1 * torch.randn(shape, generator=g)
+        else:
+            wshape = shape if key.endswith("weight") else schema[key[: -len("bias")] + "weight"]
+            bound = 1.0 / math.sqrt(int(math.prod(wshape[1:])))
+            out[key] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+    return out
