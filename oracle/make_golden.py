@@ -24,10 +24,33 @@ def randn(seed, *shape):
     return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
 
 
+def fstext_golden(ref):
+    """FSTextTransformer (seer/models/unet_3d_condition.py:379-484) on seeded weights / contexts.  The full outputs are
+    (b, F, 77, 768); the fixture keeps every 7th token and every 8th channel of each (plus mean / std of the whole)."""
+    from seervideoldm_b200.weights import random_fstext_state_dict
+    sd = random_fstext_state_dict(num_frames=16, num_layers=2, seed=0)
+    m = ref.FSTextTransformer(num_frames=16, num_layers=2).eval()
+    rl.enable_xformers_path(m)
+    m.load_state_dict(sd, strict=True)
+    cases = []
+    for i, (b, nf) in enumerate([(2, 16), (1, 6), (3, 12)]):
+        ctx = randn(7000 + i, b, 77, 768)
+        m.set_numframe(nf)
+        y = m(context=ctx)
+        cases.append(dict(ctx_seed=7000 + i, b=b, num_frames=nf, y_sub=y[:, :, ::7, ::8].clone(), mean=float(y.mean()),
+                          std=float(y.std())))
+    torch.save(dict(weight_seed=0, num_frames=16, num_layers=2, token_stride=7, channel_stride=8, cases=cases),
+               os.path.join(OUT, "fstext.pt"))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rl.load()
     torch.set_grad_enabled(False)
+    if len(sys.argv) > 1 and sys.argv[1] == "fstext":       # regenerate only the FSText fixture
+        fstext_golden(ref)
+        return
+    fstext_golden(ref)
 
     # ---- schedule (ldm/models/diffusion/ddim_video.py:27-68) -------------------------------
     for S in (30, 10):

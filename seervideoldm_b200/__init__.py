@@ -2,6 +2,7 @@
 
 Public surface mirrors the reference (seervideodiffusion/SeerVideoLDM):
     SeerUNet        <- seer/models/unet_3d_condition.py: SeerUNet
+    FSTextTransformer <- seer/models/unet_3d_condition.py: FSTextTransformer
     DDIMSampler     <- ldm/models/diffusion/ddim_video.py: DDIMSampler
     ddim_sample     <- utils/ddim_sampling_utils.py: ddim_sample
 """
@@ -12,6 +13,9 @@ def __getattr__(name):  # lazy: importing the package must not require CUDA or t
     if name == "SeerUNet":
         from .unet import SeerUNet
         return SeerUNet
+    if name == "FSTextTransformer":
+        from .fstext import FSTextTransformer
+        return FSTextTransformer
     if name == "DDIMSampler":
         from .ddim import DDIMSampler
         return DDIMSampler

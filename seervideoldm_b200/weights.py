@@ -170,7 +170,7 @@ def unet_schema_cache(cfg: UNetConfig):
 # ---------------------------------------------------------------------------------------------------------------------
 # FSTextTransformer (seer/models/unet_3d_condition.py:379-398; LinearTransformer3D attention.py:152-170, 328-362)
 # ---------------------------------------------------------------------------------------------------------------------
-MAX_TEXT_LENGTH = 77      # unet_3d_condition.py MAX_LENGTH
+MAX_TEXT_LENGTH = 1024    # unet_3d_condition.py MAX_LENGTH: pos_embed is (1, F, 1024, 768), forward slices the first L = 77 tokens
 
 
 def fstext_schema(num_frames: int = 16, num_layers: int = 2, channels: int = 768, heads: int = 8,

@@ -129,3 +129,36 @@ def test_ops_fail_loudly_without_cuda():
         ops.gemm(torch.zeros(128, 64, dtype=torch.bfloat16), torch.zeros(64, 64, dtype=torch.bfloat16))
     with pytest.raises(ValueError, match="no CPU path"):
         ops.layernorm(torch.zeros(4, 320), torch.ones(320), torch.zeros(320))
+
+
+def test_fstext_module_mirrors_reference_api():
+    """FSTextTransformer: constructor / set_numframe / state-dict schema of unet_3d_condition.py:379-398; strict loading;
+    CUDA-only forward (no CPU fallback)."""
+    import pytest
+    import torch
+    from seervideoldm_b200 import FSTextTransformer
+    from seervideoldm_b200.weights import fstext_schema, random_fstext_state_dict
+    m = FSTextTransformer(num_frames=16, num_layers=2)
+    sch = fstext_schema(16, 2)
+    assert list(m.state_dict().keys()) == list(sch.keys())
+    assert all(tuple(v.shape) == sch[k] for k, v in m.state_dict().items())
+    assert float(m.learnable_query.abs().sum()) == 0.0 and float(m.pos_embed.abs().sum()) == 0.0    # reference zero-init
+    sd = random_fstext_state_dict(16, 2, seed=0)
+    m.load_state_dict(sd, strict=True)
+    bad = dict(sd)
+    bad.pop("norm.bias")
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad, strict=True)
+    m.set_numframe(12)
+    assert m.num_frames == 12
+    assert m.enable_xformers_memory_efficient_attention() is None and m.set_attention_slice("auto") is None
+    with pytest.raises(ValueError):
+        m.set_precision("fp16")
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 77, 768))          # parameters on the CPU: the kernels are CUDA-only, nothing falls back
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 77, 512))
+    # nearest-neighbour frame resize of the position table (unet_3d_condition.py:477-478)
+    q = m._query_tokens(1, 77).view(12, 77, 768)
+    idx = (torch.arange(12) * 16 // 12)
+    assert torch.equal(q, (sd["learnable_query"] + sd["pos_embed"][:, :, :77])[0, idx])

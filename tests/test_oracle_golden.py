@@ -135,3 +135,18 @@ def test_ddim_update_is_reference_order():
     p0_ref = (x - torch.sqrt(1 - a_t) * e) / torch.sqrt(a_t)
     assert torch.equal(p0, p0_ref)
     assert torch.equal(xp, torch.sqrt(a_p) * p0_ref + torch.sqrt(1 - a_p) * e)
+
+
+def test_fstext_oracle_vs_reference_golden(golden_dir):
+    """oracle.fstext_forward against outputs of the unmodified reference FSTextTransformer (oracle/make_golden.py)."""
+    from seervideoldm_b200.weights import fstext_schema, random_fstext_state_dict
+    g = torch.load(os.path.join(golden_dir, "fstext.pt"), weights_only=False)
+    sd = random_fstext_state_dict(g["num_frames"], g["num_layers"], seed=g["weight_seed"])
+    assert list(sd.keys()) == list(fstext_schema(g["num_frames"], g["num_layers"]).keys()) and len(sd) == 72
+    assert sum(v.numel() for k, v in sd.items() if not k.endswith("freqs")) == 55100160      # reference parameter count
+    for case in g["cases"]:
+        ctx = torch.randn(case["b"], 77, 768, generator=torch.Generator().manual_seed(case["ctx_seed"]))
+        y = so.fstext_forward(sd, ctx, case["num_frames"])
+        assert y.shape == (case["b"], case["num_frames"], 77, 768)
+        assert so.rel_l2(y[:, :, ::g["token_stride"], ::g["channel_stride"]], case["y_sub"]) < 5e-6
+        assert abs(float(y.mean()) - case["mean"]) < 1e-5 and abs(float(y.std()) - case["std"]) < 1e-5
