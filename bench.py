@@ -257,6 +257,7 @@ def run_ours(args):
     peaks = measured_peaks()
     roof = None
     cpu_base = None
+    attention = None
     if rank == 0:
         x_in = torch.cat([torch.cat([x0, x_T], 2)] * 2)
         t_in, c_in = torch.full((2 * b,), 496, device=dev), torch.cat([uc, c])
@@ -277,6 +278,21 @@ def run_ours(args):
                 "flops_per_launch_avg": flops / max(1, len(prof)), "peak_source": peaks["source"] + ", sustained bf16",
                 "frac_of_burst_peak": achieved / peaks["burst"],
                 "share_of_step_time": t_ms / max(t_all_ms, 1e-9)}
+        # attention cores (SCTA / spatial / cross; BASELINE.json metric: "attn % of peak"), same live CUDA-event pass
+        att = [p for p in prof_all if p[0].startswith("attention ")]
+        att_ms = sum(p[2].elapsed_time(p[3]) for p in att)
+        att_tf = sum(p[1] for p in att) / (att_ms * 1e-3) / 1e12 if att_ms > 0 else 0.0
+        by_kind = {}
+        for kind in ("scta", "spatial", "cross"):
+            sel = [p for p in att if p[0].startswith("attention " + kind)]
+            ms_k = sum(p[2].elapsed_time(p[3]) for p in sel)
+            if ms_k > 0:
+                by_kind[kind] = {"tflops": sum(p[1] for p in sel) / (ms_k * 1e-3) / 1e12, "ms_per_eval": ms_k, "launches": len(sel)}
+        attention = {"achieved": att_tf, "unit": "TFLOP/s (causal-halved algorithmic FLOPs)", "peak": peaks["sustained"],
+                     "frac_of_tensor_peak": att_tf / peaks["sustained"], "share_of_step_time": att_ms / max(t_all_ms, 1e-9),
+                     "by_kind": by_kind,
+                     "note": "d=40 level is MUFU(ex2)-bound: 160 tensor FLOP per exp2 caps it near 31 % of the tensor peak "
+                             "(profiles/r1_attention_tc_*.summary.txt)"}
         if world == 1 and not args.no_cpu_baseline:
             fn, kind = cpu_eval_fn()
             with torch.no_grad():
@@ -302,7 +318,7 @@ def run_ours(args):
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps, "api": "seervideoldm_b200.pipeline.ddim_sample_latents (pinned host buffers)"},
-                "gpu_launches": launches, "roofline": roof}
+                "gpu_launches": launches, "roofline": roof, "attention": attention}
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line))
