@@ -76,6 +76,7 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16*
 
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams p) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   using C = AttnCfg<D>;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
@@ -257,7 +258,7 @@ static int launch_attention(const AttnParams& p, int n_problems, cudaStream_t st
     attr_done = true;
   }
   dim3 grid(ceil_div(p.Lq, ATT_BM), n_problems);
-  attention_kernel<D><<<grid, ATT_THREADS, C::SMEM_BYTES, stream>>>(p);
+  { cudaError_t le__ = launch_pdl(attention_kernel<D>, grid, ATT_THREADS, C::SMEM_BYTES, stream, p); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

@@ -66,6 +66,7 @@ template <int D>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -466,7 +467,7 @@ extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ld
     attr_done = true;
   }
   dim3 grid(nq_tiles, n_problems);
-  attention_tc_kernel<40><<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  { cudaError_t le__ = launch_pdl(attention_tc_kernel<40>, grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream, tq, tk, tv, p); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace seer {
 
@@ -31,6 +32,41 @@ __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b -
 // attention.cu (mma.sync flash attention, any head dim) — called by the dispatcher in attention_tc.cu
 int attention_mma_launch(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int mode,
                          int heads, int head_dim, int n_outer, int Lq, int Lk, int F, int H, int W, void* stream);
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its stream predecessor is
+// still draining; pdl_wait() blocks until the predecessor grid has completed and its memory is visible — it must precede
+// EVERY global-memory access of the kernel (reads and writes: buffers are recycled by the caller's allocator).
+// pdl_launch_dependents() lets the successor's CTAs be scheduled as SMs free up, so its prologue (barrier init, TMEM
+// allocation, tensor-map prefetch) and the launch latency hide behind this kernel's tail.  Both are no-ops for a kernel
+// launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// host side: SEER_PDL=0 disables the launch attribute (A/B switch)
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEER_PDL");
+    v = (e && *e) ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
+// <<<grid, block, smem, stream>>> with the PDL attribute (the kernel must start with pdl_wait())
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- generic -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -10,6 +10,7 @@ namespace seer {
 // cast fp32 -> bf16 (context embeddings, once per clip)
 // ---------------------------------------------------------------------------------------------------
 __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n8) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     const float4 a = *reinterpret_cast<const float4*>(x + i * 8);
     const float4 b = *reinterpret_cast<const float4*>(x + i * 8 + 4);
@@ -28,6 +29,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
 // ---------------------------------------------------------------------------------------------------
 __global__ void rope_kernel(__nv_bfloat16* __restrict__ qk, int ld, int M, int tokens_per_clip, int heads, int head_dim,
                             int q_col, int k_col, const float* __restrict__ freqs, int half) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const size_t total = (size_t)M * half;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int row = (int)(i / half);
@@ -54,6 +56,7 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qk, int ld, int M, int t
 // ---------------------------------------------------------------------------------------------------
 __global__ void timestep_embed_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim, float shift,
                                       int flip) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -76,6 +79,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
                                                            const float* __restrict__ bias, const float* __restrict__ add,
                                                            float* __restrict__ out, int ldo, int B, int N, int K,
                                                            int silu_in, int silu_out) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int b0 = blockIdx.y * SL_ROWS;
@@ -113,6 +117,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 constexpr int CI_PIX = 16;
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                float* __restrict__ out, int B, int Cin, int F, int H, int W, int Cout) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   extern __shared__ float s_in[];  // [CI_PIX][Cin*9]
   constexpr int K = 36;  // Cin == 4 (checked on the host)
   const int HW = H * W;
@@ -155,6 +160,7 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
 __global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__ x, const float* __restrict__ wp,
                                                        const float* __restrict__ bias, float* __restrict__ out, int B, int Cin,
                                                        int F, int H, int W, int Cout) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const int HW = H * W;
   const size_t npix = (size_t)B * F * HW;
   const size_t pix = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -190,6 +196,7 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__
 // nearest 2x upsample, fp32 [n_img, H, W, C] -> bf16 [n_img, 2H, 2W, C]   (resnet.py:52, conv input operand)
 // ---------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n_img, int H, int W, int C) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const int c8n = C / 8;
   const size_t total = (size_t)n_img * 4 * H * W * c8n;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -214,6 +221,7 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __
 template <bool IN_BF16>
 __global__ void im2col3x3_kernel(const void* __restrict__ xin, __nv_bfloat16* __restrict__ y, int n_img, int H, int W, int C,
                                  int stride) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const int nchunk = C / 64;
   const int Ho = H / stride, Wo = W / stride;
   const size_t total = (size_t)n_img * Ho * Wo * nchunk * 72;     // 72 = 9 taps x 8 groups of 8 channels
@@ -255,6 +263,7 @@ __global__ void im2col3x3_kernel(const void* __restrict__ xin, __nv_bfloat16* __
 __global__ void cfg_ddim_kernel(const float* __restrict__ eps, const float* __restrict__ x, float* __restrict__ x_prev,
                                 float* __restrict__ pred_x0, int b, int C, int F2, int cond_f, int HW, int use_cfg, float scale,
                                 float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const size_t total = (size_t)b * C * F2 * HW;
   const int F = F2 + cond_f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -292,7 +301,7 @@ using namespace seer;
 
 extern "C" int seer_b200_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream) {
   SEER_CHECK_ARG(x && y && n > 0 && n % 8 == 0);
-  cast_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, (size_t)n / 8);
+  { cudaError_t le__ = launch_pdl(cast_bf16_kernel, grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, (size_t)n / 8); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
@@ -301,8 +310,8 @@ extern "C" int seer_b200_rope_inplace(void* qk_bf16, int ld, int M, int tokens_p
                                       int k_col, const float* freqs, int n_freqs, void* stream) {
   SEER_CHECK_ARG(qk_bf16 && freqs && M > 0 && tokens_per_clip > 0 && M % tokens_per_clip == 0);
   SEER_CHECK_ARG(2 * n_freqs <= head_dim && ld % 2 == 0 && q_col % 2 == 0 && k_col % 2 == 0 && head_dim % 2 == 0);
-  rope_kernel<<<grid_for((size_t)M * n_freqs, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)qk_bf16, ld, M, tokens_per_clip,
-                                                                                   heads, head_dim, q_col, k_col, freqs, n_freqs);
+  { cudaError_t le__ = launch_pdl(rope_kernel, grid_for((size_t)M * n_freqs, 256), 256, 0, (cudaStream_t)stream, (__nv_bfloat16*)qk_bf16, ld, M, tokens_per_clip,
+                                                                                   heads, head_dim, q_col, k_col, freqs, n_freqs); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
@@ -310,7 +319,7 @@ extern "C" int seer_b200_rope_inplace(void* qk_bf16, int ld, int M, int tokens_p
 extern "C" int seer_b200_timestep_embedding(const float* t, float* out, int B, int dim, float shift, int flip_sin_to_cos,
                                             void* stream) {
   SEER_CHECK_ARG(t && out && B > 0 && dim > 0 && dim % 2 == 0);
-  timestep_embed_kernel<<<ceil_div(B * dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(t, out, B, dim, shift, flip_sin_to_cos);
+  { cudaError_t le__ = launch_pdl(timestep_embed_kernel, ceil_div(B * dim / 2, 128), 128, 0, (cudaStream_t)stream, t, out, B, dim, shift, flip_sin_to_cos); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
@@ -319,7 +328,7 @@ extern "C" int seer_b200_small_linear(const float* in, int ldi, const float* W, 
                                       int ldo, int B, int N, int K, int silu_in, int silu_out, void* stream) {
   SEER_CHECK_ARG(in && W && out && B > 0 && N > 0 && K > 0 && K % 4 == 0 && ldi % 4 == 0);
   dim3 grid(ceil_div(N, 8), ceil_div(B, SL_ROWS));
-  small_linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ldi, W, bias, add, out, ldo, B, N, K, silu_in, silu_out);
+  { cudaError_t le__ = launch_pdl(small_linear_kernel, grid, 256, 0, (cudaStream_t)stream, in, ldi, W, bias, add, out, ldo, B, N, K, silu_in, silu_out); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
@@ -329,8 +338,8 @@ extern "C" int seer_b200_conv_in(const float* x, const float* w, const float* bi
   SEER_CHECK_ARG(x && w && bias && out && Cin == 4);
   const size_t npix = (size_t)B * F * H * W;
   const int threads = Cout >= 320 ? 320 : ((Cout + 31) / 32) * 32;
-  conv_in_kernel<<<(unsigned)((npix + CI_PIX - 1) / CI_PIX), threads, CI_PIX * Cin * 9 * sizeof(float), (cudaStream_t)stream>>>(
-      x, w, bias, out, B, Cin, F, H, W, Cout);
+  { cudaError_t le__ = launch_pdl(conv_in_kernel, (unsigned)((npix + CI_PIX - 1) / CI_PIX), threads, CI_PIX * Cin * 9 * sizeof(float), (cudaStream_t)stream, 
+      x, w, bias, out, B, Cin, F, H, W, Cout); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
@@ -339,7 +348,7 @@ extern "C" int seer_b200_conv_out(const float* x, const float* w_packed, const f
                                   int H, int W, int Cout, void* stream) {
   SEER_CHECK_ARG(x && w_packed && bias && out && Cout <= 4 && Cin % 4 == 0);
   const size_t npix = (size_t)B * F * H * W;
-  conv_out_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, w_packed, bias, out, B, Cin, F, H, W, Cout);
+  { cudaError_t le__ = launch_pdl(conv_out_kernel, (unsigned)((npix + 7) / 8), 256, 0, (cudaStream_t)stream, x, w_packed, bias, out, B, Cin, F, H, W, Cout); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
@@ -347,7 +356,7 @@ extern "C" int seer_b200_conv_out(const float* x, const float* w_packed, const f
 extern "C" int seer_b200_upsample2x_to_bf16(const float* x, void* y, int n_img, int H, int W, int C, void* stream) {
   SEER_CHECK_ARG(x && y && C % 8 == 0);
   const size_t total = (size_t)n_img * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n_img, H, W, C);
+  { cudaError_t le__ = launch_pdl(upsample2x_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, n_img, H, W, C); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
@@ -357,9 +366,9 @@ extern "C" int seer_b200_im2col3x3_to_bf16(const void* x, int in_is_bf16, void* 
   SEER_CHECK_ARG(x && y && C % 64 == 0 && (stride == 1 || stride == 2) && H % stride == 0 && W % stride == 0);
   const size_t total = (size_t)n_img * (H / stride) * (W / stride) * 9 * (C / 8);
   if (in_is_bf16)
-    im2col3x3_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n_img, H, W, C, stride);
+    { cudaError_t le__ = launch_pdl(im2col3x3_kernel<true>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, n_img, H, W, C, stride); if (le__ != cudaSuccess) return (int)le__; }
   else
-    im2col3x3_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n_img, H, W, C, stride);
+    { cudaError_t le__ = launch_pdl(im2col3x3_kernel<false>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, n_img, H, W, C, stride); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
@@ -369,8 +378,8 @@ extern "C" int seer_b200_cfg_ddim_update(const float* eps, const float* x, float
                                          float sqrt_a_prev, float dir_coef, void* stream) {
   SEER_CHECK_ARG(eps && x && x_prev && pred_x0 && b > 0 && C > 0 && F2 > 0 && HW > 0 && cond_f >= 0);
   const size_t total = (size_t)b * C * F2 * HW;
-  cfg_ddim_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(eps, x, x_prev, pred_x0, b, C, F2, cond_f, HW, use_cfg,
-                                                                          scale, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef);
+  { cudaError_t le__ = launch_pdl(cfg_ddim_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, eps, x, x_prev, pred_x0, b, C, F2, cond_f, HW, use_cfg,
+                                                                          scale, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

@@ -82,6 +82,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // barrier inits visible (cluster-wide) before any arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped the previous kernel's tail; from here on global memory is touched
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops — uniform control flow; one elected lane issues) ==========
@@ -423,13 +426,15 @@ static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, const Plan&
   cfg.blockDim = dim3(64 + 32 * pl.nepi);
   cfg.dynamicSmemBytes = pl.smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, maps[0], maps[1], maps[2], maps[3], p);
   if (e != cudaSuccess) return (int)e;
   SEER_LAUNCH_CHECK();

@@ -28,6 +28,7 @@ __device__ __forceinline__ float2 load_cat2(const float* x1, int C1, const float
 __global__ void __launch_bounds__(GN_THREADS) gn_partial_kernel(const float* __restrict__ x1, int C1,
                                                                 const float* __restrict__ x2, int C2, int T, int tpc,
                                                                 float* __restrict__ partial) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const int C = C1 + C2;
   const int cpg = C / GN_GROUPS;
   const int ncol = C / 2;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_partial_kernel(const float* __r
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nchunks, int C, int T, float eps,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_rstd) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cpg = C / GN_GROUPS;
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(256) gn_finalize_cols_kernel(const float2* __r
                                                                const float2* __restrict__ st2, int C2, int T, float eps,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const int C = C1 + C2;
   const int cpg = C / GN_GROUPS;
   const int g = blockIdx.x, b = blockIdx.y;
@@ -162,6 +165,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                        int C2, int T, size_t total8, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, int silu, void* __restrict__ y,
                                                        __nv_bfloat16* __restrict__ raw) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const int C = C1 + C2;
   const int c8n = C / 8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (size_t)gridDim.x * blockDim.x) {
@@ -203,6 +207,7 @@ constexpr int LN_MAX_V4 = 10;  // C <= 1280
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int M, int C, int ldx,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, __nv_bfloat16* __restrict__ y, int ldy) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -267,17 +272,17 @@ extern "C" int seer_b200_groupnorm(const float* x1, int C1, const float* x2, int
   const int nchunks = ceil_div(T, tpc);
   float* scale = scale_shift;
   float* shift = scale_shift + (size_t)B * C;
-  gn_partial_kernel<<<dim3(nchunks, B), GN_THREADS, 0, stream>>>(x1, C1, x2, C2, T, tpc, workspace);
+  { cudaError_t le__ = launch_pdl(gn_partial_kernel, dim3(nchunks, B), GN_THREADS, 0, stream, x1, C1, x2, C2, T, tpc, workspace); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
-  gn_finalize_kernel<<<B, GN_GROUPS * 32, 0, stream>>>(workspace, nchunks, C, T, eps, gamma, beta, scale, shift, nullptr);
+  { cudaError_t le__ = launch_pdl(gn_finalize_kernel, B, GN_GROUPS * 32, 0, stream, workspace, nchunks, C, T, eps, gamma, beta, scale, shift, nullptr); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   const size_t total8 = (size_t)B * T * (C / 8);
   size_t nb = (total8 + 255) / 256; if (nb > (size_t)148 * 16) nb = (size_t)148 * 16;
   const int blocks = (int)nb;
   if (y_is_f32)
-    gn_apply_kernel<true><<<blocks, 256, 0, stream>>>(x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16);
+    { cudaError_t le__ = launch_pdl(gn_apply_kernel<true>, blocks, 256, 0, stream, x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
   else
-    gn_apply_kernel<false><<<blocks, 256, 0, stream>>>(x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16);
+    { cudaError_t le__ = launch_pdl(gn_apply_kernel<false>, blocks, 256, 0, stream, x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
@@ -291,16 +296,16 @@ extern "C" int seer_b200_groupnorm_from_stats(const float* x1, int C1, const flo
   SEER_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && (C2 == 0 || (x2 && stats2)) && C % (2 * GN_GROUPS) == 0);
   float* scale = scale_shift;
   float* shift = scale_shift + (size_t)B * C;
-  gn_finalize_cols_kernel<<<dim3(GN_GROUPS, B), 256, 0, stream>>>((const float2*)stats1, C1, (const float2*)stats2, C2, T, eps,
-                                                                  gamma, beta, scale, shift);
+  { cudaError_t le__ = launch_pdl(gn_finalize_cols_kernel, dim3(GN_GROUPS, B), 256, 0, stream, (const float2*)stats1, C1, (const float2*)stats2, C2, T, eps,
+                                                                  gamma, beta, scale, shift); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   const size_t total8 = (size_t)B * T * (C / 8);
   size_t nb = (total8 + 255) / 256; if (nb > (size_t)148 * 16) nb = (size_t)148 * 16;
   const int blocks = (int)nb;
   if (y_is_f32)
-    gn_apply_kernel<true><<<blocks, 256, 0, stream>>>(x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16);
+    { cudaError_t le__ = launch_pdl(gn_apply_kernel<true>, blocks, 256, 0, stream, x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
   else
-    gn_apply_kernel<false><<<blocks, 256, 0, stream>>>(x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16);
+    { cudaError_t le__ = launch_pdl(gn_apply_kernel<false>, blocks, 256, 0, stream, x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
@@ -309,7 +314,7 @@ extern "C" int seer_b200_layernorm(const float* x, int M, int C, int ldx, const 
                                    void* y_bf16, int ldy, void* stream) {
   SEER_CHECK_ARG(x && gamma && beta && y_bf16 && M > 0);
   SEER_CHECK_ARG(C % 4 == 0 && C <= LN_MAX_V4 * 128 && ldx % 4 == 0 && ldy % 4 == 0);
-  layernorm_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(x, M, C, ldx, gamma, beta, eps, (__nv_bfloat16*)y_bf16, ldy);
+  { cudaError_t le__ = launch_pdl(layernorm_kernel, ceil_div(M, 8), 256, 0, (cudaStream_t)stream, x, M, C, ldx, gamma, beta, eps, (__nv_bfloat16*)y_bf16, ldy); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

@@ -149,3 +149,17 @@ def test_full_size_sthv2_step(model):
     # size-independent property: eps of frame f in clip b is unchanged by permuting the CFG halves
     out2 = net(x.flip(0).contiguous().cuda(), t.cuda(), c.flip(0).contiguous().cuda())
     assert torch.equal(out2.flip(0), out)
+
+
+@pytest.mark.slow
+def test_step_64x64_latent(model):
+    """BASELINE.json config 5 geometry (512x512 frames -> 64x64 latents): level-0 spatial attention over 4096 tokens, SCTA
+    over 64 windows of 8x8, 32x32 / 16x16 / 8x8 below.  Two frames keep the CPU oracle at a few seconds."""
+    net, sd = model
+    x, c = gen(71, 1, 4, 2, 64, 64), gen(72, 1, 2, 77, 768)
+    t = torch.full((1,), 650, dtype=torch.long)
+    ref = so.unet_forward(sd, x, t, c, 0)
+    out = net(x.cuda(), t.cuda(), c.cuda())
+    err = so.rel_l2(out.cpu(), ref)
+    print(f"64x64-latent step rel-L2: {err:.3e}")
+    assert err < STEP_TOL_BF16

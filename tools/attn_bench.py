@@ -17,11 +17,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--frames", type=int, default=16)
+ap.add_argument("--latent", type=int, default=32, help="level-0 latent side (64 = BASELINE.json config 5, the 512x512 attention stress)")
 args = ap.parse_args()
 B, F, heads = args.batch, args.frames, 8
 dev = "cuda"
 cases = []
-for d, h in ((40, 32), (80, 16), (160, 8)):
+for d, h in ((40, args.latent), (80, args.latent // 2), (160, args.latent // 4)):
     C = heads * d
     M = B * F * h * h
     qkv = torch.randn(M, 3 * C, device=dev).bfloat16()
