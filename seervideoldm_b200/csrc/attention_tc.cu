@@ -401,6 +401,371 @@ static int at_map_4d(CUtensorMap* tm, const void* base, uint64_t n_frames, uint6
   return r == CUDA_SUCCESS ? SEER_OK : SEER_EINVAL;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent variant (default): 2 CTAs per SM loop over (problem, query tile) work items with ONE prologue (barrier init,
+// TMEM allocation) per CTA, and the tile pipeline runs across item boundaries: Q of the next item is fetched as soon as the
+// last Q K^T of the current one has been issued, its S(0) is computed while the softmax warps normalise and store O.
+// With 8 (spatial), 1..8 (SCTA) or 1 (cross) key tiles per item the per-CTA prologue was ~20 % of the softmax warps' time
+// (ncu, profiles/r1_attention_tc_v2.summary.txt; the L = 4096 problems of config 5 reach 77 % of the MUFU roofline with the
+// same tile loop, the L = 1024 ones 64 %).
+// The head split uses tensor maps over the [rows, heads, d] view with a 64-wide box: columns d..63 of every tile are
+// out-of-bounds of the head and arrive as ZEROS, so nothing has to be zeroed in shared memory.
+// Item order: non-causal = query tiles of a problem adjacent (K/V stay in L2); causal = longest items (highest query tile)
+// first, round-robin over the CTAs, so every CTA receives the same mix of lengths.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                            const __grid_constant__ CUtensorMap tmV, const AttnTcParams p, const int n_problems,
+                            const int nq_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + AT_TILE;
+  uint8_t* sV = sK + AT_TILE;
+  uint8_t* sP = sV + AT_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_P_BYTES);
+  uint64_t* q_full = bars + 0;     // TMA: Q of item n landed
+  uint64_t* q_empty = bars + 1;    // every Q K^T of item n has completed: Q may be overwritten
+  uint64_t* k_full = bars + 2;
+  uint64_t* k_empty = bars + 3;    // S MMA has read K
+  uint64_t* v_full = bars + 4;
+  uint64_t* v_empty = bars + 5;    // P V MMA has read V (and P)
+  uint64_t* s_full = bars + 6;     // S in TMEM
+  uint64_t* s_free = bars + 7;     // softmax pulled S into registers (count 4)
+  uint64_t* p_full = bars + 8;     // P in smem (count 4)
+  uint64_t* o_full = bars + 9;     // P V of a tile has completed
+  uint64_t* o_free = bars + 10;    // softmax read the finished O of item n (count 4): P V(0) of item n+1 may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = n_problems * nq_tiles;
+  const int n_kv_full = ceil_div(p.Lk, AT_BN);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 4);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;           // 128 columns
+  const uint32_t tO = tmem_base + 128;     // 64 columns
+  pdl_wait();                              // PDL secondary: the prologue above overlapped the previous kernel's tail
+
+  // work item -> (problem, query tile)
+  auto decode = [&](int idx, int& prob, int& qt) {
+    if (p.causal) { qt = nq_tiles - 1 - idx / n_problems; prob = idx - (idx / n_problems) * n_problems; }
+    else { prob = idx / nq_tiles; qt = idx - prob * nq_tiles; }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    uint32_t it = 0, n = 0;
+    for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n) {
+      int prob, qt;
+      decode(idx, prob, qt);
+      const int head = prob % p.heads, outer = prob / p.heads;
+      int b = 0, wy = 0, wx = 0;
+      if (p.mode == SEER_ATTN_SCTA) {
+        b = outer / p.nwin;
+        const int win = outer - b * p.nwin;
+        wy = win / p.nwx;
+        wx = win - wy * p.nwx;
+      }
+      const int n_kv = p.causal ? min(n_kv_full, qt + 1) : n_kv_full;
+      // Q: [rows, heads, d] view, columns d..63 arrive as zeros (so K's and V's pad columns — the next head's channels,
+      // fetched through the plain token-major maps with full 128-byte rows — contribute nothing to Q K^T; the matching
+      // O columns are never stored)
+      auto load_tile = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tile, int L) {
+        if (p.mode == SEER_ATTN_SCTA) tma_load_4d(dst, tm, bar, head * D, wx * 8, wy * 8, b * p.F + tile * 2);
+        else tma_load_2d(dst, tm, bar, head * D, outer * L + tile * AT_BN);
+      };
+      mbar_wait(q_empty, (n & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, AT_TILE);
+        if (p.mode == SEER_ATTN_SCTA) tma_load_5d(sQ, &tmQ, q_full, 0, head, wx * 8, wy * 8, b * p.F + qt * 2);
+        else tma_load_3d(sQ, &tmQ, q_full, 0, head, outer * p.Lq + qt * AT_BN);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_kv; ++j, ++it) {
+        mbar_wait(k_empty, (it & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(k_full, AT_TILE);
+          load_tile(sK, &tmK, k_full, j, p.Lk);
+        }
+        __syncwarp();
+        mbar_wait(v_empty, (it & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(v_full, AT_TILE);
+          load_tile(sV, &tmV, v_full, j, p.Lk);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN);          // S = Q K^T : N = 128 keys, K = 64 (padded d)
+    constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(AT_BM, AT_DP);      // O = P V   : N = 64 (padded d), K = 128 keys, V MN-major
+    const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
+    const uint64_t k_desc = umma_desc_sw128(smem_u32(sK));
+    const uint64_t v_desc = umma_desc_sw128_mn(smem_u32(sV));
+    const uint64_t p_desc0 = umma_desc_sw128(smem_u32(sP));
+    const uint64_t p_desc1 = umma_desc_sw128(smem_u32(sP + AT_BM * 128));
+    uint32_t it = 0, n = 0;
+    // S of tile `t` (global tile counter); `last` = it is the last Q K^T of its item -> Q may be refilled afterwards
+    auto issue_s = [&](uint32_t t, bool last) {
+      mbar_wait(k_full, t & 1);
+      mbar_wait(s_free, (t & 1) ^ 1);          // softmax has drained S of tile t-1
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < AT_DP / 16; ++k)
+          umma_bf16(tS, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0);
+        umma_commit(s_full);
+        umma_commit(k_empty);
+        if (last) umma_commit(q_empty);
+      }
+      __syncwarp();
+    };
+    for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n) {
+      int prob, qt;
+      decode(idx, prob, qt);
+      const int n_kv = p.causal ? min(n_kv_full, qt + 1) : n_kv_full;
+      mbar_wait(q_full, n & 1);
+      issue_s(it, n_kv == 1);
+      for (int j = 0; j < n_kv; ++j, ++it) {
+        const uint32_t ph = it & 1;
+        if (j + 1 < n_kv) issue_s(it + 1, j + 2 == n_kv);
+        mbar_wait(v_full, ph);
+        mbar_wait(p_full, ph);                 // P of this tile in smem; any rescale of O by the softmax warps has retired
+        if (j == 0) mbar_wait(o_free, (n & 1) ^ 1);   // the previous item's O has been read out of TMEM
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < AT_BN / 16; ++k) {
+            const uint64_t a = (k < 4 ? p_desc0 : p_desc1) + (uint64_t)((k & 3) * 2);
+            umma_bf16(tO, a, v_desc + (uint64_t)(k * 128), idesc_o, (j | k) != 0);
+          }
+          umma_commit(o_full);
+          umma_commit(v_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== softmax warps (thread = query row) =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;               // row inside the tile = TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const float sl2 = p.scale_log2;
+    uint32_t it = 0, n = 0;
+    for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n) {
+      int prob, qt;
+      decode(idx, prob, qt);
+      const int head = prob % p.heads, outer = prob / p.heads;
+      const int n_kv = p.causal ? min(n_kv_full, qt + 1) : n_kv_full;
+      const int qi = qt * AT_BM + r;           // query index in the sequence
+      float m_run = -INFINITY, l_run = 0.f;    // m_run: the (lazily raised) reference maximum of this row
+
+      for (int j = 0; j < n_kv; ++j, ++it) {
+        const uint32_t ph = it & 1;
+        const int kv0 = j * AT_BN;
+        const bool need_mask = (kv0 + AT_BN > p.Lk) || (p.causal && j == qt);
+        const int k_hi = min(p.Lk - kv0, p.causal && j == qt ? r + 1 : AT_BN);   // keys [0, k_hi) of this tile are visible
+        mbar_wait(s_full, ph);
+        tc_fence_after();
+        uint32_t v[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + lane_addr + c * 32, v[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (need_mask) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (c * 32 + k < k_hi) mx4[c] = fmaxf(mx4[c], __uint_as_float(v[c][k]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int k = 0; k < 32; ++k) mx4[c] = fmaxf(mx4[c], __uint_as_float(v[c][k]));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        if (j == 0) {
+          m_run = mx;                          // O is overwritten (not accumulated) by the first P V of the item; P is free:
+                                               // the previous item's epilogue waited for its last P V
+        } else {
+          mbar_wait(o_full, ph ^ 1);           // P V of the previous tile done: P may be overwritten, O may be rescaled
+          if (__any_sync(0xffffffffu, (mx - m_run) * sl2 > 8.0f)) {
+            tc_fence_after();
+            const float m_new = fmaxf(m_run, mx);
+            const float corr = exp2f((m_run - m_new) * sl2);
+            l_run *= corr;
+            m_run = m_new;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {      // columns 0..47 hold the D = 40 live output channels
+              uint32_t o[16];
+              tmem_ld_32x16(tO + lane_addr + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+              tmem_st_32x16(tO + lane_addr + c * 16, o);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+          }
+        }
+        const float msc = m_run * sl2;
+        float sum = 0.f;
+        if (need_mask) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint8_t* prow = sP + (c >> 1) * (AT_BM * 128) + r * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float e[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[k]) : "f"(fmaf(__uint_as_float(v[c][8 * g + k]), sl2, -msc)));
+                if (c * 32 + 8 * g + k >= k_hi) e[k] = 0.f;
+              }
+              sum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+              uint4 o;
+              o.x = pack_bf16(e[0], e[1]);
+              o.y = pack_bf16(e[2], e[3]);
+              o.z = pack_bf16(e[4], e[5]);
+              o.w = pack_bf16(e[6], e[7]);
+              sts128u(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4), o);
+            }
+          }
+        } else {
+          const f2_t sl22 = f2_pack(sl2, sl2), nmsc2 = f2_pack(-msc, -msc);
+          f2_t sum2[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint8_t* prow = sP + (c >> 1) * (AT_BM * 128) + r * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t o[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float x0, x1, e0, e1;
+                f2_unpack(f2_fma(f2_pack_u(v[c][8 * g + 2 * k], v[c][8 * g + 2 * k + 1]), sl22, nmsc2), x0, x1);
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+                sum2[k & 1] = f2_add(sum2[k & 1], f2_pack(e0, e1));
+                o[k] = pack_bf16(e0, e1);
+              }
+              sts128u(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+            }
+          }
+          float s0, s1;
+          f2_unpack(f2_add(sum2[0], sum2[1]), s0, s1);
+          sum = s0 + s1;
+        }
+        l_run += sum;
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+
+      // ---- item epilogue: O (accumulated in TMEM) after the last P V, handed back to the MMA warp at once ----
+      mbar_wait(o_full, (it - 1) & 1);
+      tc_fence_after();
+      uint32_t v0[32], v1[8];
+      tmem_ld_32x32(tO + lane_addr, v0);
+      tmem_ld_32x8(tO + lane_addr + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+      size_t grow;
+      if (p.mode == SEER_ATTN_SCTA) {
+        const int b = outer / p.nwin, win = outer - b * p.nwin;
+        const int wy = win / p.nwx, wx = win - wy * p.nwx;
+        const int f = qt * 2 + (r >> 6), iy = (r >> 3) & 7, ix = r & 7;
+        grow = ((size_t)(b * p.F + f) * p.H + wy * 8 + iy) * p.W + wx * 8 + ix;
+      } else {
+        grow = (size_t)outer * p.Lq + qi;
+      }
+      if (qi < p.Lq) {
+        const float inv = 1.0f / l_run;
+        __nv_bfloat16* dst = p.o + grow * p.ldo + head * D;
+#pragma unroll
+        for (int g = 0; g < D / 8; ++g) {
+          const uint32_t* src = g < 4 ? &v0[8 * g] : &v1[8 * (g - 4)];
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+          o.y = pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+          o.z = pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+          o.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+          *reinterpret_cast<uint4*>(dst + 8 * g) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncwarp();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// head-split maps with zero fill beyond the head: [rows, heads, d] view, box {64, 1, 128}
+static int at_map_heads_3d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t heads, uint64_t d, uint64_t ld) {
+  EncodeTiledFn enc = at_encode_fn();
+  if (!enc) return SEER_ENODRIVER;
+  cuuint64_t dims[3] = {d, heads, rows};
+  cuuint64_t strides[2] = {d * 2, ld * 2};
+  cuuint32_t box[3] = {AT_DP, 1, AT_BN};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SEER_OK : SEER_EUNSUPPORTED;
+}
+// [n_frames, H, W, heads, d] view; box {64, 1, 8, 8, 2 frames} = one 8x8 window of two frames of one head
+static int at_map_heads_5d(CUtensorMap* tm, const void* base, uint64_t n_frames, uint64_t H, uint64_t W, uint64_t heads, uint64_t d,
+                           uint64_t ld) {
+  EncodeTiledFn enc = at_encode_fn();
+  if (!enc) return SEER_ENODRIVER;
+  cuuint64_t dims[5] = {d, heads, W, H, n_frames};
+  cuuint64_t strides[4] = {d * 2, ld * 2, W * ld * 2, H * W * ld * 2};
+  cuuint32_t box[5] = {AT_DP, 1, 8, 8, 2};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SEER_OK : SEER_EUNSUPPORTED;
+}
+
 static int env_flag(const char* name, int dflt) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : dflt;
@@ -450,6 +815,41 @@ extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ld
   const uint64_t C = (uint64_t)heads * head_dim;
   CUtensorMap tq, tk, tv;
   int rc;
+  if (env_flag("SEER_ATTN_PERSIST", 1)) {
+    // persistent kernel, zero-filling head-split maps
+    int ok;
+    if (mode == SEER_ATTN_SCTA) {
+      const uint64_t nf = (uint64_t)n_outer * F;
+      ok = at_map_heads_5d(&tq, q, nf, H, W, heads, head_dim, ldq) == SEER_OK && at_map_4d(&tk, k, nf, H, W, C, ldk) == SEER_OK &&
+           at_map_4d(&tv, v, nf, H, W, C, ldv) == SEER_OK;
+    } else {
+      ok = at_map_heads_3d(&tq, q, (uint64_t)n_outer * Lq, heads, head_dim, ldq) == SEER_OK &&
+           at_map_2d(&tk, k, (uint64_t)n_outer * Lk, C, ldk) == SEER_OK && at_map_2d(&tv, v, (uint64_t)n_outer * Lk, C, ldv) == SEER_OK;
+    }
+    if (ok) {
+      static bool attr_done_p = false;
+      if (!attr_done_p) {
+        cudaError_t e = cudaFuncSetAttribute(attention_tc_persist_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_done_p = true;
+      }
+      int dev = 0, nsm = 148;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0)
+        nsm = 148;
+      const long total = (long)n_problems * nq_tiles;
+      const int grid = (int)(total < 2L * nsm ? total : 2L * nsm);
+      cudaError_t le = launch_pdl(attention_tc_persist_kernel<40>, dim3(grid), dim3(AT_THREADS), (size_t)AT_SMEM, (cudaStream_t)stream, tq, tk,
+                                  tv, p, n_problems, nq_tiles);
+      if (le != cudaSuccess) return (int)le;
+      SEER_LAUNCH_CHECK();
+      return SEER_OK;
+    }
+    static bool warned = false;
+    if (!warned) {
+      warned = true;
+      fprintf(stderr, "[seer_b200] attention: head-split tensor maps rejected by the driver, using the one-tile-per-CTA kernel\n");
+    }
+  }
   if (mode == SEER_ATTN_SCTA) {
     const uint64_t nf = (uint64_t)n_outer * F;
     if ((rc = at_map_4d(&tq, q, nf, H, W, C, ldq))) return rc;
