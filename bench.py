@@ -292,7 +292,7 @@ def run_ours(args):
                      "frac_of_tensor_peak": att_tf / peaks["sustained"], "share_of_step_time": att_ms / max(t_all_ms, 1e-9),
                      "by_kind": by_kind,
                      "note": "d=40 level is MUFU(ex2)-bound: 160 tensor FLOP per exp2 caps it near 31 % of the tensor peak "
-                             "(profiles/r1_attention_tc_*.summary.txt)"}
+                             "(profiles/r1_attention_tc.summary.txt)"}
         if world == 1 and not args.no_cpu_baseline:
             fn, kind = cpu_eval_fn()
             with torch.no_grad():

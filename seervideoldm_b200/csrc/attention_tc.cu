@@ -406,7 +406,7 @@ static int at_map_4d(CUtensorMap* tm, const void* base, uint64_t n_frames, uint6
 // TMEM allocation) per CTA, and the tile pipeline runs across item boundaries: Q of the next item is fetched as soon as the
 // last Q K^T of the current one has been issued, its S(0) is computed while the softmax warps normalise and store O.
 // With 8 (spatial), 1..8 (SCTA) or 1 (cross) key tiles per item the per-CTA prologue was ~20 % of the softmax warps' time
-// (ncu, profiles/r1_attention_tc_v2.summary.txt; the L = 4096 problems of config 5 reach 77 % of the MUFU roofline with the
+// (ncu, profiles/r1_attention_tc.summary.txt; the L = 4096 problems of config 5 reach 77 % of the MUFU roofline with the
 // same tile loop, the L = 1024 ones 64 %).
 // The head split uses tensor maps over the [rows, heads, d] view with a 64-wide box: columns d..63 of every tile are
 // out-of-bounds of the head and arrive as ZEROS, so nothing has to be zeroed in shared memory.

@@ -114,11 +114,11 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 // conv_in: 3x3, Cin = 4 -> Cout, fp32, input in the reference's (B, Cin, F, H, W) layout, output token-major
 // [B*F*H*W, Cout] fp32.   unet_3d_condition.py:94,311.
 // ---------------------------------------------------------------------------------------------------
-constexpr int CI_PIX = 16;
+constexpr int CI_PIX = 64;     // pixels per block: the 36 weights a thread keeps in registers are fetched once per 64 pixels
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                float* __restrict__ out, int B, int Cin, int F, int H, int W, int Cout) {
   pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
-  extern __shared__ float s_in[];  // [CI_PIX][Cin*9]
+  extern __shared__ __align__(16) float s_in[];  // [CI_PIX][Cin*9]
   constexpr int K = 36;  // Cin == 4 (checked on the host)
   const int HW = H * W;
   const size_t npix = (size_t)B * F * HW;
@@ -145,50 +145,103 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
     for (int pi = 0; pi < CI_PIX; ++pi) {
       if (p0 + pi >= npix) break;
       float acc = bz;
+      const float4* sp = reinterpret_cast<const float4*>(s_in + pi * K);     // broadcast reads, 16 bytes each
 #pragma unroll
-      for (int k = 0; k < K; ++k) acc += s_in[pi * K + k] * wr[k];
+      for (int k4 = 0; k4 < K / 4; ++k4) {
+        const float4 v = sp[k4];
+        acc += v.x * wr[4 * k4];
+        acc += v.y * wr[4 * k4 + 1];
+        acc += v.z * wr[4 * k4 + 2];
+        acc += v.w * wr[4 * k4 + 3];
+      }
       out[(p0 + pi) * Cout + co] = acc;
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// conv_out: 3x3, Cin -> 4, fp32, input token-major [B*F*H*W, Cin] fp32 (already GroupNorm+SiLU'd), output in the
-// reference's (B, Cout, F, H, W) layout.  One warp per output pixel.   unet_3d_condition.py:205,370.
-// Weights pre-packed as wp[co][tap][Cin].
+// conv_out: 3x3, Cin -> <= 4, fp32, input token-major [B*F*H*W, Cin] fp32 (already GroupNorm+SiLU'd), output in the
+// reference's (B, Cout, F, H, W) layout.   unet_3d_condition.py:205,370.  Weights pre-packed as wp[co][tap][Cin].
+// One block = one output image row.  Per 64-channel chunk the three input rows (and the chunk's weights) are staged in
+// shared memory once — every input pixel is read from L2 by the 3 row-blocks that need it instead of by 9 taps x 1 warp —
+// and a half-warp (16 lanes = the chunk's 16 channel quads) accumulates 4 adjacent output pixels x 4 output channels,
+// so a weight quad fetched from smem feeds 4 pixels.  Deterministic: fixed summation order, no atomics.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__ x, const float* __restrict__ wp,
-                                                       const float* __restrict__ bias, float* __restrict__ out, int B, int Cin,
-                                                       int F, int H, int W, int Cout) {
+constexpr int CO_CK = 64;        // channels per chunk
+constexpr int CO_PIX = 4;        // output pixels per half-warp pass
+constexpr int CO_THREADS = 128;
+__global__ void __launch_bounds__(CO_THREADS) conv_out_kernel(const float* __restrict__ x, const float* __restrict__ wp,
+                                                              const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                              int Cin, int F, int H, int W, int Cout) {
   pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
-  const int HW = H * W;
-  const size_t npix = (size_t)B * F * HW;
-  const size_t pix = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (pix >= npix) return;
-  const int bf = (int)(pix / HW), rem = (int)(pix - (size_t)bf * HW);
-  const int y = rem / W, xq = rem % W;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int tap = 0; tap < 9; ++tap) {
-    const int yy = y + tap / 3 - 1, xx = xq + tap % 3 - 1;
-    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-    const float* src = x + ((size_t)bf * HW + yy * W + xx) * Cin;
-    for (int c = lane * 4; c < Cin; c += 128) {
-      const float4 v = *reinterpret_cast<const float4*>(src + c);
+  extern __shared__ __align__(16) float co_smem[];
+  float* sx = co_smem;                       // [3][W][CO_CK]
+  float* sw = sx + 3 * W * CO_CK;            // [9][4][CO_CK]
+  const int bf = blockIdx.x / H, y = blockIdx.x - bf * H;
+  const int tid = threadIdx.x;
+  const int hw = tid >> 4, l = tid & 15;     // half-warp index (0..7), channel quad
+  const int n_groups = (W + CO_PIX - 1) / CO_PIX;
+  constexpr int MAX_G = 2;                   // pixel groups per half-warp (W <= 64)
+  float acc[MAX_G][CO_PIX][4];
 #pragma unroll
-      for (int co = 0; co < 4; ++co) {
-        if (co < Cout) {
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(wp + ((size_t)co * 9 + tap) * Cin + c));
-          acc[co] += (v.x * wv.x + v.y * wv.y) + (v.z * wv.z + v.w * wv.w);
+  for (int g = 0; g < MAX_G; ++g)
+#pragma unroll
+    for (int p = 0; p < CO_PIX; ++p) acc[g][p][0] = acc[g][p][1] = acc[g][p][2] = acc[g][p][3] = 0.f;
+
+  for (int c0 = 0; c0 < Cin; c0 += CO_CK) {
+    __syncthreads();                         // previous chunk consumed
+    for (int i = tid; i < 3 * W * (CO_CK / 4); i += CO_THREADS) {
+      const int q = i % (CO_CK / 4), px = (i / (CO_CK / 4)) % W, rr = i / ((CO_CK / 4) * W);
+      const int yy = y + rr - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yy >= 0 && yy < H) v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)bf * H + yy) * W + px) * Cin + c0) + q);
+      reinterpret_cast<float4*>(sx)[i] = v;
+    }
+    for (int i = tid; i < 9 * 4 * (CO_CK / 4); i += CO_THREADS) {
+      const int q = i % (CO_CK / 4), co = (i / (CO_CK / 4)) % 4, tap = i / ((CO_CK / 4) * 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (co < Cout) v = __ldg(reinterpret_cast<const float4*>(wp + ((size_t)co * 9 + tap) * Cin + c0) + q);
+      reinterpret_cast<float4*>(sw)[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < MAX_G; ++g) {
+      const int grp = hw + g * 8;
+      if (grp >= n_groups) break;
+      const int x0 = grp * CO_PIX;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int rr = tap / 3, dx = tap % 3 - 1;
+        float4 wv[4];
+#pragma unroll
+        for (int co = 0; co < 4; ++co) wv[co] = reinterpret_cast<const float4*>(sw)[(tap * 4 + co) * (CO_CK / 4) + l];
+#pragma unroll
+        for (int p = 0; p < CO_PIX; ++p) {
+          const int xx = x0 + p + dx;
+          if (xx < 0 || xx >= W) continue;
+          const float4 v = reinterpret_cast<const float4*>(sx)[(rr * W + xx) * (CO_CK / 4) + l];
+#pragma unroll
+          for (int co = 0; co < 4; ++co)
+            acc[g][p][co] += (v.x * wv[co].x + v.y * wv[co].y) + (v.z * wv[co].z + v.w * wv[co].w);
         }
       }
     }
   }
   const int b = bf / F, f = bf - b * F;
 #pragma unroll
-  for (int co = 0; co < 4; ++co) {
-    const float v = warp_sum(acc[co]);
-    if (lane == 0 && co < Cout) out[((((size_t)b * Cout + co) * F + f) * H + y) * W + xq] = v + bias[co];
+  for (int g = 0; g < MAX_G; ++g) {
+    const int grp = hw + g * 8;
+    if (grp >= n_groups) break;
+#pragma unroll
+    for (int p = 0; p < CO_PIX; ++p) {
+#pragma unroll
+      for (int co = 0; co < 4; ++co) {
+        float v = acc[g][p][co];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);    // within the 16-lane half
+        const int xq = grp * CO_PIX + p;
+        if (l == 0 && co < Cout && xq < W) out[((((size_t)b * Cout + co) * F + f) * H + y) * W + xq] = v + bias[co];
+      }
+    }
   }
 }
 
@@ -346,9 +399,15 @@ extern "C" int seer_b200_conv_in(const float* x, const float* w, const float* bi
 
 extern "C" int seer_b200_conv_out(const float* x, const float* w_packed, const float* bias, float* out, int B, int Cin, int F,
                                   int H, int W, int Cout, void* stream) {
-  SEER_CHECK_ARG(x && w_packed && bias && out && Cout <= 4 && Cin % 4 == 0);
-  const size_t npix = (size_t)B * F * H * W;
-  { cudaError_t le__ = launch_pdl(conv_out_kernel, (unsigned)((npix + 7) / 8), 256, 0, (cudaStream_t)stream, x, w_packed, bias, out, B, Cin, F, H, W, Cout); if (le__ != cudaSuccess) return (int)le__; }
+  SEER_CHECK_ARG(x && w_packed && bias && out && Cout <= 4 && Cin % CO_CK == 0 && W >= 1 && W <= 64);
+  const size_t smem = (size_t)(3 * W * CO_CK + 9 * 4 * CO_CK) * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    smem_set = smem;
+  }
+  { cudaError_t le__ = launch_pdl(conv_out_kernel, (unsigned)(B * F * H), CO_THREADS, smem, (cudaStream_t)stream, x, w_packed, bias, out, B, Cin, F, H, W, Cout); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

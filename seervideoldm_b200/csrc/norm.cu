@@ -125,15 +125,22 @@ __global__ void __launch_bounds__(256) gn_finalize_cols_kernel(const float2* __r
   const int g = blockIdx.x, b = blockIdx.y;
   const int slabs = T / 32;
   const int total = slabs * cpg;
-  double s = 0.0, q = 0.0;
+  // per-thread partial in compensated fp32 (Kahan: the fp64 pipe of this part runs at 1/64 rate and two DADDs per
+  // element made this kernel 10 us long); threads are combined in double below
+  float sf = 0.f, qf = 0.f, sc_ = 0.f, qc_ = 0.f;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int sl = i / cpg;
     const int c = g * cpg + (i - sl * cpg);
     const size_t slab = (size_t)b * slabs + sl;
     const float2 v = c < C1 ? st1[slab * C1 + c] : st2[slab * C2 + (c - C1)];
-    s += (double)v.x;
-    q += (double)v.y;
+    const float ys = __fsub_rn(v.x, sc_), ts = __fadd_rn(sf, ys);
+    sc_ = __fsub_rn(__fsub_rn(ts, sf), ys);
+    sf = ts;
+    const float yq = __fsub_rn(v.y, qc_), tq = __fadd_rn(qf, yq);
+    qc_ = __fsub_rn(__fsub_rn(tq, qf), yq);
+    qf = tq;
   }
+  double s = (double)sf - (double)sc_, q = (double)qf - (double)qc_;
   __shared__ double sh[2][8];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -158,48 +165,94 @@ __global__ void __launch_bounds__(256) gn_finalize_cols_kernel(const float2* __r
   }
 }
 
-// y = act(x * scale[b, c] + shift[b, c]);  8 channels per thread.  Optional second output: raw bf16 copy of x
-// (the un-normalised concat that feeds the fused ResNet 1x1 shortcut GEMM).
+// y = act(x * scale[b, c] + shift[b, c]).  Optional second output: raw bf16 copy of x (the un-normalised concat that feeds
+// the fused ResNet 1x1 shortcut GEMM).  HBM-bound (4 B in, 2 B out per element): a thread owns ONE 8-channel chunk for
+// its whole life — the 16 scale / shift values sit in registers, the inner loop is two 16-byte loads, 8 FMAs (+ SiLU) and
+// one 16-byte store per row with no index arithmetic, unrolled by 4 rows so eight loads are in flight per thread.
+// Block = rps rows x (C/8) chunks (consecutive threads = consecutive chunks of a row: 32-byte pieces of one contiguous row),
+// it walks `rows_per_block` rows of ONE sample; grid = (blocks per sample, B).
 template <bool OUT_F32>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
-                                                       int C2, int T, size_t total8, const float* __restrict__ scale,
+__global__ void __launch_bounds__(512) gn_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
+                                                       int C2, int T, int rows_per_block, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, int silu, void* __restrict__ y,
                                                        __nv_bfloat16* __restrict__ raw) {
   pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const int C = C1 + C2;
   const int c8n = C / 8;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t row = i / c8n;
-    const int c = (int)(i - row * c8n) * 8;
-    const int b = (int)(row / T);
-    const float* src = c < C1 ? x1 + row * C1 + c : x2 + row * C2 + (c - C1);
-    const float4 a0 = *reinterpret_cast<const float4*>(src);
-    const float4 a1 = *reinterpret_cast<const float4*>(src + 4);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * C + c));
-    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * C + c + 4));
-    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + (size_t)b * C + c));
-    const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + (size_t)b * C + c + 4));
-    float v[8] = {a0.x * s0.x + h0.x, a0.y * s0.y + h0.y, a0.z * s0.z + h0.z, a0.w * s0.w + h0.w,
-                  a1.x * s1.x + h1.x, a1.y * s1.y + h1.y, a1.z * s1.z + h1.z, a1.w * s1.w + h1.w};
+  const int rps = blockDim.x / c8n;                 // rows per step
+  const int chunk = threadIdx.x % c8n, rl = threadIdx.x / c8n;
+  const int c = chunk * 8;
+  const int b = blockIdx.y;
+  const int r_begin = blockIdx.x * rows_per_block;
+  const int r_end = min(T, r_begin + rows_per_block);
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * C + c));
+  const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * C + c + 4));
+  const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + (size_t)b * C + c));
+  const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + (size_t)b * C + c + 4));
+  const bool first = c < C1;
+  const int ldx = first ? C1 : C2;
+  const float* src = (first ? x1 + c : x2 + (c - C1)) + ((size_t)b * T + r_begin + rl) * ldx;
+  const size_t out_off = ((size_t)b * T + r_begin + rl) * C + c;
+  const size_t in_step = (size_t)rps * ldx, out_step = (size_t)rps * C;
+
+  auto emit = [&](const float4& a0, const float4& a1, size_t off) {
+    float v[8] = {fmaf(a0.x, s0.x, h0.x), fmaf(a0.y, s0.y, h0.y), fmaf(a0.z, s0.z, h0.z), fmaf(a0.w, s0.w, h0.w),
+                  fmaf(a1.x, s1.x, h1.x), fmaf(a1.y, s1.y, h1.y), fmaf(a1.z, s1.z, h1.z), fmaf(a1.w, s1.w, h1.w)};
     if (silu) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
     }
     if (OUT_F32) {
-      float* dst = reinterpret_cast<float*>(y) + row * C + c;
+      float* dst = reinterpret_cast<float*>(y) + off;
       *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
     } else {
       uint4 o;
       o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + row * C + c) = o;
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + off) = o;
     }
     if (raw) {
       uint4 o;
       o.x = pack_bf16(a0.x, a0.y); o.y = pack_bf16(a0.z, a0.w); o.z = pack_bf16(a1.x, a1.y); o.w = pack_bf16(a1.z, a1.w);
-      *reinterpret_cast<uint4*>(raw + row * C + c) = o;
+      *reinterpret_cast<uint4*>(raw + off) = o;
     }
+  };
+
+  if (rl >= rps) return;                            // threads beyond rps * c8n (block size rounded up to a warp multiple)
+  int r = r_begin + rl;
+  size_t oo = out_off;
+  for (; r + 3 * rps < r_end; r += 4 * rps) {
+    float4 a0[4], a1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a0[u] = __ldcs(reinterpret_cast<const float4*>(src + u * in_step));
+      a1[u] = __ldcs(reinterpret_cast<const float4*>(src + u * in_step + 4));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(a0[u], a1[u], oo + u * out_step);
+    src += 4 * in_step;
+    oo += 4 * out_step;
   }
+  for (; r < r_end; r += rps) {
+    const float4 a0 = __ldcs(reinterpret_cast<const float4*>(src));
+    const float4 a1 = __ldcs(reinterpret_cast<const float4*>(src + 4));
+    emit(a0, a1, oo);
+    src += in_step;
+    oo += out_step;
+  }
+}
+
+// launch geometry of gn_apply_kernel: block = rps rows x C/8 chunks (rounded up to a warp multiple), blocks per sample
+static inline void gn_apply_geometry(int T, int C, int B, int& threads, int& rows_per_block, int& blocks_per_sample) {
+  const int c8n = C / 8;
+  const int rps = c8n >= 256 ? 1 : 256 / c8n;
+  threads = ((rps * c8n + 31) / 32) * 32;
+  int want = (148 * 12 + B - 1) / B;                  // ~12 blocks per SM in total
+  if (want < 1) want = 1;
+  rows_per_block = (T + want - 1) / want;
+  if (rows_per_block < 4 * rps) rows_per_block = 4 * rps;
+  rows_per_block = ((rows_per_block + rps - 1) / rps) * rps;
+  blocks_per_sample = (T + rows_per_block - 1) / rows_per_block;
 }
 
 // LayerNorm over the last dim, one warp per row, two-pass in registers (exact mean/variance), bf16 out.
@@ -267,7 +320,7 @@ extern "C" int seer_b200_groupnorm(const float* x1, int C1, const float* x2, int
   const int C = C1 + C2;
   SEER_CHECK_ARG(x1 && gamma && beta && workspace && scale_shift && y && B > 0 && T > 0);
   SEER_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && (C2 == 0 || x2) && C % (2 * GN_GROUPS) == 0);
-  SEER_CHECK_ARG(C / 2 <= GN_THREADS * GN_MAX_SLOTS);
+  SEER_CHECK_ARG(C / 2 <= GN_THREADS * GN_MAX_SLOTS && C / 8 <= 512);
   const int tpc = seer_b200_groupnorm_tokens_per_chunk(T);
   const int nchunks = ceil_div(T, tpc);
   float* scale = scale_shift;
@@ -276,13 +329,12 @@ extern "C" int seer_b200_groupnorm(const float* x1, int C1, const float* x2, int
   SEER_LAUNCH_CHECK();
   { cudaError_t le__ = launch_pdl(gn_finalize_kernel, B, GN_GROUPS * 32, 0, stream, workspace, nchunks, C, T, eps, gamma, beta, scale, shift, nullptr); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
-  const size_t total8 = (size_t)B * T * (C / 8);
-  size_t nb = (total8 + 255) / 256; if (nb > (size_t)148 * 16) nb = (size_t)148 * 16;
-  const int blocks = (int)nb;
+  int ga_threads, ga_rows, ga_blocks;
+  gn_apply_geometry(T, C, B, ga_threads, ga_rows, ga_blocks);
   if (y_is_f32)
-    { cudaError_t le__ = launch_pdl(gn_apply_kernel<true>, blocks, 256, 0, stream, x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
+    { cudaError_t le__ = launch_pdl(gn_apply_kernel<true>, dim3(ga_blocks, B), ga_threads, 0, stream, x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
   else
-    { cudaError_t le__ = launch_pdl(gn_apply_kernel<false>, blocks, 256, 0, stream, x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
+    { cudaError_t le__ = launch_pdl(gn_apply_kernel<false>, dim3(ga_blocks, B), ga_threads, 0, stream, x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
@@ -293,19 +345,18 @@ extern "C" int seer_b200_groupnorm_from_stats(const float* x1, int C1, const flo
   cudaStream_t stream = (cudaStream_t)stream_;
   const int C = C1 + C2;
   SEER_CHECK_ARG(x1 && stats1 && gamma && beta && scale_shift && y && B > 0 && T > 0 && T % 32 == 0);
-  SEER_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && (C2 == 0 || (x2 && stats2)) && C % (2 * GN_GROUPS) == 0);
+  SEER_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && (C2 == 0 || (x2 && stats2)) && C % (2 * GN_GROUPS) == 0 && C / 8 <= 512);
   float* scale = scale_shift;
   float* shift = scale_shift + (size_t)B * C;
   { cudaError_t le__ = launch_pdl(gn_finalize_cols_kernel, dim3(GN_GROUPS, B), 256, 0, stream, (const float2*)stats1, C1, (const float2*)stats2, C2, T, eps,
                                                                   gamma, beta, scale, shift); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
-  const size_t total8 = (size_t)B * T * (C / 8);
-  size_t nb = (total8 + 255) / 256; if (nb > (size_t)148 * 16) nb = (size_t)148 * 16;
-  const int blocks = (int)nb;
+  int ga_threads, ga_rows, ga_blocks;
+  gn_apply_geometry(T, C, B, ga_threads, ga_rows, ga_blocks);
   if (y_is_f32)
-    { cudaError_t le__ = launch_pdl(gn_apply_kernel<true>, blocks, 256, 0, stream, x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
+    { cudaError_t le__ = launch_pdl(gn_apply_kernel<true>, dim3(ga_blocks, B), ga_threads, 0, stream, x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
   else
-    { cudaError_t le__ = launch_pdl(gn_apply_kernel<false>, blocks, 256, 0, stream, x1, C1, x2, C2, T, total8, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
+    { cudaError_t le__ = launch_pdl(gn_apply_kernel<false>, dim3(ga_blocks, B), ga_threads, 0, stream, x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

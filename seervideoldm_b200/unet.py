@@ -409,8 +409,8 @@ class SeerUNet(nn.Module):
             return unet_fp32.forward(self, pk, sample, t, context, cond_frame, self._context_kv(pk, context.to(dev)))
         temb = ops.timestep_embedding(t, cfg.block_out_channels[0], float(cfg.freq_shift), cfg.flip_sin_to_cos)
         e1 = ops.small_linear(temb, pk["te1_w"], pk["te1_b"], silu_out=True)
-        emb = ops.small_linear(e1, pk["te2_w"], pk["te2_b"])
-        temb_all = ops.small_linear(emb, pk["temb_w"], pk["temb_b"], silu_in=True)      # all 22 time_emb_proj at once
+        emb = ops.small_linear(e1, pk["te2_w"], pk["te2_b"], silu_out=True)   # = SiLU(emb): emb is consumed only through time_emb_proj(SiLU(emb)), resnet.py:190-192
+        temb_all = ops.small_linear(emb, pk["temb_w"], pk["temb_b"])      # all 22 time_emb_proj at once
         kvs = iter(self._context_kv(pk, context.to(dev)))
 
         # 2. conv_in -> token-major fp32 stream

@@ -213,8 +213,8 @@ def forward(net, pk: dict, sample: torch.Tensor, t: torch.Tensor, context: torch
     B, _, F, H, W = sample.shape
     temb = ops.timestep_embedding(t, cfg.block_out_channels[0], float(cfg.freq_shift), cfg.flip_sin_to_cos)
     e1 = ops.small_linear(temb, pk["te1_w"], pk["te1_b"], silu_out=True)
-    emb = ops.small_linear(e1, pk["te2_w"], pk["te2_b"])
-    temb_all = ops.small_linear(emb, pk["temb_w"], pk["temb_b"], silu_in=True)
+    emb = ops.small_linear(e1, pk["te2_w"], pk["te2_b"], silu_out=True)   # = SiLU(emb): emb is consumed only through time_emb_proj(SiLU(emb)), resnet.py:190-192
+    temb_all = ops.small_linear(emb, pk["temb_w"], pk["temb_b"])
     kvs = iter(kv)
     x = ops.conv_in(sample.contiguous(), pk["conv_in_w"], pk["conv_in_b"])
     h, w = H, W

@@ -413,6 +413,13 @@ def test_conv_in_out():
     eps = ops.conv_out(h, pack_conv_out(wo.cpu()).to(DEV), bo, B, Fr, H, H)
     ref = so.conv_framewise(h.cpu().reshape(B, Fr, H, H, 320).permute(0, 4, 1, 2, 3), wo.cpu(), bo.cpu())
     assert eps.shape == (B, 4, Fr, H, H) and rel(eps, ref) < 1e-5
+    # row-block kernel geometry: one / two pixel groups per half-warp, ragged last group, fewer output channels, 2 chunks
+    for (n_b, n_f, hh, ww, cin, cout) in [(1, 2, 32, 32, 320, 4), (1, 1, 16, 64, 128, 4), (2, 1, 5, 6, 64, 3), (1, 3, 4, 4, 64, 4)]:
+        h = rn(86, n_b * n_f * hh * ww, cin)
+        wo, bo = rn(87, cout, cin, 3, 3, scale=0.05), rn(88, cout)
+        eps = ops.conv_out(h, pack_conv_out(wo.cpu()).to(DEV), bo, n_b, n_f, hh, ww)
+        ref = so.conv_framewise(h.cpu().reshape(n_b, n_f, hh, ww, cin).permute(0, 4, 1, 2, 3), wo.cpu(), bo.cpu())
+        assert eps.shape == ref.shape and rel(eps, ref) < 1e-5, (n_b, n_f, hh, ww, cin, cout)
 
 
 def test_upsample_and_cast():
