@@ -1,4 +1,4 @@
-// tcgen05 flash attention for the d = 80 level of the Seer UNet (16x16 latents at the bench shape, 32x32 at config 5):
+// tcgen05 flash attention for the d = 80 and d = 160 levels of the Seer UNet (16x16 / 8x8 / 4x4 latents at the bench shape):
 // the persistent structure of attention_tc.cu (2 CTAs per SM looping over (problem, query tile) items, S / O in TMEM, lazily
 // raised maximum, packed fp32x2 softmax) with the tile geometry a two-atom head needs:
 //
@@ -9,7 +9,9 @@
 //   * SCTA windows are 4x4 (H = 16) or 8x8 (H = 32): the window partition is a 4-D TMA box {64 ch, ws, ws, frames}.
 //
 // Reference: seer/models/attention.py:310-322, 512-554 (spatial / cross), :632-703 (SCTA), window order :42-53.
-// Selected by seer_b200_attention for head_dim == 80 (SEER_ATTN_TC80=0 falls back to the mma.sync kernel).
+// d = 160 = 64 + 64 + 32: three atoms, 10 exact k-steps, Q 48 KB + K 24 KB + V 24 KB + P 16 KB = 112 KB — two CTAs still share
+// an SM because the 1024-byte alignment slack is cut to the 896 bytes a 128-byte-aligned dynamic smem window can need.
+// Selected by seer_b200_attention for head_dim 80 / 160 (SEER_ATTN_TC80=0 falls back to the mma.sync kernel).
 #include "common.cuh"
 #include "seer_b200.h"
 
@@ -17,12 +19,16 @@ namespace seer {
 
 constexpr int A8_BM = 128;               // queries per tile
 constexpr int A8_BN = 64;                // keys per tile
-constexpr int A8_D = 80;
-constexpr int A8_Q_BYTES = 2 * A8_BM * 128;      // two atoms of 128 rows
-constexpr int A8_KV_BYTES = 2 * A8_BN * 128;     // two atoms of 64 rows
 constexpr int A8_P_BYTES = A8_BM * 128;          // one atom: 64 keys
-constexpr int A8_SMEM = A8_Q_BYTES + 2 * A8_KV_BYTES + A8_P_BYTES + 256 + 1024;
+constexpr int A8_SLACK = 896;                    // dynamic smem starts 128-byte aligned: 1024-alignment costs <= 896 B
 constexpr int A8_THREADS = 192;
+template <int D>
+struct A8Cfg {
+  static constexpr int NA = (D + 63) / 64;               // 64-channel swizzle atoms per row
+  static constexpr int Q_BYTES = NA * A8_BM * 128;
+  static constexpr int KV_BYTES = NA * A8_BN * 128;
+  static constexpr int SMEM = Q_BYTES + 2 * KV_BYTES + A8_P_BYTES + 128 + A8_SLACK;
+};
 
 struct Attn80Params {
   __nv_bfloat16* o;
@@ -62,13 +68,20 @@ __device__ __forceinline__ uint64_t a8_desc_mn(uint32_t smem_addr, uint32_t lbo_
   return d;
 }
 
+template <int D>
 __global__ void __launch_bounds__(A8_THREADS, 2)
 attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const Attn80Params p, const int n_problems, const int nq_tiles) {
   extern __shared__ uint8_t smem_raw[];
+  using C = A8Cfg<D>;
+  constexpr int A8_D = D, A8_Q_BYTES = C::Q_BYTES, A8_KV_BYTES = C::KV_BYTES;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                        // [2 atoms][128 rows][128 B]
-  uint8_t* sK = sQ + A8_Q_BYTES;             // [2 atoms][64 rows][128 B]
+  if (threadIdx.x == 0 && (size_t)(smem - smem_raw) > (size_t)A8_SLACK) {
+    printf("[seer_b200] attention_tc80: dynamic shared memory base is not 128-byte aligned\n");
+    __trap();
+  }
+  uint8_t* sQ = smem;                        // [NA atoms][128 rows][128 B]
+  uint8_t* sK = sQ + A8_Q_BYTES;             // [NA atoms][64 rows][128 B]
   uint8_t* sV = sK + A8_KV_BYTES;
   uint8_t* sP = sV + A8_KV_BYTES;            // [128 rows][128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + A8_P_BYTES);
@@ -116,7 +129,7 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base;           // 64 columns
-  const uint32_t tO = tmem_base + 64;      // 80 columns
+  const uint32_t tO = tmem_base + 64;      // D columns
   pdl_wait();
 
   auto decode = [&](int idx, int& prob, int& qt) {
@@ -145,7 +158,7 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       // one tile = two 64-column atoms; `rows` tile rows, `atom_bytes` bytes per atom
       auto load_tile = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int row0, int L, int atom_bytes) {
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < C::NA; ++a) {
           if (p.mode == SEER_ATTN_SCTA) tma_load_4d(dst + a * atom_bytes, tm, bar, col0 + 64 * a, wx * p.ws, wy * p.ws, b * p.F + row0 / tpf);
           else tma_load_2d(dst + a * atom_bytes, tm, bar, col0 + 64 * a, outer * L + row0);
         }
@@ -173,10 +186,10 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_s = umma_idesc_bf16(A8_BM, A8_BN);          // S = Q K^T : N = 64 keys, K = 80
-    constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(A8_BM, A8_D);       // O = P V   : N = 80, K = 64 keys, V MN-major
-    const uint64_t q_desc0 = umma_desc_sw128(smem_u32(sQ)), q_desc1 = umma_desc_sw128(smem_u32(sQ + A8_BM * 128));
-    const uint64_t k_desc0 = umma_desc_sw128(smem_u32(sK)), k_desc1 = umma_desc_sw128(smem_u32(sK + A8_BN * 128));
+    constexpr uint32_t idesc_s = umma_idesc_bf16(A8_BM, A8_BN);          // S = Q K^T : N = 64 keys, K = D
+    constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(A8_BM, A8_D);       // O = P V   : N = D, K = 64 keys, V MN-major
+    const uint64_t q_desc0 = umma_desc_sw128(smem_u32(sQ));              // atom a: + a * 128 rows * 128 B (in 16-byte units)
+    const uint64_t k_desc0 = umma_desc_sw128(smem_u32(sK));              // atom a: + a * 64 rows * 128 B
     const uint64_t v_desc = a8_desc_mn(smem_u32(sV), A8_BN * 128);
     const uint64_t p_desc = umma_desc_sw128(smem_u32(sP));
     uint32_t it = 0, n = 0;
@@ -186,8 +199,15 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tS, q_desc0 + (uint64_t)(k * 2), k_desc0 + (uint64_t)(k * 2), idesc_s, k != 0);
-        umma_bf16(tS, q_desc1, k_desc1, idesc_s, 1);                      // channels 64..79
+        for (int a = 0; a < C::NA; ++a) {
+          constexpr int full = 4;
+          const int steps = (D - 64 * a) >= 64 ? full : (D - 64 * a) / 16;   // the last atom holds D % 64 live channels
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < steps)
+              umma_bf16(tS, q_desc0 + (uint64_t)(a * (A8_BM * 128 / 16) + k * 2), k_desc0 + (uint64_t)(a * (A8_BN * 128 / 16) + k * 2),
+                        idesc_s, (a | k) != 0);
+        }
         umma_commit(s_full);
         umma_commit(k_empty);
         if (last) umma_commit(q_empty);
@@ -272,7 +292,7 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             l_run *= corr;
             m_run = m_new;
 #pragma unroll
-            for (int c = 0; c < 5; ++c) {
+            for (int c = 0; c < D / 16; ++c) {
               uint32_t o[16];
               tmem_ld_32x16(tO + lane_addr + c * 16, o);
               tmem_ld_wait();
@@ -337,39 +357,44 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (lane == 0) mbar_arrive(p_full);
       }
 
-      // ---- item epilogue ----
+      // ---- item epilogue: O out of TMEM in 80-column pieces (register budget), handed back to the MMA warp after the last ----
       mbar_wait(o_full, (it - 1) & 1);
       tc_fence_after();
-      uint32_t v0[32], v1[32], v2[16];
-      tmem_ld_32x32(tO + lane_addr, v0);
-      tmem_ld_32x32(tO + lane_addr + 32, v1);
-      tmem_ld_32x16(tO + lane_addr + 64, v2);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);
-      if (qi < p.Lq) {
-        size_t grow;
-        if (p.mode == SEER_ATTN_SCTA) {
-          const int b = outer / p.nwin, win = outer - b * p.nwin;
-          const int wy = win / p.nwx, wx = win - wy * p.nwx;
-          const int f = qi / tpf, rem = qi - f * tpf;
-          const int iy = rem / p.ws, ix = rem - iy * p.ws;
-          grow = ((size_t)(b * p.F + f) * p.H + wy * p.ws + iy) * p.W + wx * p.ws + ix;
-        } else {
-          grow = (size_t)outer * p.Lq + qi;
-        }
-        const float inv = 1.0f / l_run;
-        __nv_bfloat16* dst = p.o + grow * p.ldo + head * A8_D;
+      size_t grow = 0;
+      if (p.mode == SEER_ATTN_SCTA) {
+        const int b = outer / p.nwin, win = outer - b * p.nwin;
+        const int wy = win / p.nwx, wx = win - wy * p.nwx;
+        const int f = qi / tpf, rem = qi - f * tpf;
+        const int iy = rem / p.ws, ix = rem - iy * p.ws;
+        grow = ((size_t)(b * p.F + f) * p.H + wy * p.ws + iy) * p.W + wx * p.ws + ix;
+      } else {
+        grow = (size_t)outer * p.Lq + qi;
+      }
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* dst = p.o + grow * p.ldo + head * A8_D;
 #pragma unroll
-        for (int g = 0; g < A8_D / 8; ++g) {
-          const uint32_t* src = g < 4 ? &v0[8 * g] : (g < 8 ? &v1[8 * (g - 4)] : &v2[8 * (g - 8)]);
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
-          o.y = pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
-          o.z = pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
-          o.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
-          *reinterpret_cast<uint4*>(dst + 8 * g) = o;
+      for (int piece = 0; piece < D / 80; ++piece) {
+        uint32_t v0[32], v1[32], v2[16];
+        tmem_ld_32x32(tO + lane_addr + piece * 80, v0);
+        tmem_ld_32x32(tO + lane_addr + piece * 80 + 32, v1);
+        tmem_ld_32x16(tO + lane_addr + piece * 80 + 64, v2);
+        tmem_ld_wait();
+        if (piece == D / 80 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_free);
+        }
+        if (qi < p.Lq) {
+#pragma unroll
+          for (int g = 0; g < 10; ++g) {
+            const uint32_t* src = g < 4 ? &v0[8 * g] : (g < 8 ? &v1[8 * (g - 4)] : &v2[8 * (g - 8)]);
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+            o.y = pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+            o.z = pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+            o.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+            *reinterpret_cast<uint4*>(dst + piece * 80 + 8 * g) = o;
+          }
         }
       }
     }
@@ -413,14 +438,44 @@ static int a8_map_4d(CUtensorMap* tm, const void* base, uint64_t n_frames, uint6
 }
 
 // Returns SEER_EUNSUPPORTED when the geometry is not covered (caller falls back to the mma.sync kernel).
+template <int D>
+static int a8_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Attn80Params& p, int n_problems,
+                     int nq_tiles, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc80_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, A8Cfg<D>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  int dev = 0, nsm = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0)
+    nsm = 148;
+  const long total = (long)n_problems * nq_tiles;
+  const int grid = (int)(total < 2L * nsm ? total : 2L * nsm);
+  cudaError_t le = launch_pdl(attention_tc80_kernel<D>, dim3(grid), dim3(A8_THREADS), (size_t)A8Cfg<D>::SMEM, stream, tq, tk, tv, p,
+                              n_problems, nq_tiles);
+  if (le != cudaSuccess) return (int)le;
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
 int attention_tc80_launch(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int mode,
-                          int heads, int n_outer, int Lq, int Lk, int F, int H, int W, void* stream) {
+                          int heads, int head_dim, int n_outer, int Lq, int Lk, int F, int H, int W, void* stream) {
+  if (head_dim != 80 && head_dim != 160) return SEER_EUNSUPPORTED;
+  const int A8_D = head_dim;
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return SEER_EUNSUPPORTED;
   if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) % 16) return SEER_EUNSUPPORTED;
   Attn80Params p{};
   int n_problems, nq_tiles;
-  if (mode == SEER_ATTN_SCTA) {
-    if (F <= 0 || H <= 4 || W <= 4) return SEER_EUNSUPPORTED;
+  if (mode == SEER_ATTN_SCTA && H <= 4) {
+    // no windows at the 4x4 level (attention.py:661): one causal sequence of F*H*W plain token rows per clip
+    if (F <= 0 || H <= 0 || W <= 0) return SEER_EUNSUPPORTED;
+    mode = SEER_ATTN_SPATIAL;
+    Lq = Lk = F * H * W;
+    p.Lq = Lq; p.Lk = Lk; p.causal = 1; p.nwin = 1; p.nwx = 1; p.ws = 1;
+    n_problems = n_outer * heads;
+  } else if (mode == SEER_ATTN_SCTA) {
+    if (F <= 0 || W <= 4) return SEER_EUNSUPPORTED;
     const int ws = (H / 8) >= 4 ? 8 : 4;                 // window rule of attention.py:30-33,661-668
     const int tpf = ws * ws;
     if (H % ws || W % ws) return SEER_EUNSUPPORTED;
@@ -453,22 +508,8 @@ int attention_tc80_launch(const void* q, int ldq, const void* k, int ldk, const 
     if ((rc = a8_map_2d(&tk, k, (uint64_t)n_outer * Lk, C, ldk, A8_BN))) return rc;
     if ((rc = a8_map_2d(&tv, v, (uint64_t)n_outer * Lk, C, ldv, A8_BN))) return rc;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc80_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A8_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
-  }
-  int dev = 0, nsm = 148;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0)
-    nsm = 148;
-  const long total = (long)n_problems * nq_tiles;
-  const int grid = (int)(total < 2L * nsm ? total : 2L * nsm);
-  cudaError_t le = launch_pdl(attention_tc80_kernel, dim3(grid), dim3(A8_THREADS), (size_t)A8_SMEM, (cudaStream_t)stream, tq, tk, tv, p,
-                              n_problems, nq_tiles);
-  if (le != cudaSuccess) return (int)le;
-  SEER_LAUNCH_CHECK();
-  return SEER_OK;
+  return head_dim == 80 ? a8_launch<80>(tq, tk, tv, p, n_problems, nq_tiles, (cudaStream_t)stream)
+                        : a8_launch<160>(tq, tk, tv, p, n_problems, nq_tiles, (cudaStream_t)stream);
 }
 
 }  // namespace seer

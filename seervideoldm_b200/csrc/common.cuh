@@ -68,9 +68,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-// attention_tc80.cu (tcgen05 flash attention, head dim 80); SEER_EUNSUPPORTED = geometry not covered, use the mma.sync kernel
+// attention_tc80.cu (tcgen05 flash attention, head dims 80 and 160); SEER_EUNSUPPORTED = geometry not covered, use the mma.sync kernel
 int attention_tc80_launch(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int mode,
-                          int heads, int n_outer, int Lq, int Lk, int F, int H, int W, void* stream);
+                          int heads, int head_dim, int n_outer, int Lq, int Lk, int F, int H, int W, void* stream);
 
 // ---- generic -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -284,7 +284,7 @@ def _attn_ref(q, k, v, causal):
 
 
 @pytest.mark.parametrize("d,frames,L", [(40, 3, 1024), (80, 2, 256), (160, 5, 64), (160, 3, 16), (40, 1, 100), (40, 5, 256),
-                                        (40, 2, 4096), (80, 1, 1024), (80, 3, 100), (80, 40, 256), (80, 2, 64)])
+                                        (40, 2, 4096), (80, 1, 1024), (80, 3, 100), (80, 40, 256), (80, 2, 64), (160, 40, 64), (160, 2, 256)])
 def test_attention_spatial(d, frames, L):
     heads = 8
     C = heads * d
@@ -328,7 +328,7 @@ def test_attention_tc_lazy_rescale(mode):
     assert rel(out.float(), ref) < 8e-3
 
 
-@pytest.mark.parametrize("d,frames,L", [(40, 3, 1024), (80, 2, 256), (160, 4, 16), (80, 3, 100), (80, 40, 1024)])
+@pytest.mark.parametrize("d,frames,L", [(40, 3, 1024), (80, 2, 256), (160, 4, 16), (80, 3, 100), (80, 40, 1024), (160, 40, 64)])
 def test_attention_cross_77(d, frames, L):
     heads, Lk = 8, 77
     C = heads * d
@@ -344,7 +344,7 @@ def test_attention_cross_77(d, frames, L):
 
 @pytest.mark.parametrize("d,B,Fr,H", [(40, 2, 3, 32), (80, 1, 4, 16), (160, 2, 3, 8), (160, 2, 5, 4), (40, 1, 2, 64),
                                       (40, 2, 4, 32), (40, 1, 16, 32), (80, 2, 16, 16), (80, 1, 12, 16), (80, 1, 4, 32),
-                                      (80, 3, 8, 16), (80, 1, 3, 16)])
+                                      (80, 3, 8, 16), (80, 1, 3, 16), (160, 2, 16, 8), (160, 1, 12, 8), (160, 2, 16, 4), (160, 1, 7, 4)])
 def test_attention_scta(d, B, Fr, H):
     heads = 8
     C = heads * d
