@@ -135,6 +135,11 @@ int seer_b200_small_linear(const float* in, int ldi, const float* W, const float
 /* conv_in (3x3, 4 -> Cout, fp32): x (B,4,F,H,W) -> out [B*F*H*W, Cout].  unet_3d_condition.py:94,311. */
 int seer_b200_conv_in(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int F, int H, int W,
                       int Cout, void* stream);
+/* conv_in that also emits col_stats [B*F*H*W/32][Cout][2] (sum, sumsq per 32-row slab and channel, the layout of
+ * SeerGemmDesc::col_stats) so the GroupNorms consuming its output (first ResNet norm1, last up-block skip concat) skip their
+ * statistics pass; col_stats may be NULL.  Needs B*F*H*W % 32 == 0 when given. */
+int seer_b200_conv_in_stats(const float* x, const float* w, const float* bias, float* out, float* col_stats, int B, int Cin, int F,
+                            int H, int W, int Cout, void* stream);
 /* conv_out (3x3, Cin -> <=4, fp32): x [B*F*H*W, Cin] -> out (B,Cout,F,H,W); w_packed[co][tap][Cin].  :205,370. */
 int seer_b200_conv_out(const float* x, const float* w_packed, const float* bias, float* out, int B, int Cin, int F, int H,
                        int W, int Cout, void* stream);

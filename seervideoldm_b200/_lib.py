@@ -57,6 +57,7 @@ SIGNATURES = {
     "seer_b200_timestep_embedding": (_i, [_vp, _vp, _i, _i, _f, _i, _vp]),
     "seer_b200_small_linear": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "seer_b200_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "seer_b200_conv_in_stats": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "seer_b200_conv_out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "seer_b200_upsample2x_to_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "seer_b200_im2col3x3_to_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),

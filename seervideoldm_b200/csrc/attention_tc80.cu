@@ -307,10 +307,15 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const float msc = m_run * sl2;
         float sum = 0.f;
         if (need_mask) {
+          const int k_vis = __reduce_max_sync(0xffffffffu, k_hi);   // no row of this warp sees keys >= k_vis
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
+              if (c * 32 + 8 * g >= k_vis) {                         // warp-uniform: P = 0, no exp2
+                sts128u(prow + (((c * 4 + g) ^ (r & 7)) << 4), make_uint4(0, 0, 0, 0));
+                continue;
+              }
               float e[8];
 #pragma unroll
               for (int k = 0; k < 8; ++k) {

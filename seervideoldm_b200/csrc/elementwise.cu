@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------------
 constexpr int CI_PIX = 64;     // pixels per block: the 36 weights a thread keeps in registers are fetched once per 64 pixels
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                               float* __restrict__ out, int B, int Cin, int F, int H, int W, int Cout) {
+                               float* __restrict__ out, int B, int Cin, int F, int H, int W, int Cout, float2* __restrict__ col_stats) {
   pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   extern __shared__ __align__(16) float s_in[];  // [CI_PIX][Cin*9]
   constexpr int K = 36;  // Cin == 4 (checked on the host)
@@ -142,6 +142,7 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
 #pragma unroll
     for (int k = 0; k < K; ++k) wr[k] = w[(size_t)co * K + k];  // weight (Cout, Cin, 3, 3) is already [co][c*9 + tap]
     const float bz = bias[co];
+    float ssum = 0.f, ssq = 0.f;             // per-(32-pixel slab, channel) sums for the GroupNorms that consume this tensor
     for (int pi = 0; pi < CI_PIX; ++pi) {
       if (p0 + pi >= npix) break;
       float acc = bz;
@@ -155,6 +156,12 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
         acc += v.w * wr[4 * k4 + 3];
       }
       out[(p0 + pi) * Cout + co] = acc;
+      ssum += acc;
+      ssq = fmaf(acc, acc, ssq);
+      if (col_stats && ((pi & 31) == 31)) {
+        col_stats[((p0 + pi) >> 5) * Cout + co] = make_float2(ssum, ssq);     // same layout as SeerGemmDesc::col_stats
+        ssum = ssq = 0.f;
+      }
     }
   }
 }
@@ -388,11 +395,17 @@ extern "C" int seer_b200_small_linear(const float* in, int ldi, const float* W, 
 
 extern "C" int seer_b200_conv_in(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int F, int H,
                                  int W, int Cout, void* stream) {
+  return seer_b200_conv_in_stats(x, w, bias, out, nullptr, B, Cin, F, H, W, Cout, stream);
+}
+
+extern "C" int seer_b200_conv_in_stats(const float* x, const float* w, const float* bias, float* out, float* col_stats, int B, int Cin,
+                                       int F, int H, int W, int Cout, void* stream) {
   SEER_CHECK_ARG(x && w && bias && out && Cin == 4);
   const size_t npix = (size_t)B * F * H * W;
+  SEER_CHECK_ARG(!col_stats || npix % 32 == 0);
   const int threads = Cout >= 320 ? 320 : ((Cout + 31) / 32) * 32;
   { cudaError_t le__ = launch_pdl(conv_in_kernel, (unsigned)((npix + CI_PIX - 1) / CI_PIX), threads, CI_PIX * Cin * 9 * sizeof(float), (cudaStream_t)stream, 
-      x, w, bias, out, B, Cin, F, H, W, Cout); if (le__ != cudaSuccess) return (int)le__; }
+      x, w, bias, out, B, Cin, F, H, W, Cout, (float2*)col_stats); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

@@ -357,18 +357,21 @@ def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
 
 
 @_timed_op
-def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
-    """x:(B,4,F,H,W) fp32 -> [B*F*H*W, Cout] fp32."""
+def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, col_stats: bool = False):
+    """x:(B,4,F,H,W) fp32 -> [B*F*H*W, Cout] fp32.  col_stats=True also returns the [M/32, Cout, 2] per-slab channel
+    (sum, sumsq) the consuming GroupNorms need (None when M % 32 != 0): returns (out, stats)."""
     _req(x, torch.float32, "x", 5)
     if not x.is_contiguous():
         raise ValueError("x must be contiguous (B,C,F,H,W)")
     B, Cin, F, H, W = x.shape
     Cout = w.shape[0]
-    out = torch.empty((B * F * H * W, Cout), device=x.device, dtype=torch.float32)
-    rc = _lib.lib().seer_b200_conv_in(_p(x), _p(w), _p(bias), _p(out), B, Cin, F, H, W, Cout, _stream())
+    M = B * F * H * W
+    out = torch.empty((M, Cout), device=x.device, dtype=torch.float32)
+    st = torch.empty((M // 32, Cout, 2), device=x.device, dtype=torch.float32) if (col_stats and M % 32 == 0) else None
+    rc = _lib.lib().seer_b200_conv_in_stats(_p(x), _p(w), _p(bias), _p(out), _p(st), B, Cin, F, H, W, Cout, _stream())
     _lib.check(rc, "conv_in")
     _count()
-    return out
+    return (out, st) if col_stats else out
 
 
 @_timed_op

@@ -414,7 +414,7 @@ class SeerUNet(nn.Module):
         kvs = iter(self._context_kv(pk, context.to(dev)))
 
         # 2. conv_in -> token-major fp32 stream
-        x = (ops.conv_in(sample.contiguous(), pk["conv_in_w"], pk["conv_in_b"]), None)     # (tensor, GroupNorm col_stats)
+        x = ops.conv_in(sample.contiguous(), pk["conv_in_w"], pk["conv_in_b"], col_stats=True)   # (tensor, GroupNorm col_stats)
         h, w = H, W
         skips: List[tuple] = [x]
         n = len(cfg.block_out_channels)

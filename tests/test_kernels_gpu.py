@@ -408,6 +408,11 @@ def test_conv_in_out():
     out = ops.conv_in(x, w.reshape(320, 36).contiguous(), b)
     ref = so.conv_framewise(x.cpu(), w.cpu(), b.cpu()).permute(0, 2, 3, 4, 1).reshape(-1, 320)
     assert rel(out, ref) < 1e-5
+    # column statistics for the consuming GroupNorms: per 32-row slab (sum, sumsq), same layout as the GEMM's col_stats
+    out2, st = ops.conv_in(x, w.reshape(320, 36).contiguous(), b, col_stats=True)
+    assert torch.equal(out2, out) and st.shape == (out.shape[0] // 32, 320, 2)
+    slabs = out.reshape(-1, 32, 320).double()
+    assert rel(st[..., 0], slabs.sum(1)) < 1e-5 and rel(st[..., 1], (slabs * slabs).sum(1)) < 1e-5
     h = rn(83, B * Fr * H * H, 320)
     wo, bo = rn(84, 4, 320, 3, 3, scale=0.02), rn(85, 4)
     from seervideoldm_b200.packing import pack_conv_out
