@@ -784,7 +784,8 @@ extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ld
                                    int mode, int heads, int head_dim, int n_outer, int Lq, int Lk, int F, int H, int W,
                                    void* stream) {
   SEER_CHECK_ARG(q && k && v && o && heads > 0 && n_outer > 0);
-  if ((head_dim == 80 || (head_dim == 160 && env_flag("SEER_ATTN_TC160", 1))) && mode != SEER_ATTN_FRAME && env_flag("SEER_ATTN_TC80", 1)) {
+  if ((head_dim == 80 || (head_dim == 160 && env_flag("SEER_ATTN_TC160", 1)) || (head_dim == 40 && env_flag("SEER_ATTN_D40_BN64", 0))) &&
+      mode != SEER_ATTN_FRAME && env_flag("SEER_ATTN_TC80", 1)) {
     const int rc80 = attention_tc80_launch(q, ldq, k, ldk, v, ldv, o, ldo, mode, heads, head_dim, n_outer, Lq, Lk, F, H, W, stream);
     if (rc80 != SEER_EUNSUPPORTED) return rc80;
   }

@@ -28,6 +28,12 @@ struct A8Cfg {
   static constexpr int Q_BYTES = NA * A8_BM * 128;
   static constexpr int KV_BYTES = NA * A8_BN * 128;
   static constexpr int SMEM = Q_BYTES + 2 * KV_BYTES + A8_P_BYTES + 128 + A8_SLACK;
+  static constexpr int DP = (D + 15) / 16 * 16;         // contraction extent of Q K^T in whole k-steps (d = 40 -> 48)
+  static constexpr bool QZ = (D % 16) != 0;             // Q needs zero-filled pad columns (fetched through a [rows, heads, d] map)
+  static constexpr int DO = DP;                         // N of the P V MMA / O columns in TMEM
+  static constexpr int TMEM_COLS = (64 + DO) <= 128 ? 128 : 256;
+  static constexpr int MIN_CTAS = D <= 48 ? 3 : 2;      // d = 40: 48 KB smem, 128 TMEM columns -> three CTAs per SM
+  static constexpr int MAXREG = 65536 / (MIN_CTAS * A8_THREADS) / 8 * 8;   // 112 / 168
 };
 
 struct Attn80Params {
@@ -69,7 +75,7 @@ __device__ __forceinline__ uint64_t a8_desc_mn(uint32_t smem_addr, uint32_t lbo_
 }
 
 template <int D>
-__global__ void __launch_bounds__(A8_THREADS, 2)
+__global__ void __launch_bounds__(A8_THREADS) __maxnreg__(A8Cfg<D>::MAXREG)
 attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const Attn80Params p, const int n_problems, const int nq_tiles) {
   extern __shared__ uint8_t smem_raw[];
@@ -121,7 +127,7 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -166,7 +172,14 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_wait(q_empty, (n & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(q_full, A8_Q_BYTES);
-        load_tile(sQ, &tmQ, q_full, qt * A8_BM, p.Lq, A8_BM * 128);
+        if constexpr (C::QZ) {
+          // d not a multiple of 16: Q through the [rows, heads, d] view, columns d..63 arrive as zeros, so the garbage
+          // K reads in the padded k-step contributes nothing (K / V keep full-row maps: partial-extent boxes are ~3x slower)
+          if (p.mode == SEER_ATTN_SCTA) tma_load_5d(sQ, &tmQ, q_full, 0, head, wx * p.ws, wy * p.ws, b * p.F + (qt * A8_BM) / tpf);
+          else tma_load_3d(sQ, &tmQ, q_full, 0, head, outer * p.Lq + qt * A8_BM);
+        } else {
+          load_tile(sQ, &tmQ, q_full, qt * A8_BM, p.Lq, A8_BM * 128);
+        }
       }
       __syncwarp();
       for (int j = 0; j < n_kv; ++j, ++it) {
@@ -187,7 +200,7 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_s = umma_idesc_bf16(A8_BM, A8_BN);          // S = Q K^T : N = 64 keys, K = D
-    constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(A8_BM, A8_D);       // O = P V   : N = D, K = 64 keys, V MN-major
+    constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(A8_BM, C::DO);      // O = P V   : N = D (padded to 16), K = 64 keys, V MN-major
     const uint64_t q_desc0 = umma_desc_sw128(smem_u32(sQ));              // atom a: + a * 128 rows * 128 B (in 16-byte units)
     const uint64_t k_desc0 = umma_desc_sw128(smem_u32(sK));              // atom a: + a * 64 rows * 128 B
     const uint64_t v_desc = a8_desc_mn(smem_u32(sV), A8_BN * 128);
@@ -201,7 +214,7 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
         for (int a = 0; a < C::NA; ++a) {
           constexpr int full = 4;
-          const int steps = (D - 64 * a) >= 64 ? full : (D - 64 * a) / 16;   // the last atom holds D % 64 live channels
+          const int steps = (C::DP - 64 * a) >= 64 ? full : (C::DP - 64 * a) / 16;   // the last atom holds DP % 64 live channels
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             if (k < steps)
@@ -292,7 +305,7 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             l_run *= corr;
             m_run = m_new;
 #pragma unroll
-            for (int c = 0; c < D / 16; ++c) {
+            for (int c = 0; c < C::DO / 16; ++c) {
               uint32_t o[16];
               tmem_ld_32x16(tO + lane_addr + c * 16, o);
               tmem_ld_wait();
@@ -377,28 +390,35 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       const float inv = 1.0f / l_run;
       __nv_bfloat16* dst = p.o + grow * p.ldo + head * A8_D;
+      constexpr int PW = D % 80 == 0 ? 80 : D;          // columns per piece (D = 40: one piece of 40)
 #pragma unroll
-      for (int piece = 0; piece < D / 80; ++piece) {
+      for (int piece = 0; piece < D / PW; ++piece) {
         uint32_t v0[32], v1[32], v2[16];
-        tmem_ld_32x32(tO + lane_addr + piece * 80, v0);
-        tmem_ld_32x32(tO + lane_addr + piece * 80 + 32, v1);
-        tmem_ld_32x16(tO + lane_addr + piece * 80 + 64, v2);
+        tmem_ld_32x32(tO + lane_addr + piece * PW, v0);
+        if constexpr (PW == 80) {
+          tmem_ld_32x32(tO + lane_addr + piece * PW + 32, v1);
+          tmem_ld_32x16(tO + lane_addr + piece * PW + 64, v2);
+        } else {
+          tmem_ld_32x16(tO + lane_addr + piece * PW + 32, v2);      // D = 40: columns 32..47 (40..47 are padding)
+        }
         tmem_ld_wait();
-        if (piece == D / 80 - 1) {
+        if (piece == D / PW - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(o_free);
         }
         if (qi < p.Lq) {
 #pragma unroll
-          for (int g = 0; g < 10; ++g) {
-            const uint32_t* src = g < 4 ? &v0[8 * g] : (g < 8 ? &v1[8 * (g - 4)] : &v2[8 * (g - 8)]);
+          for (int g = 0; g < PW / 8; ++g) {
+            const uint32_t* src;
+            if constexpr (PW == 80) src = g < 4 ? &v0[8 * g] : (g < 8 ? &v1[8 * (g - 4)] : &v2[8 * (g - 8)]);
+            else src = g < 4 ? &v0[8 * g] : &v2[8 * (g - 4)];
             uint4 o;
             o.x = pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
             o.y = pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
             o.z = pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
             o.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
-            *reinterpret_cast<uint4*>(dst + piece * 80 + 8 * g) = o;
+            *reinterpret_cast<uint4*>(dst + piece * PW + 8 * g) = o;
           }
         }
       }
@@ -410,7 +430,7 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -442,6 +462,33 @@ static int a8_map_4d(CUtensorMap* tm, const void* base, uint64_t n_frames, uint6
   return r == CUDA_SUCCESS ? SEER_OK : SEER_EINVAL;
 }
 
+// head-split Q maps with zero fill beyond the head ([rows, heads, d] / [frames, H, W, heads, d] views), for d % 16 != 0
+static int a8_map_heads_3d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t heads, uint64_t d, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn80 enc = a8_encode_fn();
+  if (!enc) return SEER_ENODRIVER;
+  cuuint64_t dims[3] = {d, heads, rows};
+  cuuint64_t strides[2] = {d * 2, ld * 2};
+  cuuint32_t box[3] = {64, 1, box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SEER_OK : SEER_EUNSUPPORTED;
+}
+static int a8_map_heads_5d(CUtensorMap* tm, const void* base, uint64_t n_frames, uint64_t H, uint64_t W, uint64_t heads, uint64_t d,
+                           uint64_t ld, uint32_t ws, uint32_t box_frames) {
+  EncodeTiledFn80 enc = a8_encode_fn();
+  if (!enc) return SEER_ENODRIVER;
+  cuuint64_t dims[5] = {d, heads, W, H, n_frames};
+  cuuint64_t strides[4] = {d * 2, ld * 2, W * ld * 2, H * W * ld * 2};
+  cuuint32_t box[5] = {64, 1, ws, ws, box_frames};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SEER_OK : SEER_EUNSUPPORTED;
+}
+
 // Returns SEER_EUNSUPPORTED when the geometry is not covered (caller falls back to the mma.sync kernel).
 template <int D>
 static int a8_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Attn80Params& p, int n_problems,
@@ -456,7 +503,8 @@ static int a8_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0)
     nsm = 148;
   const long total = (long)n_problems * nq_tiles;
-  const int grid = (int)(total < 2L * nsm ? total : 2L * nsm);
+  const long resident = (long)A8Cfg<D>::MIN_CTAS * nsm;
+  const int grid = (int)(total < resident ? total : resident);
   cudaError_t le = launch_pdl(attention_tc80_kernel<D>, dim3(grid), dim3(A8_THREADS), (size_t)A8Cfg<D>::SMEM, stream, tq, tk, tv, p,
                               n_problems, nq_tiles);
   if (le != cudaSuccess) return (int)le;
@@ -466,7 +514,7 @@ static int a8_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
 
 int attention_tc80_launch(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int mode,
                           int heads, int head_dim, int n_outer, int Lq, int Lk, int F, int H, int W, void* stream) {
-  if (head_dim != 80 && head_dim != 160) return SEER_EUNSUPPORTED;
+  if (head_dim != 40 && head_dim != 80 && head_dim != 160) return SEER_EUNSUPPORTED;
   const int A8_D = head_dim;
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return SEER_EUNSUPPORTED;
   if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) % 16) return SEER_EUNSUPPORTED;
@@ -505,14 +553,17 @@ int attention_tc80_launch(const void* q, int ldq, const void* k, int ldk, const 
   if (mode == SEER_ATTN_SCTA) {
     const uint64_t nf = (uint64_t)n_outer * F;
     const uint32_t tpf = p.ws * p.ws;
-    if ((rc = a8_map_4d(&tq, q, nf, H, W, C, ldq, p.ws, A8_BM / tpf))) return rc;
+    if (head_dim % 16) { if ((rc = a8_map_heads_5d(&tq, q, nf, H, W, heads, head_dim, ldq, p.ws, A8_BM / tpf))) return rc; }
+    else if ((rc = a8_map_4d(&tq, q, nf, H, W, C, ldq, p.ws, A8_BM / tpf))) return rc;
     if ((rc = a8_map_4d(&tk, k, nf, H, W, C, ldk, p.ws, A8_BN / tpf))) return rc;
     if ((rc = a8_map_4d(&tv, v, nf, H, W, C, ldv, p.ws, A8_BN / tpf))) return rc;
   } else {
-    if ((rc = a8_map_2d(&tq, q, (uint64_t)n_outer * Lq, C, ldq, A8_BM))) return rc;
+    if (head_dim % 16) { if ((rc = a8_map_heads_3d(&tq, q, (uint64_t)n_outer * Lq, heads, head_dim, ldq, A8_BM))) return rc; }
+    else if ((rc = a8_map_2d(&tq, q, (uint64_t)n_outer * Lq, C, ldq, A8_BM))) return rc;
     if ((rc = a8_map_2d(&tk, k, (uint64_t)n_outer * Lk, C, ldk, A8_BN))) return rc;
     if ((rc = a8_map_2d(&tv, v, (uint64_t)n_outer * Lk, C, ldv, A8_BN))) return rc;
   }
+  if (head_dim == 40) return a8_launch<40>(tq, tk, tv, p, n_problems, nq_tiles, (cudaStream_t)stream);
   return head_dim == 80 ? a8_launch<80>(tq, tk, tv, p, n_problems, nq_tiles, (cudaStream_t)stream)
                         : a8_launch<160>(tq, tk, tv, p, n_problems, nq_tiles, (cudaStream_t)stream);
 }
