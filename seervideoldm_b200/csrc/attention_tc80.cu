@@ -27,13 +27,18 @@ struct A8Cfg {
   static constexpr int NA = (D + 63) / 64;               // 64-channel swizzle atoms per row
   static constexpr int Q_BYTES = NA * A8_BM * 128;
   static constexpr int KV_BYTES = NA * A8_BN * 128;
-  static constexpr int SMEM = Q_BYTES + 2 * KV_BYTES + A8_P_BYTES + 128 + A8_SLACK;
+  // P double-buffered (softmax of tile t+1 writes P while P V of tile t still reads the other buffer) when two CTAs still fit an SM
+  static constexpr int NP = (Q_BYTES + 2 * KV_BYTES + 2 * A8_P_BYTES + 128 + A8_SLACK) <= 115712 ? 2 : 1;
+  static constexpr int SMEM = Q_BYTES + 2 * KV_BYTES + NP * A8_P_BYTES + 128 + A8_SLACK;
   static constexpr int DP = (D + 15) / 16 * 16;         // contraction extent of Q K^T in whole k-steps (d = 40 -> 48)
   static constexpr bool QZ = (D % 16) != 0;             // Q needs zero-filled pad columns (fetched through a [rows, heads, d] map)
   static constexpr int DO = DP;                         // N of the P V MMA / O columns in TMEM
   static constexpr int TMEM_COLS = (64 + DO) <= 128 ? 128 : 256;
-  static constexpr int MIN_CTAS = D <= 48 ? 3 : 2;      // d = 40: 48 KB smem, 128 TMEM columns -> three CTAs per SM
-  static constexpr int MAXREG = 65536 / (MIN_CTAS * A8_THREADS) / 8 * 8;   // 112 / 168
+  static constexpr int MIN_CTAS = 2;
+  static constexpr int MAXREG = 65536 / (MIN_CTAS * A8_THREADS) / 8 * 8;   // 168
+  // S of tile t+1 pulled into a second register set in the middle of the exp2 pass of tile t (hides the tcgen05.ld latency
+  // and hands S back to the MMA warp earlier); needs 64 more registers: only where the epilogue does not need them
+  static constexpr bool PRE = D <= 48;
 };
 
 struct Attn80Params {
@@ -90,7 +95,7 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint8_t* sK = sQ + A8_Q_BYTES;             // [NA atoms][64 rows][128 B]
   uint8_t* sV = sK + A8_KV_BYTES;
   uint8_t* sP = sV + A8_KV_BYTES;            // [128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + A8_P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + C::NP * A8_P_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
   uint64_t* k_full = bars + 2;
@@ -100,9 +105,9 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* s_full = bars + 6;
   uint64_t* s_free = bars + 7;     // count 4
   uint64_t* p_full = bars + 8;     // count 4
-  uint64_t* o_full = bars + 9;
-  uint64_t* o_free = bars + 10;    // count 4
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* o_full = bars + 9;     // [2] P V of tile t has completed: barrier t & 1 (a wait two tiles back stays an unambiguous parity wait)
+  uint64_t* o_free = bars + 11;    // count 4
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = n_problems * nq_tiles;
@@ -122,7 +127,8 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_init(s_full, 1);
     mbar_init(s_free, 4);
     mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
     mbar_init(o_free, 4);
     fence_barrier_init();
   }
@@ -243,8 +249,9 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < A8_BN / 16; ++k)    // A: 16 keys = 32 B inside P's atom; B: 16 keys = two 8-row groups = 2048 B
-            umma_bf16(tO, p_desc + (uint64_t)(k * 2), v_desc + (uint64_t)(k * 128), idesc_o, (j | k) != 0);
-          umma_commit(o_full);
+            umma_bf16(tO, p_desc + (uint64_t)((C::NP == 2 ? ph : 0) * (A8_P_BYTES >> 4) + k * 2), v_desc + (uint64_t)(k * 128), idesc_o,
+                      (j | k) != 0);
+          umma_commit(&o_full[ph]);
           umma_commit(v_empty);
         }
         __syncwarp();
@@ -256,7 +263,6 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float sl2 = p.scale_log2;
-    uint8_t* const prow = sP + r * 128;
     uint32_t it = 0, n = 0;
     for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n) {
       int prob, qt;
@@ -266,20 +272,30 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const int qi = qt * A8_BM + r;
       float m_run = -INFINITY, l_run = 0.f;
 
+      bool have_next = false;                  // v_next already holds S of the coming tile (and S was handed back)
+      uint32_t v_next[2][32];
       for (int j = 0; j < n_kv; ++j, ++it) {
         const uint32_t ph = it & 1;
         const int kv0 = j * A8_BN;
         const bool need_mask = (kv0 + A8_BN > p.Lk) || (p.causal && kv0 + A8_BN - 1 > qt * A8_BM);
         const int k_hi = min(p.Lk - kv0, p.causal ? qi - kv0 + 1 : A8_BN);   // keys [0, k_hi) visible (may be <= 0)
-        mbar_wait(s_full, ph);
-        tc_fence_after();
         uint32_t v[2][32];
-        tmem_ld_32x32(tS + lane_addr, v[0]);
-        tmem_ld_32x32(tS + lane_addr + 32, v[1]);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_free);
+        if (C::PRE && have_next) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[c][k] = v_next[c][k];
+          have_next = false;
+        } else {
+          mbar_wait(s_full, ph);
+          tc_fence_after();
+          tmem_ld_32x32(tS + lane_addr, v[0]);
+          tmem_ld_32x32(tS + lane_addr + 32, v[1]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free);
+        }
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (need_mask) {
 #pragma unroll
@@ -294,31 +310,34 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             for (int k = 0; k < 32; ++k) mx4[2 * c + (k & 1)] = fmaxf(mx4[2 * c + (k & 1)], __uint_as_float(v[c][k]));
         }
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // the P buffer this tile writes was last read by P V of tile it-NP
+        if (C::NP == 2) { if (it >= 2) mbar_wait(&o_full[ph], ((it >> 1) - 1) & 1); }
+        else if (it >= 1) mbar_wait(&o_full[ph ^ 1], ((it - 1) >> 1) & 1);
         if (j == 0) {
           m_run = mx;                          // tile 0 always holds key 0, visible to every valid row
-        } else {
-          mbar_wait(o_full, ph ^ 1);           // P V of the previous tile done: P may be overwritten, O may be rescaled
-          if (__any_sync(0xffffffffu, (mx - m_run) * sl2 > 8.0f)) {
-            tc_fence_after();
-            const float m_new = fmaxf(m_run, mx);
-            const float corr = exp2f((m_run - m_new) * sl2);
-            l_run *= corr;
-            m_run = m_new;
+        } else if (__any_sync(0xffffffffu, (mx - m_run) * sl2 > 8.0f)) {
+          mbar_wait(&o_full[ph ^ 1], ((it - 1) >> 1) & 1);     // O may only be rescaled once P V of the previous tile is done
+          tc_fence_after();
+          const float m_new = fmaxf(m_run, mx);
+          const float corr = exp2f((m_run - m_new) * sl2);
+          l_run *= corr;
+          m_run = m_new;
 #pragma unroll
-            for (int c = 0; c < C::DO / 16; ++c) {
-              uint32_t o[16];
-              tmem_ld_32x16(tO + lane_addr + c * 16, o);
-              tmem_ld_wait();
+          for (int c = 0; c < C::DO / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x16(tO + lane_addr + c * 16, o);
+            tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-              tmem_st_32x16(tO + lane_addr + c * 16, o);
-            }
-            tmem_st_wait();
-            tc_fence_before();
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+            tmem_st_32x16(tO + lane_addr + c * 16, o);
           }
+          tmem_st_wait();
+          tc_fence_before();
         }
         const float msc = m_run * sl2;
+        uint8_t* const prow = sP + (C::NP == 2 ? ph : 0) * A8_P_BYTES + r * 128;
         float sum = 0.f;
+        bool pre_issued = false;
         if (need_mask) {
           const int k_vis = __reduce_max_sync(0xffffffffu, k_hi);   // no row of this warp sees keys >= k_vis
 #pragma unroll
@@ -349,6 +368,16 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           f2_t sum2[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
+            if (C::PRE && c == 1 && j + 1 < n_kv) {
+              // half of the exp2 pass is done: if S of the next tile is already in TMEM, start pulling it into v_next now
+              const bool ready = __shfl_sync(0xffffffffu, (int)mbar_test_wait(s_full, ph ^ 1), 0) != 0;
+              if (ready) {
+                tc_fence_after();
+                tmem_ld_32x32(tS + lane_addr, v_next[0]);
+                tmem_ld_32x32(tS + lane_addr + 32, v_next[1]);
+                pre_issued = true;
+              }
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint32_t o[4];
@@ -369,14 +398,22 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           sum = s0 + s1;
         }
         l_run += sum;
+        if (C::PRE && pre_issued) {                // S of the next tile has landed in v_next: hand S back to the MMA warp
+          tmem_ld_wait_regs(v_next[0]);
+          reg_fence32(v_next[1]);
+          have_next = true;
+        }
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
+        if (lane == 0) {
+          if (C::PRE && pre_issued) mbar_arrive(s_free);
+          mbar_arrive(p_full);
+        }
       }
 
       // ---- item epilogue: O out of TMEM in 80-column pieces (register budget), handed back to the MMA warp after the last ----
-      mbar_wait(o_full, (it - 1) & 1);
+      mbar_wait(&o_full[(it - 1) & 1], ((it - 1) >> 1) & 1);
       tc_fence_after();
       size_t grow = 0;
       if (p.mode == SEER_ATTN_SCTA) {

@@ -124,24 +124,6 @@ __device__ __forceinline__ f2_t f2_gelu_erf(f2_t x) {
 
 // tcgen05.wait::ld that also names the destination registers of the outstanding load, so no use of them can be
 // scheduled above the wait (the load is issued a whole chunk earlier than it is consumed)
-__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.wait::ld.sync.aligned;"
-      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-        "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
-        "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
-        "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-      :
-      : "memory");
-}
-__device__ __forceinline__ void reg_fence32(uint32_t (&v)[32]) {
-  asm volatile(""
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
-                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
-                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]));
-}
-
 // f[k] (pairs of one 32-column accumulator chunk) = rstd * (acc - mean * colsum) + bias | acc + bias | acc.
 // BSRC: 0 none, 1 shared memory (staged slice), 2 global row pointer (rows of the warp span two bias rows — rare)
 template <bool LN, int BSRC>
