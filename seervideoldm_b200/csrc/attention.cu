@@ -251,12 +251,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
 template <int D>
 static int launch_attention(const AttnParams& p, int n_problems, cudaStream_t stream) {
   using C = AttnCfg<D>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
-  }
+  static SmemAttrOnce smem_attr_attr_done;
+  { cudaError_t e = smem_attr_attr_done.ensure(attention_kernel<D>, C::SMEM_BYTES); if (e != cudaSuccess) return (int)e; }
   dim3 grid(ceil_div(p.Lq, ATT_BM), n_problems);
   { cudaError_t le__ = launch_pdl(attention_kernel<D>, grid, ATT_THREADS, C::SMEM_BYTES, stream, p); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();

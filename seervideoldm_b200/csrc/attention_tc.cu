@@ -837,12 +837,8 @@ extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ld
            at_map_2d(&tk, k, (uint64_t)n_outer * Lk, C, ldk) == SEER_OK && at_map_2d(&tv, v, (uint64_t)n_outer * Lk, C, ldv) == SEER_OK;
     }
     if (ok) {
-      static bool attr_done_p = false;
-      if (!attr_done_p) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc_persist_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr_done_p = true;
-      }
+      static SmemAttrOnce smem_attr_attr_done_p;
+  { cudaError_t e = smem_attr_attr_done_p.ensure(attention_tc_persist_kernel<40>, AT_SMEM); if (e != cudaSuccess) return (int)e; }
       int dev = 0, nsm = 148;
       if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0)
         nsm = 148;
@@ -870,12 +866,8 @@ extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ld
     if ((rc = at_map_2d(&tk, k, (uint64_t)n_outer * Lk, C, ldk))) return rc;
     if ((rc = at_map_2d(&tv, v, (uint64_t)n_outer * Lk, C, ldv))) return rc;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
-  }
+  static SmemAttrOnce smem_attr_attr_done;
+  { cudaError_t e = smem_attr_attr_done.ensure(attention_tc_kernel<40>, AT_SMEM); if (e != cudaSuccess) return (int)e; }
   dim3 grid(nq_tiles, n_problems);
   { cudaError_t le__ = launch_pdl(attention_tc_kernel<40>, grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream, tq, tk, tv, p); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();

@@ -530,12 +530,8 @@ static int a8_map_heads_5d(CUtensorMap* tm, const void* base, uint64_t n_frames,
 template <int D>
 static int a8_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Attn80Params& p, int n_problems,
                      int nq_tiles, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc80_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, A8Cfg<D>::SMEM);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
-  }
+  static SmemAttrOnce smem_attr_attr_done;
+  { cudaError_t e = smem_attr_attr_done.ensure(attention_tc80_kernel<D>, A8Cfg<D>::SMEM); if (e != cudaSuccess) return (int)e; }
   int dev = 0, nsm = 148;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0)
     nsm = 148;

@@ -72,6 +72,23 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 int attention_tc80_launch(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int mode,
                           int heads, int head_dim, int n_outer, int Lq, int Lk, int F, int H, int W, void* stream);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remember it per device, not per process (a process may
+// drive several GPUs; the library itself keeps no other per-device state).
+struct SmemAttrOnce {
+  int bytes[64] = {};
+  template <typename K>
+  cudaError_t ensure(K kernel, int want) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    dev &= 63;
+    if (bytes[dev] >= want) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e == cudaSuccess) bytes[dev] = want;
+    return e;
+  }
+};
+
 // ---- generic -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

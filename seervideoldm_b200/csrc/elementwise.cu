@@ -414,12 +414,8 @@ extern "C" int seer_b200_conv_out(const float* x, const float* w_packed, const f
                                   int H, int W, int Cout, void* stream) {
   SEER_CHECK_ARG(x && w_packed && bias && out && Cout <= 4 && Cin % CO_CK == 0 && W >= 1 && W <= 64);
   const size_t smem = (size_t)(3 * W * CO_CK + 9 * 4 * CO_CK) * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    smem_set = smem;
-  }
+  static SmemAttrOnce smem_attr;
+  if (smem > 48 * 1024) { cudaError_t e = smem_attr.ensure(conv_out_kernel, (int)smem); if (e != cudaSuccess) return (int)e; }
   { cudaError_t le__ = launch_pdl(conv_out_kernel, (unsigned)(B * F * H), CO_THREADS, smem, (cudaStream_t)stream, x, w_packed, bias, out, B, Cin, F, H, W, Cout); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;

@@ -273,12 +273,8 @@ __global__ void __launch_bounds__(A32_WARPS * 32) attention_f32_kernel(const Att
 template <int D>
 static int launch_attention_f32(const Attn32Params& p, int n_problems, cudaStream_t stream) {
   constexpr int SMEM = (A32_WARPS * D + 2 * A32_KT * (D + 4)) * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attention_f32_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
-  }
+  static SmemAttrOnce smem_attr_attr_done;
+  { cudaError_t e = smem_attr_attr_done.ensure(attention_f32_kernel<D>, SMEM); if (e != cudaSuccess) return (int)e; }
   dim3 grid(ceil_div(p.Lq, A32_WARPS), n_problems);
   attention_f32_kernel<D><<<grid, A32_WARPS * 32, SMEM, stream>>>(p);
   SEER_LAUNCH_CHECK();

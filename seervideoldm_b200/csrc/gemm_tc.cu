@@ -415,12 +415,8 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
 
 template <int BN, int CG>
 static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, const Plan& pl, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
-  }
+  static SmemAttrOnce smem_attr;
+  { cudaError_t e = smem_attr.ensure(gemm_tc_kernel<BN, CG>, SMEM_LIMIT); if (e != cudaSuccess) return (int)e; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(pl.grid);
   cfg.blockDim = dim3(64 + 32 * pl.nepi);
