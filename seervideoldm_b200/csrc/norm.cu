@@ -124,21 +124,36 @@ __global__ void __launch_bounds__(256) gn_finalize_cols_kernel(const float2* __r
   const int cpg = C / GN_GROUPS;
   const int g = blockIdx.x, b = blockIdx.y;
   const int slabs = T / 32;
-  const int total = slabs * cpg;
-  // per-thread partial in compensated fp32 (Kahan: the fp64 pipe of this part runs at 1/64 rate and two DADDs per
-  // element made this kernel 10 us long); threads are combined in double below
+  // thread = (slab stripe, channel of the group): fixed channel, slabs strided by the number of stripes, four independent
+  // loads in flight per thread and no division in the loop (the kernel is latency-bound: 20 MB of statistics at most).
+  // Per-thread partials in compensated fp32 (Kahan) — the fp64 pipe of this part runs at 1/64 rate; threads are combined in
+  // double below.
   float sf = 0.f, qf = 0.f, sc_ = 0.f, qc_ = 0.f;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int sl = i / cpg;
-    const int c = g * cpg + (i - sl * cpg);
-    const size_t slab = (size_t)b * slabs + sl;
-    const float2 v = c < C1 ? st1[slab * C1 + c] : st2[slab * C2 + (c - C1)];
+  auto kahan = [&](float2 v) {
     const float ys = __fsub_rn(v.x, sc_), ts = __fadd_rn(sf, ys);
     sc_ = __fsub_rn(__fsub_rn(ts, sf), ys);
     sf = ts;
     const float yq = __fsub_rn(v.y, qc_), tq = __fadd_rn(qf, yq);
     qc_ = __fsub_rn(__fsub_rn(tq, qf), yq);
     qf = tq;
+  };
+  const int stripes = blockDim.x / cpg;
+  const int cl = threadIdx.x % cpg, st = threadIdx.x / cpg;
+  if (st < stripes) {
+    const int c = g * cpg + cl;
+    const bool first = c < C1;
+    const float2* base = first ? st1 + c : st2 + (c - C1);
+    const size_t ld = first ? C1 : C2;
+    const size_t slab0 = (size_t)b * slabs;
+    int sl = st;
+    for (; sl + 3 * stripes < slabs; sl += 4 * stripes) {
+      const float2 v0 = __ldg(base + (slab0 + sl) * ld);
+      const float2 v1 = __ldg(base + (slab0 + sl + stripes) * ld);
+      const float2 v2 = __ldg(base + (slab0 + sl + 2 * stripes) * ld);
+      const float2 v3 = __ldg(base + (slab0 + sl + 3 * stripes) * ld);
+      kahan(v0); kahan(v1); kahan(v2); kahan(v3);
+    }
+    for (; sl < slabs; sl += stripes) kahan(__ldg(base + (slab0 + sl) * ld));
   }
   double s = (double)sf - (double)sc_, q = (double)qf - (double)qc_;
   __shared__ double sh[2][8];
