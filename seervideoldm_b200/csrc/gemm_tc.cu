@@ -331,7 +331,11 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   const double bytes = (double)d.M * (d.X ? d.Cin + d.K2 : Kd) * 2 + (double)N * Kd * 2 +
                        (double)d.M * n_out * ((d.out_f32 ? 4 : 0) + (d.out_bf16 ? 2 : 0) + (d.residual ? (d.residual_bf16 ? 2 : 4) : 0));
   const double t_mem = bytes / 5.5e12, t_mma = 2.0 * d.M * N * Kd / 1.6e15;
-  int cg = (d.M > BM && t_mma > t_mem) ? 2 : 1;
+  // (measured again after the epilogue rewrite, profiles/r1_gemm_sweep_cg.txt: pairs are now faster or equal on every shape of
+  // the UNet, HBM-bound ones included — L1 proj_in 88 -> 70 us, L0 FF-out 270 -> 245 us, L2 attention-out 72 -> 66 us — so the
+  // roofline estimate no longer selects single CTAs; t_mma / t_mem are kept for the planner's other decisions)
+  int cg = d.M > BM ? 2 : 1;
+  if (env_int("SEER_GEMM_CG", 0) == 3) cg = (d.M > BM && t_mma > t_mem) ? 2 : 1;     // A/B hook: the former roofline rule
   // B-stationary candidates (K <= 320, measured: proj_in 168 -> 118 us, qkv 412 -> 286 us at M = 262144; K = 640 and the
   // epilogue-bound GEGLU launches ran slower with it): a pair halves the resident panel
   const bool bstat_ok = d.M > BM && Kd <= 320.0 && !d.geglu && env_int("SEER_GEMM_BSTAT", 1);
