@@ -39,13 +39,25 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qk, int ld, int M, int t
     float sn, cs;
     sincosf(ang, &sn, &cs);
     __nv_bfloat16* base = qk + (size_t)row * ld + 2 * j;
-    for (int h = 0; h < heads; ++h) {
+    // all loads of a batch of heads first, then the stores: the read-modify-write chain per (head, q/k) serialised 16 global
+    // round trips per thread (ncu: 63 us at 42 % DRAM throughput, issue slots 20 % busy — latency-bound)
+    constexpr int HB = 8;
+    for (int h0 = 0; h0 < heads; h0 += HB) {
+      uint32_t raw[HB][2];
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        uint32_t* ptr = reinterpret_cast<uint32_t*>(base + (w ? k_col : q_col) + h * head_dim);
-        const float2 x = unpack_bf16(*ptr);
-        *ptr = pack_bf16(x.x * cs - x.y * sn, x.y * cs + x.x * sn);
-      }
+      for (int hh = 0; hh < HB; ++hh)
+#pragma unroll
+        for (int w = 0; w < 2; ++w)
+          if (h0 + hh < heads) raw[hh][w] = *reinterpret_cast<const uint32_t*>(base + (w ? k_col : q_col) + (h0 + hh) * head_dim);
+#pragma unroll
+      for (int hh = 0; hh < HB; ++hh)
+#pragma unroll
+        for (int w = 0; w < 2; ++w)
+          if (h0 + hh < heads) {
+            const float2 x = unpack_bf16(raw[hh][w]);
+            *reinterpret_cast<uint32_t*>(base + (w ? k_col : q_col) + (h0 + hh) * head_dim) =
+                pack_bf16(x.x * cs - x.y * sn, x.y * cs + x.x * sn);
+          }
     }
   }
 }
