@@ -27,8 +27,10 @@ struct A8Cfg {
   static constexpr int NA = (D + 63) / 64;               // 64-channel swizzle atoms per row
   static constexpr int Q_BYTES = NA * A8_BM * 128;
   static constexpr int KV_BYTES = NA * A8_BN * 128;
-  // P double-buffered (softmax of tile t+1 writes P while P V of tile t still reads the other buffer) when two CTAs still fit an SM
-  static constexpr int NP = (Q_BYTES + 2 * KV_BYTES + 2 * A8_P_BYTES + 128 + A8_SLACK) <= 115712 ? 2 : 1;
+  // P is single-buffered.  (Double-buffering it lets the softmax warps run two tiles ahead of the P V MMA, and then p_full —
+  // one barrier, waited on by parity — can complete twice before the MMA warp looks: the MMA warp waits for a phase that has
+  // already been overtaken and the CTA deadlocks.  Seen on 2-GPU runs; it bought nothing either: 119.5 vs 117 us at d = 80.)
+  static constexpr int NP = 1;
   static constexpr int SMEM = Q_BYTES + 2 * KV_BYTES + NP * A8_P_BYTES + 128 + A8_SLACK;
   static constexpr int DP = (D + 15) / 16 * 16;         // contraction extent of Q K^T in whole k-steps (d = 40 -> 48)
   static constexpr bool QZ = (D % 16) != 0;             // Q needs zero-filled pad columns (fetched through a [rows, heads, d] map)
