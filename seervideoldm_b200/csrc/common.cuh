@@ -217,7 +217,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (clock64() - t0 > 20000000000LL) {
       printf("[seer_b200] mbarrier wait timeout (grid %d block %d,%d threads %d thread %d barrier smem+0x%x parity %u)\n", gridDim.x,
              blockIdx.x, blockIdx.y, blockDim.x, threadIdx.x, smem_u32(bar), parity);
       __trap();
