@@ -120,6 +120,19 @@ class SeerUNet(nn.Module):
         self._kv_key = None
         return out
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, **kwargs):
+        """`SeerUNet.from_pretrained(sd15_dir, subfolder="unet", revision=..., low_cpu_mem_usage=False)` as the
+        reference's scripts call it (inference.py:82-87): local `config.json` + `diffusion_pytorch_model.{bin,safetensors}`;
+        a 2-D Stable Diffusion UNet inflates (its keys are a subset of the schema, the temporal attentions keep their
+        initialisation).  See checkpoint.py."""
+        from .checkpoint import unet_from_pretrained
+        return unet_from_pretrained(cls, pretrained_model_name_or_path, subfolder=subfolder, **kwargs)
+
+    def save_pretrained(self, save_directory, safe_serialization: bool = False, **kwargs):
+        from .checkpoint import unet_save_pretrained
+        unet_save_pretrained(self, save_directory, safe_serialization=safe_serialization)
+
     @property
     def dtype(self) -> torch.dtype:
         return self.conv_in.weight.dtype
