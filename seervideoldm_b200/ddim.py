@@ -73,6 +73,7 @@ class DDIMSampler(object):
         self.schedule = schedule
         self.device = torch.device(device) if not isinstance(device, torch.device) else device
         self.use_cuda_graph = kwargs.get("use_cuda_graph", True)
+        self._branch = None            # (process group, branch index) while the CFG-branch split is enabled
         self._graphs = {}
 
     def register_buffer(self, name, attr):
@@ -165,6 +166,19 @@ class DDIMSampler(object):
                 intermediates["pred_x0"].append(pred_x0)
         return img, intermediates
 
+    def enable_cfg_branch_split(self, group, branch: int) -> "DDIMSampler":
+        """Optional latency mode (parallel.py): this rank evaluates only CFG branch `branch` (0 = unconditional,
+        1 = conditional) and exchanges the noise prediction with its partner in `group` every step.  Both ranks must
+        sample the same clips with the same seeds; eta > 0 additionally needs identical CUDA RNG states."""
+        if branch not in (0, 1):
+            raise ValueError("branch must be 0 (unconditional) or 1 (conditional)")
+        self._branch = (group, branch)
+        return self
+
+    def disable_cfg_branch_split(self) -> "DDIMSampler":
+        self._branch = None
+        return self
+
     def _evaluate(self, unet, x_in, t_in, c_in, cond_frame):
         """One UNet evaluation; replayed from a CUDA graph when the model is a seer_b200 SeerUNet."""
         if not (self.use_cuda_graph and isinstance(unet, SeerUNet) and x_in.is_cuda):
@@ -195,6 +209,10 @@ class DDIMSampler(object):
         use_cfg = not (uc is None or unconditional_guidance_scale == 1.)
         if not use_cfg:
             eps = self._evaluate(unet, x_cat, t, c, 0)                        # ddim_video.py:196 passes no cond_frame
+        elif self._branch is not None:
+            from .parallel import gather_cfg_branches
+            group, branch = self._branch
+            eps = gather_cfg_branches(self._evaluate(unet, x_cat, t, uc if branch == 0 else c, cond_frames), group)
         elif uc.shape[2] == c.shape[2]:
             c_in = self._cfg_context(uc, c)
             eps = self._evaluate(unet, torch.cat([x_cat] * 2), torch.cat([t] * 2), c_in, cond_frames)

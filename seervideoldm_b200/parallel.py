@@ -4,10 +4,19 @@ The reference's only parallelism is data parallel over the dataloader (inference
 `accelerator.gather` after sampling (utils/ddim_sampling_utils.py:9-12,60-63); there is no collective inside
 the denoising step, so none is invented here: rank r owns clips r, r+W, r+2W, ... and the
 only exchange is `all_gather_into_tensor` of (n_local, 4, F2, H, W) fp32 latents over NCCL/NVLink (gloo on CPU).
+
+Optional latency mode — CFG-branch split (BASELINE.json north_star "sharding independent clips and CFG branches",
+SURVEY §8e row 2): when there are more GPUs than clips, ranks pair up (2p, 2p+1); the even rank evaluates the
+unconditional branch, the odd rank the conditional one (UNet batch b instead of 2b), and the two exchange the noise
+prediction once per DDIM step (`gather_cfg_branches`: one all-gather of (b,4,F,H,W) fp32 inside the pair, 262 KB per
+clip at the bench shape) before both apply the fused CFG+DDIM update redundantly.  This is the one place a collective sits
+inside the step, so it is off by default; it never changes results: a clip evaluated at UNet batch b is bit-identical
+to the same clip inside the [uc; c] batch of 2b (batch independence, tests/test_unet_gpu.py), hence branch-split latents
+equal single-GPU latents bit for bit (profiles/r1_cfg_branch_split_2gpu.txt).
 """
 from __future__ import annotations
 
-from typing import Callable, List, Sequence
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -36,13 +45,61 @@ def gather_latents(local: torch.Tensor, n_clips: int, rank: int, world: int) -> 
     return res
 
 
-def sample_sharded(sample_fn: Callable[[Sequence[int]], torch.Tensor], n_clips: int, batch: int) -> torch.Tensor:
-    """Run `sample_fn(clip_ids) -> (len(ids), ...) latents` over this rank's clips in local batches, then all-gather."""
+def sample_sharded(sample_fn: Callable[[Sequence[int]], torch.Tensor], n_clips: int, batch: int,
+                   cfg_branch_split: bool = False) -> torch.Tensor:
+    """Run `sample_fn(clip_ids) -> (len(ids), ...) latents` over this rank's clips in local batches, then all-gather.
+    With `cfg_branch_split` the unit of ownership is the rank PAIR (both ranks of a pair run `sample_fn` on the same
+    clips, their sampler exchanging CFG branches per step) and the even rank's copy is the one kept."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
-    mine = shard_clips(n_clips, rank, world)
+    if cfg_branch_split:
+        if world % 2:
+            raise ValueError("cfg_branch_split needs an even number of ranks")
+        owner, owners = rank // 2, world // 2
+    else:
+        owner, owners = rank, world
+    mine = shard_clips(n_clips, owner, owners)
     outs = [sample_fn(mine[i: i + batch]) for i in range(0, len(mine), batch)]
     local = torch.cat(outs) if outs else None
     if local is None:
-        raise ValueError("rank has no clips: n_clips must be >= world size")
-    return gather_latents(local, n_clips, rank, world)
+        raise ValueError("rank has no clips: n_clips must be >= the number of owners (ranks, or rank pairs)")
+    if not cfg_branch_split:
+        return gather_latents(local, n_clips, rank, world)
+    per = (n_clips + owners - 1) // owners
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad)
+    out = out.reshape(world, per, *local.shape[1:])
+    res = torch.empty((n_clips,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for o in range(owners):
+        ids = shard_clips(n_clips, o, owners)
+        res[ids] = out[2 * o, : len(ids)]
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CFG-branch split (optional latency mode)
+# ---------------------------------------------------------------------------------------------------------------------
+def cfg_branch_group(rank: Optional[int] = None, world: Optional[int] = None) -> Tuple["dist.ProcessGroup", int]:
+    """Pair ranks (2p, 2p+1) -> (this rank's pair group, branch index): 0 = unconditional, 1 = conditional — the
+    order of the reference's `[uc; c]` batch (ddim_video.py:199-203).  Collective: every rank must call it."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    if world % 2:
+        raise ValueError("CFG-branch split needs an even number of ranks")
+    mine = None
+    for p in range(world // 2):
+        g = dist.new_group(ranks=[2 * p, 2 * p + 1])         # new_group is collective over the whole world
+        if rank // 2 == p:
+            mine = g
+    return mine, rank % 2
+
+
+def gather_cfg_branches(eps_local: torch.Tensor, group) -> torch.Tensor:
+    """(b, C, F, H, W) noise prediction of this rank's branch -> (2b, C, F, H, W) in `[uc; c]` order on both ranks of
+    the pair (all-gather concatenates along dim 0 in group-rank order = branch order)."""
+    eps_local = eps_local.contiguous()
+    out = torch.empty((2 * eps_local.shape[0],) + tuple(eps_local.shape[1:]), dtype=eps_local.dtype, device=eps_local.device)
+    dist.all_gather_into_tensor(out, eps_local, group=group)
+    return out

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from seervideoldm_b200.parallel import gather_latents, sample_sharded, shard_clips
+from seervideoldm_b200.parallel import cfg_branch_group, gather_cfg_branches, gather_latents, sample_sharded, shard_clips
 
 
 def test_shard_clips_partition():
@@ -54,3 +54,55 @@ def test_sharded_sampling_gathers_in_clip_order(n_clips, batch):
 def test_single_process_passthrough():
     x = torch.randn(3, 4)
     assert gather_latents(x, 3, 0, 1) is x
+
+
+def _branch_worker(rank, world, port, n_clips, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    group, branch = cfg_branch_group()
+    seen = []
+
+    def sample_fn(ids):
+        # stand-in for the DDIM loop: each rank "evaluates" only its CFG branch, the pair exchanges per step
+        x = torch.stack([torch.full((4, 2, 2, 2), float(i)) for i in ids])
+        for step in range(3):
+            eps_local = x * (step + 1) + (100.0 if branch == 1 else 0.0)           # branch 1 = conditional
+            eps = gather_cfg_branches(eps_local, group)
+            e_uc, e_c = eps.chunk(2)                                                # the reference's [uc; c] order
+            seen.append((torch.equal(e_uc, x * (step + 1)), torch.equal(e_c, x * (step + 1) + 100.0)))
+            x = x + (e_c - e_uc) / 100.0                                            # both ranks apply the same update
+        return x
+
+    out = sample_sharded(sample_fn, n_clips, 8, cfg_branch_split=True)
+    q.put((rank, branch, out, seen))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_clips", [(2, 1), (4, 3)])
+def test_cfg_branch_split_pairs_exchange_in_uc_c_order(world, n_clips):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_branch_worker, args=(r, world, port, n_clips, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = torch.stack([torch.full((4, 2, 2, 2), float(i) + 3.0) for i in range(n_clips)])
+    for rank, branch, out, seen in res:
+        assert branch == rank % 2
+        assert torch.equal(out, want)                         # every rank: all clips, global order
+        assert seen and all(a and b for a, b in seen)         # gathered eps is [uc; c] on both ranks of each pair
+
+
+def test_cfg_branch_split_argument_checks():
+    from seervideoldm_b200.ddim import DDIMSampler
+    with pytest.raises(ValueError, match="even number"):
+        cfg_branch_group(rank=0, world=3)
+    s = DDIMSampler("cpu")
+    with pytest.raises(ValueError, match="branch must be"):
+        s.enable_cfg_branch_split(None, 2)
+    assert s.enable_cfg_branch_split(None, 1)._branch == (None, 1) and s.disable_cfg_branch_split()._branch is None
