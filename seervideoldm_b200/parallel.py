@@ -10,9 +10,11 @@ SURVEY §8e row 2): when there are more GPUs than clips, ranks pair up (2p, 2p+1
 unconditional branch, the odd rank the conditional one (UNet batch b instead of 2b), and the two exchange the noise
 prediction once per DDIM step (`gather_cfg_branches`: one all-gather of (b,4,F,H,W) fp32 inside the pair, 262 KB per
 clip at the bench shape) before both apply the fused CFG+DDIM update redundantly.  This is the one place a collective sits
-inside the step, so it is off by default; it never changes results: a clip evaluated at UNet batch b is bit-identical
-to the same clip inside the [uc; c] batch of 2b (batch independence, tests/test_unet_gpu.py), hence branch-split latents
-equal single-GPU latents bit for bit (profiles/r1_cfg_branch_split_2gpu.txt).
+inside the step, so it is off by default.  Both ranks of a pair end with bit-identical latents.  Against the single-GPU
+`[uc; c]` batch the latents agree to bf16 rounding noise, not bit for bit (measured rel-L2 6.0e-3 after 31 steps at 16
+frames — the size of the bf16-vs-fp32 distance, 5.4e-3; budget 5e-2; `profiles/r1_cfg_branch_split_2gpu.txt`).  Batch independence IS
+bit-exact at the small test shape (tests/test_unet_gpu.py); at the full shape the LayerNorm row statistics a GEMM emits are
+split into a tile-plan-dependent number of partials, which moves mean / rstd by one fp32 ulp; measured latency gain 1.48x (16 frames) / 1.31x (12 frames).
 """
 from __future__ import annotations
 
