@@ -162,3 +162,34 @@ def test_fstext_module_mirrors_reference_api():
     q = m._query_tokens(1, 77).view(12, 77, 768)
     idx = (torch.arange(12) * 16 // 12)
     assert torch.equal(q, (sd["learnable_query"] + sd["pos_embed"][:, :, :77])[0, idx])
+
+
+def test_c_host_compiles_against_the_header_and_links_the_library(tmp_path):
+    """The boundary is a C ABI: a plain C99 host includes include/seer_b200.h, links libseer_b200.so and calls the entry
+    points that need no GPU (version string, descriptor size, argument validation -> SEER_EINVAL)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    _lib.build(verbose=False)
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "seer_b200.h"
+int main(void) {
+  SeerGemmDesc d;
+  memset(&d, 0, sizeof d);
+  if ((int)sizeof d != seer_b200_gemm_desc_size()) { printf("desc size %d vs %d\n", (int)sizeof d, seer_b200_gemm_desc_size()); return 2; }
+  int rc = seer_b200_gemm_ex(&d, 0);                 /* all-zero descriptor: rejected before any CUDA call */
+  int rc2 = seer_b200_gemm_ex(0, 0);
+  printf("%s rc=%d rc2=%d\n", seer_b200_version(), rc, rc2);
+  return (rc < 0 && rc2 < 0) ? 0 : 3;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = os.path.join(ROOT, "seervideoldm_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lseer_b200", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "rc=-1" in out and "rc2=-1" in out and out.split()[0]
