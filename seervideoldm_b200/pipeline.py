@@ -19,10 +19,18 @@ def ddim_sample_latents(sampler, unet, shape, c, start_code, x0_emb, ddim_steps=
 
 
 @torch.no_grad()
-def ddim_sample(sampler, unet, vae, shape, c, start_code, x0_emb, ddim_steps=10, scale=1.0, uc=None):
-    samples = ddim_sample_latents(sampler, unet, shape, c, start_code, x0_emb, ddim_steps=ddim_steps, scale=scale, uc=uc)
+def decode_latents(vae, samples):
+    """Second half of the reference's `ddim_sample` (ddim_sampling_utils.py:37-41): `(n c f h w) -> ((n f) c h w)`, divide by the
+    SD latent scale 0.18215, `vae.decode(z).sample`, back to `(n c f h w)`, map [-1, 1] -> [0, 1] and clamp.  `vae` is the
+    caller's AutoencoderKL (any object with `.decode(z).sample`)."""
     n, ch, f, h, w = samples.shape
-    z = samples.permute(0, 2, 1, 3, 4).reshape(n * f, ch, h, w) * (1 / 0.18215)
+    z = 1 / 0.18215 * samples.permute(0, 2, 1, 3, 4).reshape(n * f, ch, h, w)
     x = vae.decode(z).sample
     x = x.reshape(n, f, *x.shape[1:]).permute(0, 2, 1, 3, 4)
     return torch.clamp((x + 1.0) / 2.0, min=0.0, max=1.0)
+
+
+@torch.no_grad()
+def ddim_sample(sampler, unet, vae, shape, c, start_code, x0_emb, ddim_steps=10, scale=1.0, uc=None):
+    samples = ddim_sample_latents(sampler, unet, shape, c, start_code, x0_emb, ddim_steps=ddim_steps, scale=scale, uc=uc)
+    return decode_latents(vae, samples)

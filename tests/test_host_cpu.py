@@ -193,3 +193,37 @@ int main(void) {
                     "-L", libdir, "-lseer_b200", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert "rc=-1" in out and "rc2=-1" in out and out.split()[0]
+
+
+def test_decode_latents_matches_the_reference_expressions():
+    """ddim_sampling_utils.py:37-41 restated with einops on a stub VAE: frame-major flattening, 1/0.18215 scale, clamp."""
+    from types import SimpleNamespace
+    from einops import rearrange
+    from seervideoldm_b200.pipeline import ddim_sample, decode_latents
+
+    class StubVAE:                                           # per-image, so frame order mistakes change the result
+        def decode(self, z):
+            self.seen = z
+            img = torch.nn.functional.interpolate(z[:, :3] * 0.3 + z[:, 3:4] * torch.arange(z.shape[0]).reshape(-1, 1, 1, 1) * 0.01,
+                                                  scale_factor=8, mode="nearest")
+            return SimpleNamespace(sample=img)
+
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(2, 4, 5, 4, 4, generator=g)
+    vae = StubVAE()
+    got = decode_latents(vae, lat)
+    z = 1 / 0.18215 * rearrange(lat, "n c f h w -> (n f) c h w")
+    want = torch.clamp((rearrange(StubVAE().decode(z).sample, "(n f) c h w -> n c f h w", f=5) + 1.0) / 2.0, min=0.0, max=1.0)
+    assert torch.equal(vae.seen, z) and got.shape == (2, 3, 5, 32, 32) and torch.equal(got, want)
+    assert float(got.min()) >= 0.0 and float(got.max()) <= 1.0 and float((got == 0).float().mean()) > 0     # the clamp is active
+
+    class StubSampler:                                       # ddim_sample = sampler.sample(...) + decode, arguments as the reference passes them
+        def sample(self, **kw):
+            self.kw = kw
+            return lat, {}
+
+    smp = StubSampler()
+    out = ddim_sample(smp, "unet", vae, (2, 4, 5, 4, 4), "c", "xT", "x0", ddim_steps=30, scale=1.0, uc="uc")
+    assert torch.equal(out, want)
+    assert smp.kw["unconditional_conditioning"] is None and smp.kw["S"] == 30 and smp.kw["batch_size"] == 2     # scale 1 drops uc
+    assert smp.kw["shape"] == (4, 5, 4, 4) and smp.kw["eta"] == 0.0 and smp.kw["is_3d"] is True and smp.kw["x_T"] == "xT"
