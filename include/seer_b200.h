@@ -51,13 +51,14 @@ int seer_b200_gemm_bf16(const void* A, int lda, int K1, const void* A2, int lda2
  *                                                      row_stats_in = `row_parts_in` partial (sum, sumsq) pairs)
  *   v        += bias[(r / bias_div), n] + residual[r, n]                 (residual fp32 or bf16)
  *   geglu: v[:, j] = value * gelu_erf(gate)            (Wt / bias / ln_colsum rows packed value/gate in blocks of 32)
- *   outputs   : out_f32 and/or out_bf16 (either may be NULL, not both), written through TMA stores;
+ *   outputs   : out_f32 and/or out_bf16 (either may be NULL, not both), staged in shared memory and written with
+ *               coalesced 128-bit stores;
  *   col_stats : optional [ceil(M/32)][N][2] fp32 (sum, sumsq) of v per 32-row slab and column (feeds GroupNorm);
  *   row_stats_out : optional [parts][M][2] fp32 partial (sum, sumsq) of v per row (feeds the next folded LayerNorm);
  *                   parts = seer_b200_gemm_row_parts(desc).
  * Requirements: K1, K2 % 64 == 0; N % 64 == 0 (geglu: % 128); lda/lda2/ldo_bf16 % 8 == 0; ldr/ldo_f32 % 4 == 0
  * (ldr % 8 for a bf16 residual); all bases 16-byte aligned; conv: Cin % 64 == 0, W | 128, (128/W) | H or H | (128/W).
- * col_stats needs out_f32. */
+ * col_stats is computed from the fp32 values whichever output dtype is stored. */
 typedef struct SeerGemmDesc {
   const void* A; int lda; int K1;
   const void* X; int n_img, H, W, Cin;
@@ -71,6 +72,14 @@ typedef struct SeerGemmDesc {
   float* col_stats;
   float* row_stats_out;
   const float* row_stats_in; int row_parts_in; float ln_eps; const float* ln_colsum;
+  /* conv variants (X != NULL; all 0 = the 3x3 / stride-1 / pad-1 conv):
+   *   conv_stride 2: Downsample3D (resnet.py:95-104) read straight from X through a strided TMA box; M = n_img*(H/2)*(W/2);
+   *   conv_taps_w x conv_taps_h taps, tap t reading pixel (s*y + t / taps_w + conv_off_y, s*x + t % taps_w + conv_off_x),
+   *     K1 = taps*Cin in the order [Cin/64][tap][64] (0 x 0 = 3 x 3 taps with offsets -1);
+   *   out_up_phase 1 + (2 py + px): GEMM row m = low-res pixel (n, y, x) is stored at the row of pixel (n, 2y+py, 2x+px) of the
+   *     [n_img, 2H, 2W] output and its col_stats slab at 4 (m / 32) + phase — Upsample3D (resnet.py:47-61: nearest 2x, then
+   *     conv3x3) as four 2x2-tap convs on the low-res image with pre-summed weights (W must be a power of two). */
+  int conv_stride; int conv_taps_w, conv_taps_h, conv_off_x, conv_off_y; int out_up_phase;
 } SeerGemmDesc;
 int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream);
 /* sizeof(SeerGemmDesc) as compiled into the library (binding sanity check) */
@@ -101,6 +110,12 @@ int seer_b200_groupnorm(const float* x1, int C1, const float* x2, int C2, int B,
 int seer_b200_groupnorm_from_stats(const float* x1, int C1, const float* stats1, const float* x2, int C2, const float* stats2,
                                    int B, int T, const float* gamma, const float* beta, float eps, int silu, float* scale_shift,
                                    void* y, int y_is_f32, void* raw_bf16, void* stream);
+
+/* As above with x1 optionally a bf16 tensor (x1_is_bf16: conv1's output, which only GroupNorm 2 of the ResNet block reads;
+ * needs C2 == 0 and a bf16 y). */
+int seer_b200_groupnorm_from_stats_ex(const void* x1, int x1_is_bf16, int C1, const float* stats1, const float* x2, int C2,
+                                      const float* stats2, int B, int T, const float* gamma, const float* beta, float eps, int silu,
+                                      float* scale_shift, void* y, int y_is_f32, void* raw_bf16, void* stream);
 
 /* LayerNorm over the last dim (fp32 in, bf16 out).  Replaces nn.LayerNorm: attention.py:198-200,237,244,311,322-323. */
 int seer_b200_layernorm(const float* x, int M, int C, int ldx, const float* gamma, const float* beta, float eps, void* y_bf16,

@@ -34,6 +34,8 @@ class GemmDesc(ctypes.Structure):
         ("col_stats", _vp),
         ("row_stats_out", _vp),
         ("row_stats_in", _vp), ("row_parts_in", _i), ("ln_eps", _f), ("ln_colsum", _vp),
+        ("conv_stride", _i), ("conv_taps_w", _i), ("conv_taps_h", _i), ("conv_off_x", _i), ("conv_off_y", _i),
+        ("out_up_phase", _i),
     ]
 
 
@@ -45,6 +47,7 @@ SIGNATURES = {
     "seer_b200_gemm_row_parts": (_i, [_dp]),
     "seer_b200_gemm_desc_size": (_i, []),
     "seer_b200_groupnorm_from_stats": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _i, _vp, _vp]),
+    "seer_b200_groupnorm_from_stats_ex": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _i, _vp, _vp]),
     "seer_b200_version": (_c.c_char_p, []),
     "seer_b200_gemm_bf16": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "seer_b200_conv3x3_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp]),

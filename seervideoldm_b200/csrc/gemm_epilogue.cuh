@@ -32,8 +32,8 @@ constexpr int EVEC_BYTES_PER_WARP = 2 * EVEC_FLOATS * 4;
 constexpr int BIAS_ONE_ROW = 0x7fffffff;               // GemmParams::bias_div value meaning "a single bias row"
 
 // epilogue option bits (template parameter SPEC of the epilogue; -1 = decide at run time from GemmParams)
-enum : int { EF_LN = 1, EF_GEGLU = 2, EF_RES32 = 4, EF_OUT32 = 8, EF_OUT16 = 16, EF_CSTAT = 32, EF_RSTAT = 64 };
-// the combinations one UNet evaluation issues (all with a bias vector, fp32 residual if any)
+enum : int { EF_LN = 1, EF_GEGLU = 2, EF_RES32 = 4, EF_OUT32 = 8, EF_OUT16 = 16, EF_CSTAT = 32, EF_RSTAT = 64, EF_RES16 = 128 };
+// the combinations one UNet evaluation issues (all with a bias vector)
 constexpr int EK_PIN = EF_OUT32 | EF_OUT16 | EF_RSTAT;               // proj_in: fp32 + bf16 token stream, LN row sums
 constexpr int EK_QKV = EF_LN | EF_OUT16;                              // LN-folded q / qkv projections
 constexpr int EK_ATTN_OUT = EF_RES32 | EF_OUT32 | EF_OUT16 | EF_RSTAT;  // to_out + residual
@@ -43,6 +43,12 @@ constexpr int EK_FF2 = EF_RES32 | EF_OUT16;                           // FF out 
 constexpr int EK_POUT = EF_RES32 | EF_OUT32 | EF_CSTAT;               // proj_out / conv2 + residual, GroupNorm column sums
 constexpr int EK_CONV = EF_OUT32 | EF_CSTAT;                          // conv1 / conv2+shortcut / resample convs
 constexpr int EK_BF16 = EF_OUT16;                                     // plain bf16 projection
+// bf16 token stream inside a transformer block (the reference's own autocast dtype, attention.py:231-248,308-327): the
+// residual is read and written as bf16, fp32 only at the block boundary (proj_out + the block input)
+constexpr int EK_PIN16 = EF_OUT16 | EF_RSTAT;                         // proj_in: bf16 token stream + LN row sums
+constexpr int EK_ATTN_OUT16 = EF_RES16 | EF_OUT16 | EF_RSTAT;         // to_out + bf16 residual
+constexpr int EK_FF2_16 = EF_RES16 | EF_OUT16;                        // FF out + bf16 residual
+constexpr int EK_CONV16 = EF_OUT16 | EF_CSTAT;                        // conv1: bf16 out (only GroupNorm 2 reads it) + column sums
 
 struct GemmParams {
   int M, N;            // N = accumulator columns (GEGLU: twice the output columns)
@@ -53,6 +59,9 @@ struct GemmParams {
   int H, W;            // conv image geometry
   int tiles_n, num_tiles;
   int stages, nepi, ring, slot_bytes;
+  int ntaps, taps_w, taps_h, off_x, off_y, cstride;   // conv taps: tap t reads pixel (s*y + t / taps_w + off_y, s*x + t % taps_w + off_x)
+  int up_phase;        // 0: output row = GEMM row; 1 + (2 py + px): rows are the (py, px) phase of a nearest-2x upsampled image
+  int up_wshift;       //    (low-res width = 1 << up_wshift): out row = ((m >> ws) << (ws + 2)) + py * 2W + 2 (m & (W - 1)) + px
   int bstat;           // 1: the whole Wt panel of this CTA's (fixed) n-block is resident in smem; only A is streamed
   int epi_spec;        // EK_* combination compiled as a specialisation, or -1 (generic runtime-flag epilogue)
   const float* bias;
@@ -172,7 +181,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
   constexpr bool S = SPEC >= 0;
   constexpr bool GEGLU = S && (SPEC & EF_GEGLU) != 0;      // the host routes every GEGLU launch to a specialisation
   const bool f_ln = S ? (SPEC & EF_LN) != 0 : p.row_stats_in != nullptr;
-  const int res_mode = S ? ((SPEC & EF_RES32) ? 1 : 0) : p.res_mode;
+  const int res_mode = S ? ((SPEC & EF_RES32) ? 1 : ((SPEC & EF_RES16) ? 2 : 0)) : p.res_mode;
   const bool f_o32 = S ? (SPEC & EF_OUT32) != 0 : p.out_f32 != nullptr;
   const bool f_o16 = S ? (SPEC & EF_OUT16) != 0 : p.out_bf16 != nullptr;
   const bool f_cst = S ? (SPEC & EF_CSTAT) != 0 : p.col_stats != nullptr;
@@ -291,6 +300,13 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
   // right after the previous chunk's registers were consumed — and completed (tcgen05.wait::ld) at the END of that
   // step, behind its staging / store phase, so no asynchronously written register is live across the loop edge.
   bool have = false;
+  // output row of GEMM row m: identity, or the (py, px) phase rows of the nearest-2x upsampled image (Upsample3D folded
+  // into four 2x2-tap convs on the low-res image, resnet.py:52)
+  const int up_ws = p.up_wshift, up_mask = (1 << p.up_wshift) - 1;
+  const int up_off = p.up_phase ? (((p.up_phase - 1) >> 1) << (p.up_wshift + 1)) + ((p.up_phase - 1) & 1) : 0;
+  auto out_row = [&](int m) -> size_t {
+    return p.up_phase ? (size_t)(((m >> up_ws) << (up_ws + 2)) + up_off + ((m & up_mask) << 1)) : (size_t)m;
+  };
 
   int g = 0, it = 0, slot_i = 0;
   uint32_t slot_par = 0;                   // parity of the residual barrier of slot `slot_i` = (g / R) & 1
@@ -420,16 +436,18 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
       // at ~1000 cycles of serial latency per warp (tools/tma_store_bench.cu).
       const int ocol = (GEGLU ? (n0 >> 1) : n0) + c * 32;
       __syncwarp();                          // every lane has read its residual row: the slot may be overwritten
-      if (f_o32) {
+      if (f_o32 || f_cst) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) sts128_f2(slot + sw128(lane, k), f[2 * k], f[2 * k + 1]);
         __syncwarp();
-        float* dst = p.out_f32 + (size_t)row0 * p.ldo_f32 + ocol + (lane & 7) * 4;
+        if (f_o32) {
+          float* dst = p.out_f32 + ocol + (lane & 7) * 4;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = 4 * i + (lane >> 3);
-          const float4 t = lds128(slot + sw128(r, lane & 7));
-          if (row0 + r < p.M) *reinterpret_cast<float4*>(dst + (size_t)r * p.ldo_f32) = t;
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            const float4 t = lds128(slot + sw128(r, lane & 7));
+            if (row0 + r < p.M) *reinterpret_cast<float4*>(dst + out_row(row0 + r) * p.ldo_f32) = t;
+          }
         }
         if (f_cst) {
           // lane = column: (sum, sumsq) over this warp's 32 rows, read back from the staged fp32 tile
@@ -441,8 +459,10 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
             cs += t;
             cq = fmaf(t, t, cq);
           }
-          if (row0 < p.M)
-            reinterpret_cast<float2*>(p.col_stats)[(size_t)(row0 >> 5) * p.N + ocol + lane] = make_float2(cs, cq);
+          if (row0 < p.M) {
+            const size_t slab = p.up_phase ? (((size_t)(row0 >> 5) << 2) + (size_t)(p.up_phase - 1)) : (size_t)(row0 >> 5);
+            reinterpret_cast<float2*>(p.col_stats)[slab * p.N + ocol + lane] = make_float2(cs, cq);
+          }
         }
         __syncwarp();
       }
@@ -457,12 +477,12 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
           sts128u(slot + sw64(lane, k), o);
         }
         __syncwarp();
-        __nv_bfloat16* dst = p.out_bf16 + (size_t)row0 * p.ldo_bf16 + ocol + (lane & 3) * 8;
+        __nv_bfloat16* dst = p.out_bf16 + ocol + (lane & 3) * 8;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = 8 * i + (lane >> 2);
           const uint4 t = lds128u(slot + sw64(r, lane & 3));
-          if (row0 + r < p.M) *reinterpret_cast<uint4*>(dst + (size_t)r * p.ldo_bf16) = t;
+          if (row0 + r < p.M) *reinterpret_cast<uint4*>(dst + out_row(row0 + r) * p.ldo_bf16) = t;
         }
         __syncwarp();
       }

@@ -118,6 +118,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           img0 = m0 / hw;
           y0 = (m0 % hw) / p.W;
         }
+        // conv tap cursor, advanced incrementally (no division by the run-time tap count on the producer's critical path)
+        int t_kx = 0, t_ky = 0, t_c0 = 0;
         for (int kb = 0; kb < p.kb_total; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sA = stage_base + s * stage_stride;
@@ -131,11 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               } else {
                 // K order [Cin/64][tap][64]: the 9 shifted views of one 64-channel slab are fetched back to back, so
                 // the slab (and its halo) is served from L2 while it is hot instead of being re-read 9 x Cin/64 k-blocks apart
-                const int chunk = kb / 9;
-                const int tap = kb - chunk * 9;
-                const int c0 = chunk * BK;
-                const int ky = tap / 3, kx = tap - ky * 3;
-                tma_load_4d(sA, &tmA, &full_bar[s], c0, kx - 1, y0 + ky - 1, img0);
+                tma_load_4d(sA, &tmA, &full_bar[s], t_c0, t_kx + p.off_x, p.cstride * y0 + t_ky + p.off_y, img0);
               }
             } else {
               tma_load_2d(sA, &tmA2, &full_bar[s], (kb - p.kb_main) * BK, m0);
@@ -151,11 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               } else {
                 // K order [Cin/64][tap][64]: the 9 shifted views of one 64-channel slab are fetched back to back, so
                 // the slab (and its halo) is served from L2 while it is hot instead of being re-read 9 x Cin/64 k-blocks apart
-                const int chunk = kb / 9;
-                const int tap = kb - chunk * 9;
-                const int c0 = chunk * BK;
-                const int ky = tap / 3, kx = tap - ky * 3;
-                tma_load_4d_cg2(sA, &tmA, fb, c0, kx - 1, y0 + ky - 1, img0);
+                tma_load_4d_cg2(sA, &tmA, fb, t_c0, t_kx + p.off_x, p.cstride * y0 + t_ky + p.off_y, img0);
               }
             } else {
               tma_load_2d_cg2(sA, &tmA2, fb, (kb - p.kb_main) * BK, m0);
@@ -164,6 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           }
           __syncwarp();
+          if (++t_kx == p.taps_w) { t_kx = 0; if (++t_ky == p.taps_h) { t_ky = 0; t_c0 += BK; } }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -220,6 +215,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       case EK_POUT: SEER_EPI(EK_POUT); break;
       case EK_CONV: SEER_EPI(EK_CONV); break;
       case EK_BF16: SEER_EPI(EK_BF16); break;
+      case EK_PIN16: SEER_EPI(EK_PIN16); break;
+      case EK_ATTN_OUT16: SEER_EPI(EK_ATTN_OUT16); break;
+      case EK_FF2_16: SEER_EPI(EK_FF2_16); break;
+      case EK_CONV16: SEER_EPI(EK_CONV16); break;
       case EK_FF1:
         if constexpr (BN == 128 || BN == 256) SEER_EPI(EK_FF1);
         break;
@@ -284,14 +283,16 @@ static int make_map_bf16_k64(CUtensorMap* tm, const void* base, uint64_t rows, u
 }
 
 // 4-D bf16 activation [n_img, H, W, C] (C contiguous), box = {64, bw, bh, bn}.
+// `stride` > 1: every stride-th pixel of a (bw*stride) x (bh*stride) bounding box (TMA traversal stride) — the stride-2
+// Downsample3D conv reads its taps straight from the full-resolution image.
 static int make_map_4d(CUtensorMap* tm, const void* base, uint64_t n_img, uint64_t H, uint64_t W, uint64_t C, uint32_t bw,
-                       uint32_t bh, uint32_t bn) {
+                       uint32_t bh, uint32_t bn, uint32_t stride = 1) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return SEER_ENODRIVER;
   cuuint64_t dims[4] = {C, W, H, n_img};
   cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-  cuuint32_t box[4] = {64, bw, bh, bn};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {64, bw * stride, bh * stride, bn};
+  cuuint32_t estr[4] = {1, stride, stride, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -321,12 +322,16 @@ static int env_int(const char* name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 
+static inline int conv_ntaps(const SeerGemmDesc& d) {
+  return (d.conv_taps_w > 0 && d.conv_taps_h > 0) ? d.conv_taps_w * d.conv_taps_h : 9;
+}
+
 static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   const int N = d.N;
   // CTA pairs (cta_group::2, 256-row tiles) for tensor-bound launches: they halve the Wt bytes each SM pulls from L2
   // per FLOP (measured +15..25 % on K >= 1280 GEMMs); HBM-bound launches (small K, fp32 residual + output) run a
   // little better as independent 128-row CTAs.  Crude roofline estimate with the measured peaks (profiles/).
-  const double Kd = d.X ? 9.0 * d.Cin + d.K2 : (double)d.K1 + d.K2;
+  const double Kd = d.X ? (double)conv_ntaps(d) * d.Cin + d.K2 : (double)d.K1 + d.K2;
   const double n_out = d.geglu ? N / 2 : N;
   const double bytes = (double)d.M * (d.X ? d.Cin + d.K2 : Kd) * 2 + (double)N * Kd * 2 +
                        (double)d.M * n_out * ((d.out_f32 ? 4 : 0) + (d.out_bf16 ? 2 : 0) + (d.residual ? (d.residual_bf16 ? 2 : 4) : 0));
@@ -374,7 +379,7 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   // slot: residual chunk and staged output chunk share the bytes (fp32: 32 x 128 B, bf16: 32 x 64 B)
   const bool of = d.out_f32 != nullptr;
   const int rm = d.residual ? (d.residual_bf16 ? 2 : 1) : 0;
-  pl.slot_bytes = (of || rm == 1) ? 4096 : 2048;
+  pl.slot_bytes = (of || rm == 1 || d.col_stats) ? 4096 : 2048;
   // 8 epilogue warps (two per scheduler, so one warp's dependent-issue latency hides behind the other's) unless a long
   // main loop (big K) hides the epilogue anyway and the smem is better spent on operand stages
   pl.nepi = env_int("SEER_GEMM_NEPI", (d.geglu || !of || Kd <= 1280.0) ? 8 : 4);
@@ -452,8 +457,14 @@ static int check_desc(const SeerGemmDesc& d) {
   SEER_CHECK_ARG(d.K2 % 64 == 0 && (d.K2 == 0 || (d.A2 && d.lda2 % 8 == 0)));
   if (d.X) {
     SEER_CHECK_ARG(d.n_img > 0 && d.H > 0 && d.W > 0 && d.Cin > 0 && d.Cin % 64 == 0);
-    SEER_CHECK_ARG(d.M == d.n_img * d.H * d.W);
+    const int cs = d.conv_stride > 1 ? d.conv_stride : 1;
+    SEER_CHECK_ARG(cs <= 2 && d.H % cs == 0 && d.W % cs == 0);
+    SEER_CHECK_ARG(d.M == d.n_img * (d.H / cs) * (d.W / cs));
+    SEER_CHECK_ARG((d.conv_taps_w > 0) == (d.conv_taps_h > 0) && d.conv_taps_w <= 3 && d.conv_taps_h <= 3);
+    SEER_CHECK_ARG(d.out_up_phase >= 0 && d.out_up_phase <= 4);
+    if (d.out_up_phase) SEER_CHECK_ARG(cs == 1 && (d.W & (d.W - 1)) == 0 && !d.residual && !d.row_stats_out && d.M % 32 == 0);
   } else {
+    SEER_CHECK_ARG(d.out_up_phase == 0);
     SEER_CHECK_ARG(d.K1 > 0 && d.K1 % 64 == 0 && d.lda % 8 == 0);
   }
   SEER_CHECK_ARG(!d.out_f32 || d.ldo_f32 % 4 == 0);
@@ -461,7 +472,7 @@ static int check_desc(const SeerGemmDesc& d) {
   SEER_CHECK_ARG(!d.residual || (d.residual_bf16 ? d.ldr % 8 == 0 : d.ldr % 4 == 0));
   SEER_CHECK_ARG(d.ldb <= 0 || d.ldb % 4 == 0);
   if (d.geglu) SEER_CHECK_ARG(d.bias_div <= 0 && d.N % 128 == 0 && d.out_bf16 && !d.out_f32 && d.bias && !d.residual && !d.col_stats && !d.row_stats_out);
-  SEER_CHECK_ARG(!d.col_stats || d.out_f32);
+  SEER_CHECK_ARG(!d.col_stats || d.out_f32 || d.out_bf16);
   if (d.row_stats_in) SEER_CHECK_ARG(d.row_parts_in > 0 && d.ln_colsum && !d.X);
   return SEER_OK;
 }
@@ -492,12 +503,14 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   {
     // epilogue specialisation: the option combinations of the UNet's hot launches are compiled as straight-line code
     const int flags = (d.row_stats_in ? EF_LN : 0) | (d.geglu ? EF_GEGLU : 0) | ((d.residual && !d.residual_bf16) ? EF_RES32 : 0) |
+                      ((d.residual && d.residual_bf16) ? EF_RES16 : 0) |
                       (d.out_f32 ? EF_OUT32 : 0) | (d.out_bf16 ? EF_OUT16 : 0) | (d.col_stats ? EF_CSTAT : 0) |
                       (d.row_stats_out ? EF_RSTAT : 0);
-    static const int kinds[] = {EK_PIN, EK_QKV, EK_ATTN_OUT, EK_FF1, EK_FF1_PLAIN, EK_FF2, EK_POUT, EK_CONV, EK_BF16};
+    static const int kinds[] = {EK_PIN, EK_QKV, EK_ATTN_OUT, EK_FF1, EK_FF1_PLAIN, EK_FF2, EK_POUT, EK_CONV, EK_BF16,
+                                EK_PIN16, EK_ATTN_OUT16, EK_FF2_16, EK_CONV16};
     p.epi_spec = -1;
     const bool generic_forced = env_int("SEER_GEMM_GENERIC", 0) != 0 && !d.geglu;    // A/B hook
-    if (d.bias && !(d.residual && d.residual_bf16) && !generic_forced)
+    if (d.bias && !generic_forced)
       for (int k : kinds)
         if (k == flags) p.epi_spec = k;
     if (d.geglu && p.epi_spec < 0) return SEER_EUNSUPPORTED;
@@ -517,7 +530,8 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   if (d.X) {
     // A 128-pixel M tile must be a whole number of image rows (or of images): W | 128 and the tile never
     // straddles an image boundary mid-row.
-    const int W = d.W, H = d.H;
+    const int cs = d.conv_stride > 1 ? d.conv_stride : 1;
+    const int W = d.W / cs, H = d.H / cs;          // OUTPUT geometry: an M tile is whole output rows
     if (W > 128 || 128 % W != 0) return SEER_EUNSUPPORTED;
     const int rows = 128 / W;
     int bh, bn_img;
@@ -530,13 +544,25 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
     }
     p.mode = 1;
     p.cblk = d.Cin / 64;
-    p.kb_main = 9 * p.cblk;
+    p.ntaps = conv_ntaps(d);
+    p.taps_w = d.conv_taps_w > 0 ? d.conv_taps_w : 3;
+    p.taps_h = d.conv_taps_w > 0 ? d.conv_taps_h : 3;
+    p.off_x = d.conv_taps_w > 0 ? d.conv_off_x : -1;
+    p.off_y = d.conv_taps_w > 0 ? d.conv_off_y : -1;
+    p.cstride = cs;
+    p.kb_main = p.ntaps * p.cblk;
     p.H = H; p.W = W;
-    Ktot = 9 * d.Cin + d.K2;
-    if ((rc = make_map_4d(&maps[0], d.X, d.n_img, H, W, d.Cin, W, bh, bn_img))) return rc;
+    Ktot = p.ntaps * d.Cin + d.K2;
+    if (d.out_up_phase) {
+      p.up_phase = d.out_up_phase;
+      p.up_wshift = 0;
+      while ((1 << p.up_wshift) < W) ++p.up_wshift;
+    }
+    if ((rc = make_map_4d(&maps[0], d.X, d.n_img, d.H, d.W, d.Cin, W, bh, bn_img, cs))) return rc;
   } else {
     p.mode = 0;
     p.cblk = 1; p.H = 1; p.W = 1;
+    p.ntaps = 9; p.taps_w = 3; p.taps_h = 3; p.off_x = p.off_y = -1; p.cstride = 1;
     p.kb_main = d.K1 / 64;
     Ktot = d.K1 + d.K2;
     if ((rc = make_map_bf16_k64(&maps[0], d.A, d.M, d.K1, d.lda, BM))) return rc;

@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(256) gn_finalize_cols_kernel(const float2* __r
 // one 16-byte store per row with no index arithmetic, unrolled by 4 rows so eight loads are in flight per thread.
 // Block = rps rows x (C/8) chunks (consecutive threads = consecutive chunks of a row: 32-byte pieces of one contiguous row),
 // it walks `rows_per_block` rows of ONE sample; grid = (blocks per sample, B).
-template <bool OUT_F32>
-__global__ void __launch_bounds__(512) gn_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
+template <bool OUT_F32, bool IN_BF16>
+__global__ void __launch_bounds__(512) gn_apply_kernel(const void* __restrict__ x1v, int C1, const float* __restrict__ x2,
                                                        int C2, int T, int rows_per_block, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, int silu, void* __restrict__ y,
                                                        __nv_bfloat16* __restrict__ raw) {
@@ -206,7 +206,10 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const float* __restrict__
   const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + (size_t)b * C + c + 4));
   const bool first = c < C1;
   const int ldx = first ? C1 : C2;
-  const float* src = (first ? x1 + c : x2 + (c - C1)) + ((size_t)b * T + r_begin + rl) * ldx;
+  // IN_BF16: x1 is a bf16 tensor (conv1's output, read only by this GroupNorm); the concat partner is fp32-only (C2 == 0)
+  const float* src = IN_BF16 ? nullptr
+                             : (first ? reinterpret_cast<const float*>(x1v) + c : x2 + (c - C1)) + ((size_t)b * T + r_begin + rl) * ldx;
+  const __nv_bfloat16* src16 = IN_BF16 ? reinterpret_cast<const __nv_bfloat16*>(x1v) + c + ((size_t)b * T + r_begin + rl) * ldx : nullptr;
   const size_t out_off = ((size_t)b * T + r_begin + rl) * C + c;
   const size_t in_step = (size_t)rps * ldx, out_step = (size_t)rps * C;
 
@@ -232,28 +235,49 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const float* __restrict__
       *reinterpret_cast<uint4*>(raw + off) = o;
     }
   };
+  auto emit16 = [&](const uint4& a, size_t off) {
+    const float2 p0 = unpack_bf16(a.x), p1 = unpack_bf16(a.y), p2 = unpack_bf16(a.z), p3 = unpack_bf16(a.w);
+    emit(make_float4(p0.x, p0.y, p1.x, p1.y), make_float4(p2.x, p2.y, p3.x, p3.y), off);
+  };
 
   if (rl >= rps) return;                            // threads beyond rps * c8n (block size rounded up to a warp multiple)
   int r = r_begin + rl;
   size_t oo = out_off;
-  for (; r + 3 * rps < r_end; r += 4 * rps) {
-    float4 a0[4], a1[4];
+  if constexpr (IN_BF16) {
+    for (; r + 3 * rps < r_end; r += 4 * rps) {
+      uint4 a[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      a0[u] = __ldcs(reinterpret_cast<const float4*>(src + u * in_step));
-      a1[u] = __ldcs(reinterpret_cast<const float4*>(src + u * in_step + 4));
+      for (int u = 0; u < 4; ++u) a[u] = __ldcs(reinterpret_cast<const uint4*>(src16 + u * in_step));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) emit16(a[u], oo + u * out_step);
+      src16 += 4 * in_step;
+      oo += 4 * out_step;
     }
+    for (; r < r_end; r += rps) {
+      emit16(__ldcs(reinterpret_cast<const uint4*>(src16)), oo);
+      src16 += in_step;
+      oo += out_step;
+    }
+  } else {
+    for (; r + 3 * rps < r_end; r += 4 * rps) {
+      float4 a0[4], a1[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) emit(a0[u], a1[u], oo + u * out_step);
-    src += 4 * in_step;
-    oo += 4 * out_step;
-  }
-  for (; r < r_end; r += rps) {
-    const float4 a0 = __ldcs(reinterpret_cast<const float4*>(src));
-    const float4 a1 = __ldcs(reinterpret_cast<const float4*>(src + 4));
-    emit(a0, a1, oo);
-    src += in_step;
-    oo += out_step;
+      for (int u = 0; u < 4; ++u) {
+        a0[u] = __ldcs(reinterpret_cast<const float4*>(src + u * in_step));
+        a1[u] = __ldcs(reinterpret_cast<const float4*>(src + u * in_step + 4));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) emit(a0[u], a1[u], oo + u * out_step);
+      src += 4 * in_step;
+      oo += 4 * out_step;
+    }
+    for (; r < r_end; r += rps) {
+      const float4 a0 = __ldcs(reinterpret_cast<const float4*>(src));
+      const float4 a1 = __ldcs(reinterpret_cast<const float4*>(src + 4));
+      emit(a0, a1, oo);
+      src += in_step;
+      oo += out_step;
+    }
   }
 }
 
@@ -347,20 +371,21 @@ extern "C" int seer_b200_groupnorm(const float* x1, int C1, const float* x2, int
   int ga_threads, ga_rows, ga_blocks;
   gn_apply_geometry(T, C, B, ga_threads, ga_rows, ga_blocks);
   if (y_is_f32)
-    { cudaError_t le__ = launch_pdl(gn_apply_kernel<true>, dim3(ga_blocks, B), ga_threads, 0, stream, x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
+    { cudaError_t le__ = launch_pdl(gn_apply_kernel<true, false>, dim3(ga_blocks, B), ga_threads, 0, stream, (const void*)x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
   else
-    { cudaError_t le__ = launch_pdl(gn_apply_kernel<false>, dim3(ga_blocks, B), ga_threads, 0, stream, x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
+    { cudaError_t le__ = launch_pdl(gn_apply_kernel<false, false>, dim3(ga_blocks, B), ga_threads, 0, stream, (const void*)x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
 
-extern "C" int seer_b200_groupnorm_from_stats(const float* x1, int C1, const float* stats1, const float* x2, int C2,
-                                              const float* stats2, int B, int T, const float* gamma, const float* beta, float eps,
-                                              int silu, float* scale_shift, void* y, int y_is_f32, void* raw_bf16, void* stream_) {
+extern "C" int seer_b200_groupnorm_from_stats_ex(const void* x1, int x1_is_bf16, int C1, const float* stats1, const float* x2, int C2,
+                                                 const float* stats2, int B, int T, const float* gamma, const float* beta, float eps,
+                                                 int silu, float* scale_shift, void* y, int y_is_f32, void* raw_bf16, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int C = C1 + C2;
   SEER_CHECK_ARG(x1 && stats1 && gamma && beta && scale_shift && y && B > 0 && T > 0 && T % 32 == 0);
   SEER_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && (C2 == 0 || (x2 && stats2)) && C % (2 * GN_GROUPS) == 0 && C / 8 <= 512);
+  SEER_CHECK_ARG(!x1_is_bf16 || (C2 == 0 && !y_is_f32));
   float* scale = scale_shift;
   float* shift = scale_shift + (size_t)B * C;
   { cudaError_t le__ = launch_pdl(gn_finalize_cols_kernel, dim3(GN_GROUPS, B), 256, 0, stream, (const float2*)stats1, C1, (const float2*)stats2, C2, T, eps,
@@ -368,12 +393,23 @@ extern "C" int seer_b200_groupnorm_from_stats(const float* x1, int C1, const flo
   SEER_LAUNCH_CHECK();
   int ga_threads, ga_rows, ga_blocks;
   gn_apply_geometry(T, C, B, ga_threads, ga_rows, ga_blocks);
-  if (y_is_f32)
-    { cudaError_t le__ = launch_pdl(gn_apply_kernel<true>, dim3(ga_blocks, B), ga_threads, 0, stream, x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
+  cudaError_t le__;
+  if (x1_is_bf16)
+    le__ = launch_pdl(gn_apply_kernel<false, true>, dim3(ga_blocks, B), ga_threads, 0, stream, x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16);
+  else if (y_is_f32)
+    le__ = launch_pdl(gn_apply_kernel<true, false>, dim3(ga_blocks, B), ga_threads, 0, stream, x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16);
   else
-    { cudaError_t le__ = launch_pdl(gn_apply_kernel<false>, dim3(ga_blocks, B), ga_threads, 0, stream, x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
+    le__ = launch_pdl(gn_apply_kernel<false, false>, dim3(ga_blocks, B), ga_threads, 0, stream, x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16);
+  if (le__ != cudaSuccess) return (int)le__;
   SEER_LAUNCH_CHECK();
   return SEER_OK;
+}
+
+extern "C" int seer_b200_groupnorm_from_stats(const float* x1, int C1, const float* stats1, const float* x2, int C2,
+                                              const float* stats2, int B, int T, const float* gamma, const float* beta, float eps,
+                                              int silu, float* scale_shift, void* y, int y_is_f32, void* raw_bf16, void* stream_) {
+  return seer_b200_groupnorm_from_stats_ex(x1, 0, C1, stats1, x2, C2, stats2, B, T, gamma, beta, eps, silu, scale_shift, y, y_is_f32,
+                                           raw_bf16, stream_);
 }
 
 extern "C" int seer_b200_layernorm(const float* x, int M, int C, int ldx, const float* gamma, const float* beta, float eps,

@@ -12,6 +12,7 @@ expressions), and when `unet` is a seer_b200 `SeerUNet` the evaluation is replay
 """
 from __future__ import annotations
 
+import collections
 from typing import Optional
 
 import numpy as np
@@ -74,7 +75,8 @@ class DDIMSampler(object):
         self.device = torch.device(device) if not isinstance(device, torch.device) else device
         self.use_cuda_graph = kwargs.get("use_cuda_graph", True)
         self._branch = None            # (process group, branch index) while the CFG-branch split is enabled
-        self._graphs = {}
+        self._graphs = collections.OrderedDict()      # LRU of captured evaluations (each pins a private activation pool)
+        self.max_graphs = int(kwargs.get("max_graphs", 3))
 
     def register_buffer(self, name, attr):
         if isinstance(attr, torch.Tensor) and attr.device != self.device:
@@ -183,14 +185,17 @@ class DDIMSampler(object):
         """One UNet evaluation; replayed from a CUDA graph when the model is a seer_b200 SeerUNet."""
         if not (self.use_cuda_graph and isinstance(unet, SeerUNet) and x_in.is_cuda):
             return unet(x_in, t_in, c_in, cond_frame=cond_frame)
-        key = (id(unet), tuple(x_in.shape), tuple(c_in.shape), cond_frame, unet.precision)
+        key = (id(unet), tuple(x_in.shape), tuple(c_in.shape), cond_frame, unet.precision, str(x_in.device))
         g = self._graphs.get(key)
-        if g is not None and not g.matches(unet, x_in, c_in, cond_frame):      # id() reuse after garbage collection
+        if g is not None and not g.matches(unet, x_in, c_in, cond_frame):      # id() reuse after garbage collection, or the
+            del self._graphs[key]                                              # model's weights changed since the capture
             g = None
         if g is None:
-            if len(self._graphs) >= 4:
-                self._graphs.clear()
+            while len(self._graphs) >= max(1, self.max_graphs):                # least recently used first: alternating shapes
+                self._graphs.popitem(last=False)                               # (a last partial batch) do not thrash
             g = self._graphs[key] = GraphedUNet(unet, x_in, t_in, c_in, cond_frame)
+        else:
+            self._graphs.move_to_end(key)
         return g(x_in, t_in, c_in)
 
     @torch.no_grad()
@@ -199,6 +204,9 @@ class DDIMSampler(object):
                       unconditional_guidance_scale=1., unconditional_conditioning=None, null_cond_prob=None):
         if not is_3d:
             raise NotImplementedError("SeerUNet consumes 5-D video latents; the pipelines always pass is_3d=True")
+        if null_cond_prob is not None:
+            # ddim_video.py:193-194 forwards it to a keyword SeerUNet.forward does not have (the reference raises TypeError)
+            raise NotImplementedError("null_cond_prob: the reference's branch is dead code (SeerUNet.forward has no such argument)")
         b = x.shape[0]
         cond_f = 0
         x_cat = x
@@ -228,11 +236,12 @@ class DDIMSampler(object):
             raise RuntimeError("DDIMSampler (seer_b200) needs CUDA fp32 latents; there is no CPU fallback")
         # the reference draws noise even when sigma == 0 (ddim_video.py:232): keep the RNG stream aligned
         noise = torch.randn(x.shape, device=x.device)
-        if sigma != 0.0:
+        if sigma != 0.0 or noise_dropout > 0.:
             noise = sigma * noise * temperature
-            if noise_dropout > 0.:
+            if noise_dropout > 0.:                      # the reference draws the dropout mask even when sigma == 0 (:234-236)
                 noise = torch.nn.functional.dropout(noise, p=noise_dropout)
-            x_prev = x_prev + noise
+            if sigma != 0.0:
+                x_prev = x_prev + noise
         return x_prev, pred_x0
 
     def _cfg_context(self, uc, c):

@@ -35,6 +35,30 @@ def pack_conv3x3(w: torch.Tensor, shortcut: Optional[torch.Tensor] = None) -> to
     return p.to(torch.bfloat16).contiguous()
 
 
+def pack_upsample_phases(w: torch.Tensor) -> list:
+    """Upsample3D = nearest 2x then conv3x3 (resnet.py:47-61).  Output pixel (2y+py, 2x+px) only ever sees the 2x2 low-res
+    neighbourhood {y+py-1, y+py} x {x+px-1, x+px}, each low-res pixel through the SUM of the 3x3 taps that land on its
+    duplicates: rows (py=0) [w0 | w1+w2], (py=1) [w0+w1 | w2], same along x.  Returns the four phase weights (index 2 py + px),
+    each [Cout, 4*Cin] bf16 in K order [Cin/64][ty][tx][64] — 4/9 of the FLOPs of convolving the upsampled image."""
+    cout, cin = w.shape[:2]
+    if cin % 64:
+        raise ValueError("pack_upsample_phases: Cin must be a multiple of 64")
+    w = w.float()
+    rows = {0: (w[:, :, 0], w[:, :, 1] + w[:, :, 2]), 1: (w[:, :, 0] + w[:, :, 1], w[:, :, 2])}      # [Cout, Cin, kx] per ty
+    out = []
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = []
+            for ty in (0, 1):
+                r = rows[py][ty]
+                cols = (r[:, :, 0], r[:, :, 1] + r[:, :, 2]) if px == 0 else (r[:, :, 0] + r[:, :, 1], r[:, :, 2])
+                taps += [cols[0], cols[1]]
+            p = torch.stack(taps, dim=1)                                   # [Cout, 4, Cin]
+            p = p.reshape(cout, 4, cin // 64, 64).permute(0, 2, 1, 3).reshape(cout, 4 * cin)
+            out.append(p.to(torch.bfloat16).contiguous())
+    return out
+
+
 def pack_conv_out(w: torch.Tensor) -> torch.Tensor:
     """[Cout<=4, Cin, 3, 3] -> fp32 [Cout, 9, Cin]."""
     cout, cin = w.shape[:2]

@@ -60,6 +60,8 @@ def sample_sharded(sample_fn: Callable[[Sequence[int]], torch.Tensor], n_clips: 
         owner, owners = rank // 2, world // 2
     else:
         owner, owners = rank, world
+    if n_clips < owners:          # every rank knows both numbers: all of them raise, none is left waiting in the collective
+        raise ValueError(f"n_clips ({n_clips}) must be >= the number of owners ({owners}: ranks, or rank pairs)")
     mine = shard_clips(n_clips, owner, owners)
     outs = [sample_fn(mine[i: i + batch]) for i in range(0, len(mine), batch)]
     local = torch.cat(outs) if outs else None

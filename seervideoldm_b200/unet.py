@@ -71,6 +71,7 @@ class SeerUNet(nn.Module):
         self.sample_size = sample_size
         self._packed: Optional[dict] = None
         self._packed32: Optional[dict] = None
+        self._weights_version = 0       # bumped whenever the packed weights are dropped (captured CUDA graphs check it)
         self._kv_key = None
         self._kv: List[torch.Tensor] = []
         self.precision = "bf16"
@@ -106,18 +107,23 @@ class SeerUNet(nn.Module):
                 ref = p if name.endswith("weight") else params[name[: -len("bias")] + "weight"]
                 bound = 1.0 / math.sqrt(max(1, ref[0].numel()))
                 p.uniform_(-bound, bound)
+        self._invalidate_packed()
+
+    def _invalidate_packed(self) -> None:
+        """The parameters changed (load / init / device move): drop the packed bf16 copies and the text K/V, and bump the
+        version so that CUDA graphs captured over the old packed tensors (graph.GraphedUNet) are never replayed."""
         self._packed = self._packed32 = None
+        self._kv_key = None
+        self._weights_version = getattr(self, "_weights_version", 0) + 1
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
-        self._packed = self._packed32 = None
-        self._kv_key = None
+        self._invalidate_packed()
         return out
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
-        self._packed = self._packed32 = None
-        self._kv_key = None
+        self._invalidate_packed()
         return out
 
     @classmethod
@@ -270,8 +276,8 @@ class SeerUNet(nn.Module):
                     blk["attn"].append(xf(f"up_blocks.{i}.attentions.{j}.", False))
                     blk["tattn"].append(xf(f"up_blocks.{i}.temporal_attentions.{j}.", True))
             if i < n - 1:
-                blk["up"] = (packing.pack_conv3x3(P(f"up_blocks.{i}.upsamplers.0.conv.weight")),
-                             f32(f"up_blocks.{i}.upsamplers.0.conv.bias"))
+                wu = P(f"up_blocks.{i}.upsamplers.0.conv.weight")
+                blk["up"] = (packing.pack_conv3x3(wu), f32(f"up_blocks.{i}.upsamplers.0.conv.bias"), packing.pack_upsample_phases(wu))
             pk["up"].append(blk)
         pk["temb_w"] = torch.cat(temb_w, 0).contiguous()
         pk["temb_b"] = torch.cat(temb_b, 0).contiguous()
@@ -279,14 +285,24 @@ class SeerUNet(nn.Module):
         return pk
 
     # ------------------------------------------------------------------ operators
-    def _resnet(self, r: dict, x1, x2, B, F, H, W, temb_all):
+    @staticmethod
+    def _emit(g: "ops.GemmOut", want: str):
+        """Block output record (fp32 stream, GroupNorm col_stats, bf16 copy) of the GEMM that produced it.  `want`: "f32" (fp32 +
+        statistics, the residual stream between blocks), "both" (+ bf16 copy: the stride-2 Downsample3D conv reads it), "bf16"
+        (bf16 only: the block feeds an Upsample3D conv and nothing else)."""
+        if want == "bf16":
+            return (None, None, g.out)
+        return (g.out, g.col_stats, g.out16)
+
+    def _resnet(self, r: dict, x1, x2, B, F, H, W, temb_all, want: str = "f32"):
         """ResnetBlock3D.forward (resnet.py:174-208) on the virtual concat [x1 | x2].  Activations travel as
-        (tensor, col_stats) pairs: the GEMM that produced a tensor also emitted the per-channel partial sums the next
-        GroupNorm needs, so no statistics pass re-reads the activation."""
+        (fp32 tensor, col_stats, bf16 copy or None) records: the GEMM that produced a tensor also emitted the per-channel
+        partial sums the next GroupNorm needs, so no statistics pass re-reads the activation.  conv1's output is stored as
+        bf16 only (its single reader is GroupNorm 2; the statistics are taken from the fp32 accumulators)."""
         T = F * H * W
         eps = self.cfg.norm_eps
         cin, cout = r["cin"], r["cout"]
-        (t1, s1), (t2, s2) = x1, (x2 if x2 is not None else (None, None))
+        (t1, s1), (t2, s2) = x1[:2], (x2[:2] if x2 is not None else (None, None))
         if r["sc"]:
             h, raw = ops.groupnorm(t1, t2, B, r["g1"], r["b1"], eps, True, want_raw=True, stats1=s1, stats2=s2)
         else:
@@ -294,32 +310,39 @@ class SeerUNet(nn.Module):
                 raise RuntimeError("concat input without a shortcut conv cannot occur in this architecture")
             h, raw = ops.groupnorm(t1, None, B, r["g1"], r["b1"], eps, True, stats1=s1), None
         tb = temb_all[:, r["off"]: r["off"] + cout]
-        c1 = ops.conv3x3_ex(h.view(B * F, H, W, cin), r["w1"], bias=tb, bias_div=T, col_stats=True)
+        if T % 32 == 0:
+            c1 = ops.conv3x3_ex(h.view(B * F, H, W, cin), r["w1"], bias=tb, bias_div=T, col_stats=True, out_dtype=torch.bfloat16)
+        else:       # no producer statistics for ragged samples: GroupNorm 2 takes its own pass over an fp32 tensor
+            c1 = ops.conv3x3_ex(h.view(B * F, H, W, cin), r["w1"], bias=tb, bias_div=T)
         h2 = ops.groupnorm(c1.out, None, B, r["g2"], r["b2"], eps, True, stats1=c1.col_stats)
+        o32 = want != "bf16"
+        kw = dict(bias=r["bias2"], col_stats=o32, out_dtype=torch.float32 if o32 else torch.bfloat16, also_bf16=(want == "both"))
         if r["sc"]:
-            c2 = ops.conv3x3_ex(h2.view(B * F, H, W, cout), r["w2"], a2=raw, bias=r["bias2"], col_stats=True)
+            c2 = ops.conv3x3_ex(h2.view(B * F, H, W, cout), r["w2"], a2=raw, **kw)
         else:
-            c2 = ops.conv3x3_ex(h2.view(B * F, H, W, cout), r["w2"], bias=r["bias2"], residual=t1, col_stats=True)
-        return c2.out, c2.col_stats
+            c2 = ops.conv3x3_ex(h2.view(B * F, H, W, cout), r["w2"], residual=t1, **kw)
+        return self._emit(c2, want)
 
-    def _ff(self, t: dict, tok, tok16, rstats, out_rows=None):
+    def _ff(self, t: dict, tok, rstats, out_rows=None):
         """x + FF(LN3(x)) -> bf16 (feeds proj_out only).  attention.py:244,323 + 744-747,791-793.  LN3 is folded into
-        the GEGLU projection, which reads the raw bf16 copy of the token stream."""
-        hid = ops.gemm_ex(tok16, t["ff1_w"], bias=t["ff1_b"], geglu=True, ln=(rstats, t["ff1_cs"], 1e-5)).out
+        the GEGLU projection, which reads the raw bf16 token stream."""
+        hid = ops.gemm_ex(tok, t["ff1_w"], bias=t["ff1_b"], geglu=True, ln=(rstats, t["ff1_cs"], 1e-5)).out
         return ops.gemm_ex(hid, t["ff2_w"], bias=t["ff2_b"], residual=tok, out=out_rows, out_dtype=torch.bfloat16).out
 
-    def _transformer(self, t: dict, x, B, F, H, W, kv, cond_frame):
+    def _transformer(self, t: dict, x, B, F, H, W, kv, cond_frame, want: str = "f32"):
         """SpatialTransformer3D.forward (attention.py:129-145) with its text (:308-327) or temporal (:231-248) block.
-        Token stream: fp32 master copy + bf16 copy + per-row (sum, sumsq), all written by the producing GEMM's epilogue."""
+        The token stream inside the block is bf16 (what the reference computes under autocast: Linear outputs and the
+        residual adds are low precision there too) with per-row (sum, sumsq) written by the producing GEMM's epilogue for
+        the LayerNorm folded into the next projection; the block input / output (the UNet's residual stream) stay fp32."""
         C, heads = t["C"], self.cfg.heads
         d = C // heads
         hw, T = H * W, F * H * W
         M = B * T
-        xt, xs = x
+        bf = torch.bfloat16
+        xt, xs = x[:2]
         hn = ops.groupnorm(xt, None, B, t["gn_g"], t["gn_b"], 1e-6, False, stats1=xs)
-        r = ops.gemm_ex(hn, t["pin_w"], bias=t["pin_b"], also_bf16=True, row_stats=True)          # fp32 token stream
-        qkv = ops.gemm_ex(r.out16, t["qkv_w"], bias=t["qkv_b"], out_dtype=torch.bfloat16,
-                          ln=(r.row_stats, t["qkv_cs"], 1e-5)).out                                 # [M, 3C]
+        r = ops.gemm_ex(hn, t["pin_w"], bias=t["pin_b"], out_dtype=bf, row_stats=True)
+        qkv = ops.gemm_ex(r.out, t["qkv_w"], bias=t["qkv_b"], out_dtype=bf, ln=(r.row_stats, t["qkv_cs"], 1e-5)).out     # [M, 3C]
         if t["temporal"]:
             ops.rope_inplace(qkv, T, heads, d, 0, C, t["freqs"])
             att = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], mode=ops.ATTN_SCTA, heads=heads, n_outer=B,
@@ -327,26 +350,28 @@ class SeerUNet(nn.Module):
         else:
             att = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], mode=ops.ATTN_SPATIAL, heads=heads,
                                 n_outer=B * F, Lq=hw, Lk=hw)
-        r = ops.gemm_ex(att, t["o1_w"], bias=t["o1_b"], residual=r.out, also_bf16=True, row_stats=True)
+        r = ops.gemm_ex(att, t["o1_w"], bias=t["o1_b"], residual=r.out, out_dtype=bf, row_stats=True)
         if not t["temporal"]:
-            q2 = ops.gemm_ex(r.out16, t["q2_w"], bias=t["q2_b"], out_dtype=torch.bfloat16, ln=(r.row_stats, t["q2_cs"], 1e-5)).out
+            q2 = ops.gemm_ex(r.out, t["q2_w"], bias=t["q2_b"], out_dtype=bf, ln=(r.row_stats, t["q2_cs"], 1e-5)).out
             Lk = kv.shape[0] // (B * F)
             att2 = ops.attention(q2, kv[:, :C], kv[:, C:], mode=ops.ATTN_CROSS, heads=heads, n_outer=B * F, Lq=hw, Lk=Lk)
-            r = ops.gemm_ex(att2, t["o2_w"], bias=t["o2_b"], residual=r.out, also_bf16=True, row_stats=True)
-        tok, tok16, rstats = r.out, r.out16, r.row_stats
+            r = ops.gemm_ex(att2, t["o2_w"], bias=t["o2_b"], residual=r.out, out_dtype=bf, row_stats=True)
+        tok, rstats = r.out, r.row_stats
         if t["temporal"] and cond_frame > 0:
             # the first cond_frame frames of every clip bypass the feed-forward (attention.py:240-246)
-            y = torch.empty((M, C), device=xt.device, dtype=torch.bfloat16)
+            y = torch.empty((M, C), device=xt.device, dtype=bf)
             c0 = min(cond_frame, F) * hw
             for b in range(B):
                 lo, mid, hi = b * T, b * T + c0, (b + 1) * T
-                y[lo:mid] = tok16[lo:mid]
+                y[lo:mid] = tok[lo:mid]
                 if mid < hi:
-                    self._ff(t, tok[mid:hi], tok16[mid:hi], rstats[:, mid:hi].contiguous(), out_rows=y[mid:hi])
+                    self._ff(t, tok[mid:hi], rstats[:, mid:hi].contiguous(), out_rows=y[mid:hi])
         else:
-            y = self._ff(t, tok, tok16, rstats)
-        o = ops.gemm_ex(y, t["pout_w"], bias=t["pout_b"], residual=xt, col_stats=True)
-        return o.out, o.col_stats
+            y = self._ff(t, tok, rstats)
+        o32 = want != "bf16"
+        o = ops.gemm_ex(y, t["pout_w"], bias=t["pout_b"], residual=xt, col_stats=o32, also_bf16=(want == "both"),
+                        out_dtype=torch.float32 if o32 else bf)
+        return self._emit(o, want)
 
     def _cross_layers(self, pk: dict) -> List[dict]:
         return [a for blk in pk["down"] for a in blk["attn"]] + [pk["mid"]["attn"]] + [a for blk in pk["up"] for a in blk["attn"]]
@@ -354,6 +379,9 @@ class SeerUNet(nn.Module):
     def compute_context_kv(self, context: torch.Tensor, out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
         """K/V projections of the text context for every cross-attention layer: [B*F*L, 2C] bf16 each
         (attention.py:517-518 with the per-frame context of :314-315).  `out` recomputes into existing buffers."""
+        if self.device.type == "cuda" and torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):
+                return self.compute_context_kv(context, out)
         if self.precision == "fp32":
             from . import unet_fp32
             if self._packed32 is None:
@@ -384,6 +412,14 @@ class SeerUNet(nn.Module):
     @torch.no_grad()
     def forward(self, sample: torch.Tensor, timestep, context: Optional[torch.Tensor] = None, cond_frame: int = 0,
                 return_attn: bool = False, encoder_hidden_states: Optional[torch.Tensor] = None) -> torch.Tensor:
+        # every kernel launches on the current stream of the CURRENT device and tensor maps are encoded in its context:
+        # make the model's device current for the whole evaluation (a module on cuda:1 called while cuda:0 is current)
+        if self.device.type == "cuda":
+            with torch.cuda.device(self.device):
+                return self._forward(sample, timestep, context, cond_frame, return_attn, encoder_hidden_states)
+        return self._forward(sample, timestep, context, cond_frame, return_attn, encoder_hidden_states)
+
+    def _forward(self, sample, timestep, context, cond_frame, return_attn, encoder_hidden_states) -> torch.Tensor:
         if context is None:
             context = encoder_hidden_states
         if context is None:
@@ -427,23 +463,29 @@ class SeerUNet(nn.Module):
         kvs = iter(self._context_kv(pk, context.to(dev)))
 
         # 2. conv_in -> token-major fp32 stream
-        x = ops.conv_in(sample.contiguous(), pk["conv_in_w"], pk["conv_in_b"], col_stats=True)   # (tensor, GroupNorm col_stats)
+        x = ops.conv_in(sample.contiguous(), pk["conv_in_w"], pk["conv_in_b"], col_stats=True) + (None,)   # (fp32, col_stats, bf16)
         h, w = H, W
         skips: List[tuple] = [x]
         n = len(cfg.block_out_channels)
         # 3. down
         for i, blk in enumerate(pk["down"]):
+            nres = len(blk["res"])
             for j, r in enumerate(blk["res"]):
-                x = self._resnet(r, x, None, B, F, h, w, temb_all)
+                # the block's last tensor also feeds the stride-2 conv, which reads bf16
+                last = "both" if (blk["down"] is not None and j == nres - 1) else "f32"
+                x = self._resnet(r, x, None, B, F, h, w, temb_all, want="f32" if blk["attn"] else last)
                 if blk["attn"]:
                     x = self._transformer(blk["attn"][j], x, B, F, h, w, next(kvs), cond_frame)
-                    x = self._transformer(blk["tattn"][j], x, B, F, h, w, None, cond_frame)
+                    x = self._transformer(blk["tattn"][j], x, B, F, h, w, None, cond_frame, want=last)
                 skips.append(x)
             if blk["down"] is not None:
                 wd, bd = blk["down"]
-                cols = ops.im2col3x3(x[0].view(B * F, h, w, x[0].shape[1]), stride=2)
-                dn = ops.gemm_ex(cols, wd, bias=bd, col_stats=True)
-                x = (dn.out, dn.col_stats)
+                # Downsample3D (resnet.py:95-104): stride-2 / pad-1 conv as an implicit GEMM over strided TMA boxes
+                dn = ops.gemm_ex(None, wd, x_img=x[2].view(B * F, h, w, x[2].shape[1]), conv_stride=2, bias=bd, col_stats=True)
+                if dn is None:       # geometry outside the TMA-box tiling: explicit im2col (still seer_b200 kernels)
+                    cols = ops.im2col3x3(x[2].view(B * F, h, w, x[2].shape[1]), stride=2)
+                    dn = ops.gemm_ex(cols, wd, bias=bd, col_stats=True)
+                x = (dn.out, dn.col_stats, None)
                 h, w = h // 2, w // 2
                 skips.append(x)
         # 4. mid
@@ -454,17 +496,45 @@ class SeerUNet(nn.Module):
         x = self._resnet(m["res"][1], x, None, B, F, h, w, temb_all)
         # 5. up
         for i, blk in enumerate(pk["up"]):
+            nres = len(blk["res"])
             for j, r in enumerate(blk["res"]):
-                x = self._resnet(r, x, skips.pop(), B, F, h, w, temb_all)
+                # the block's last tensor feeds only the Upsample3D conv: bf16, no statistics
+                last = "bf16" if (blk["up"] is not None and j == nres - 1) else "f32"
+                x = self._resnet(r, x, skips.pop(), B, F, h, w, temb_all, want="f32" if blk["attn"] else last)
                 if blk["attn"]:
                     x = self._transformer(blk["attn"][j], x, B, F, h, w, next(kvs), cond_frame)
-                    x = self._transformer(blk["tattn"][j], x, B, F, h, w, None, cond_frame)
+                    x = self._transformer(blk["tattn"][j], x, B, F, h, w, None, cond_frame, want=last)
             if blk["up"] is not None:
-                wu, bu = blk["up"]
-                up = ops.upsample2x(x[0], B * F, h, w)
+                x = self._upsample_conv(blk["up"], x[2], B, F, h, w)
                 h, w = 2 * h, 2 * w
-                uc = ops.conv3x3_ex(up, wu, bias=bu, col_stats=True)
-                x = (uc.out, uc.col_stats)
         # 6. out: GN -> SiLU -> conv_out, fp32, back to (B, C, F, H, W)
         y = ops.groupnorm(x[0], None, B, pk["gno_g"], pk["gno_b"], cfg.norm_eps, True, out_dtype=torch.float32, stats1=x[1])
         return ops.conv_out(y, pk["conv_out_w"], pk["conv_out_b"], B, F, h, w)
+
+    def _upsample_conv(self, up: tuple, x16: torch.Tensor, B: int, F: int, h: int, w: int):
+        """Upsample3D.forward (resnet.py:47-61): nearest 2x + conv3x3, computed as four 2x2-tap convs on the LOW-res image
+        (packing.pack_upsample_phases) whose epilogues scatter their rows to the four pixel phases of the output — the
+        upsampled tensor is never materialised and 5/9 of the FLOPs disappear."""
+        wu, bu, phases = up
+        C = x16.shape[1]
+        n_img = B * F
+        M = n_img * 4 * h * w
+        img = x16.view(n_img, h, w, C)
+        if (w & (w - 1)) == 0 and (F * h * w) % 32 == 0:        # 32-row statistics slabs must not straddle samples
+            out = torch.empty((M, wu.shape[0]), device=x16.device, dtype=torch.float32)
+            st = torch.empty((M // 32, wu.shape[0], 2), device=x16.device, dtype=torch.float32)
+            ok = True
+            for ph in range(4):
+                py, px = ph >> 1, ph & 1
+                r = ops.gemm_ex(None, phases[ph], x_img=img, conv_taps=(2, 2, px - 1, py - 1), up_phase=1 + ph, bias=bu, out=out,
+                                col_stats=st)
+                if r is None:
+                    ok = False
+                    break
+            if ok:
+                return (out, st, None)
+        # geometry outside the TMA-box tiling: materialise the upsampled image (nearest-2x of a bf16 tensor via torch indexing
+        # would be a PyTorch op on the product path, so go through the fp32 upsample kernel)
+        up_img = ops.upsample2x(x16.float(), n_img, h, w)
+        uc = ops.conv3x3_ex(up_img, wu, bias=bu, col_stats=True)
+        return (uc.out, uc.col_stats, None)

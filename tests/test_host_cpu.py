@@ -227,3 +227,23 @@ def test_decode_latents_matches_the_reference_expressions():
     assert torch.equal(out, want)
     assert smp.kw["unconditional_conditioning"] is None and smp.kw["S"] == 30 and smp.kw["batch_size"] == 2     # scale 1 drops uc
     assert smp.kw["shape"] == (4, 5, 4, 4) and smp.kw["eta"] == 0.0 and smp.kw["is_3d"] is True and smp.kw["x_T"] == "xT"
+
+
+def test_upsample_phase_weights_equal_nearest2x_conv():
+    """packing.pack_upsample_phases: nearest-2x + conv3x3 (resnet.py:47-61) == four 2x2-tap convs on the low-res image."""
+    import torch.nn.functional as F
+    from seervideoldm_b200.packing import pack_upsample_phases
+    g = torch.Generator().manual_seed(5)
+    n, C, Co, H, W = 2, 64, 8, 5, 4
+    x = torch.randn(n, C, H, W, generator=g, dtype=torch.double)
+    w = torch.randn(Co, C, 3, 3, generator=g)
+    w = w.bfloat16().float() * 0.25            # values whose pairwise / 4-way sums stay exactly representable in bf16
+    w = (w * 64).round() / 64
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w.double(), padding=1)
+    out = torch.empty_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for ph, wp in enumerate(pack_upsample_phases(w)):
+        py, px = ph >> 1, ph & 1
+        wk = wp.double().reshape(Co, C // 64, 2, 2, 64).permute(0, 1, 4, 2, 3).reshape(Co, C, 2, 2)
+        out[:, :, py::2, px::2] = F.conv2d(xp[:, :, py:py + H + 1, px:px + W + 1], wk)
+    assert torch.allclose(out, ref, rtol=1e-12, atol=1e-12)

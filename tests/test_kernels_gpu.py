@@ -193,6 +193,110 @@ def test_conv3x3_statistics_and_dual():
     assert torch.allclose(r.col_stats[..., 0].double(), slabs.sum(1), rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 320, 320), (3000, 640, 640), (1000, 1280, 1280), (262144 // 8, 320, 1280)])
+def test_gemm_bf16_token_stream_kinds(M, N, K):
+    """The epilogue kinds of the bf16 token stream inside a transformer block: proj_in (bf16 out + LayerNorm row sums),
+    to_out (bf16 residual in, bf16 out, row sums), FF out (bf16 residual, bf16 out).  Row sums are taken from the fp32
+    values before rounding."""
+    a = rn(43, M, K).bfloat16()
+    w = rn(44, N, K, scale=K ** -0.5).bfloat16()
+    bias, res16 = rn(45, N), rn(46, M, N).bfloat16()
+    base = a.double() @ w.double().t() + bias.double()
+    r = ops.gemm_ex(a, w, bias=bias, out_dtype=torch.bfloat16, row_stats=True)
+    assert r.out.dtype == torch.bfloat16 and rel(r.out.float(), base.float()) < 4e-3
+    rs = r.row_stats.double().sum(0)
+    assert torch.allclose(rs[:, 0], base.sum(1), rtol=1e-4, atol=2e-3)
+    assert torch.allclose(rs[:, 1], (base * base).sum(1), rtol=1e-4, atol=2e-3)
+    full = base + res16.double()
+    r = ops.gemm_ex(a, w, bias=bias, residual=res16, out_dtype=torch.bfloat16, row_stats=True)
+    assert rel(r.out.float(), full.float()) < 4e-3
+    rs = r.row_stats.double().sum(0)
+    assert torch.allclose(rs[:, 0], full.sum(1), rtol=1e-4, atol=2e-3)
+    assert torch.allclose(rs[:, 1], (full * full).sum(1), rtol=1e-4, atol=2e-3)
+    r2 = ops.gemm_ex(a, w, bias=bias, residual=res16, out_dtype=torch.bfloat16)
+    assert torch.equal(r2.out, r.out)            # same values with and without the statistics output
+
+
+def test_conv3x3_bf16_out_with_statistics():
+    """conv1 of a ResNet block: bf16 output (read only by GroupNorm 2), column sums from the fp32 accumulators; the
+    GroupNorm that consumes the bf16 tensor through those statistics equals GroupNorm of the fp32 conv output."""
+    B, Fr, H, Cin, Cout = 2, 3, 16, 128, 320
+    n_img = B * Fr
+    x = rn(47, n_img, H, H, Cin).bfloat16()
+    w = rn(48, Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5)
+    temb = rn(49, B, Cout)
+    from seervideoldm_b200.packing import pack_conv3x3
+    wp = pack_conv3x3(w).to(DEV)
+    T = Fr * H * H
+    r32 = ops.conv3x3_ex(x, wp, bias=temb, bias_div=T, col_stats=True)
+    r16 = ops.conv3x3_ex(x, wp, bias=temb, bias_div=T, col_stats=True, out_dtype=torch.bfloat16)
+    assert r16.out.dtype == torch.bfloat16 and torch.equal(r16.out, r32.out.bfloat16())
+    assert torch.equal(r16.col_stats, r32.col_stats)
+    g, b = rn(50, Cout), rn(51, Cout)
+    y32 = ops.groupnorm(r32.out, None, B, g, b, 1e-5, True, stats1=r32.col_stats)
+    y16 = ops.groupnorm(r16.out, None, B, g, b, 1e-5, True, stats1=r16.col_stats)
+    assert rel(y16.float(), y32.float()) < 6e-3
+    ref = F.silu(F.group_norm(r32.out.reshape(B, T, Cout).permute(0, 2, 1).double(), 32, g.double(), b.double(), 1e-5))
+    assert rel(y16.float(), ref.permute(0, 2, 1).reshape(B * T, Cout).float()) < 8e-3
+
+
+@pytest.mark.parametrize("n_img,H,C,Cout", [(3, 16, 64, 160), (4, 32, 320, 320), (32, 8, 192, 320), (6, 16, 640, 640), (256, 8, 128, 160)])
+def test_conv3x3_stride2_implicit(n_img, H, C, Cout):
+    """Downsample3D (resnet.py:95-104): stride 2, pad 1, read straight from the full-resolution bf16 image through a TMA
+    box with traversal stride 2 — against F.conv2d and against the explicit im2col path."""
+    from seervideoldm_b200.packing import pack_conv3x3
+    x = rn(52, n_img, H, H, C).bfloat16()
+    w = rn(53, Cout, C, 3, 3, scale=(9 * C) ** -0.5)
+    b = rn(54, Cout)
+    wp = pack_conv3x3(w).to(DEV)
+    r = ops.gemm_ex(None, wp, x_img=x, conv_stride=2, bias=b, col_stats=True)
+    assert r is not None and r.out.shape == (n_img * (H // 2) ** 2, Cout)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), b, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    assert rel(r.out, ref) < 2e-5
+    cols = ops.im2col3x3(x, stride=2)
+    assert rel(r.out, ops.gemm(cols, wp, bias=b)) < 2e-6
+    slabs = r.out.double().reshape(-1, 32, Cout)
+    assert torch.allclose(r.col_stats[..., 0].double(), slabs.sum(1), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("n_img,H,C,Cout", [(4, 8, 64, 160), (6, 16, 128, 320), (32, 4, 192, 160), (5, 16, 640, 640), (16, 8, 1280, 1280)])
+def test_upsample_conv_phases(n_img, H, C, Cout):
+    """Upsample3D (resnet.py:47-61): nearest 2x + conv3x3 as four 2x2-tap convs on the low-res image whose epilogues
+    scatter the rows to the four pixel phases — against F.conv2d(F.interpolate(x)) with the ORIGINAL 3x3 weights."""
+    from seervideoldm_b200.packing import pack_upsample_phases
+    x = rn(55, n_img, H, H, C).bfloat16()
+    w = rn(56, Cout, C, 3, 3, scale=(9 * C) ** -0.5)
+    b = rn(57, Cout)
+    phases = [p.to(DEV) for p in pack_upsample_phases(w.cpu())]
+    M = n_img * 4 * H * H
+    out = torch.full((M, Cout), float("nan"), device=DEV)
+    st = torch.full((M // 32, Cout, 2), float("nan"), device=DEV)
+    for ph in range(4):
+        r = ops.gemm_ex(None, phases[ph], x_img=x, conv_taps=(2, 2, (ph & 1) - 1, (ph >> 1) - 1), up_phase=1 + ph, bias=b, out=out,
+                        col_stats=st)
+        assert r is not None
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    assert torch.isfinite(out).all() and torch.isfinite(st).all()
+    # the phase weights are sums of 3x3 taps rounded to bf16 ONCE (the reference rounds each tap): bf16-weight-level agreement
+    assert rel(out, ref.float()) < 4e-3
+    # ... and exact (accumulation order only) against the same rounded phase weights applied as a dense fp32 conv
+    outp = torch.empty(n_img, 2 * H, 2 * H, Cout, device=DEV, dtype=torch.double)
+    xp = F.pad(x.double().permute(0, 3, 1, 2), (1, 1, 1, 1))
+    for ph in range(4):
+        py, px = ph >> 1, ph & 1
+        wk = phases[ph].double().reshape(Cout, C // 64, 2, 2, 64).permute(0, 1, 4, 2, 3).reshape(Cout, C, 2, 2)
+        o = F.conv2d(xp[:, :, py:py + H + 1, px:px + H + 1], wk, b.double())
+        outp[:, py::2, px::2] = o.permute(0, 2, 3, 1)
+    assert rel(out, outp.reshape(-1, Cout).float()) < 2e-5
+    # statistics: slab s of the output holds 32 consecutive OUTPUT-tensor rows?  No — slab 4*(m/32)+phase holds the phase rows of
+    # 32 consecutive low-res pixels; what GroupNorm needs is that each sample's slabs sum to the sample's column sums
+    S = st.double().reshape(n_img, -1, Cout, 2).sum(1)
+    v = out.double().reshape(n_img, -1, Cout)
+    assert torch.allclose(S[..., 0], v.sum(1), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(S[..., 1], (v * v).sum(1), rtol=1e-5, atol=1e-2)
+
+
 def test_gemm_rejects_bad_shapes():
     a = rn(1, 128, 100).bfloat16()
     w = rn(2, 160, 100).bfloat16()
