@@ -32,6 +32,11 @@ extern "C" {
 #define SEER_ATTN_FRAME 3 /* causal attention along the frame axis, one sequence per (clip, token): FSText temporal blocks */
 
 const char* seer_b200_version(void);
+/* Debug hooks: a description of the kernel the dispatcher chose for the calling thread's last seer_b200_attention /
+ * seer_b200_gemm_ex launch ("attention_tc_persist_kernel<40> tcgen05", "attention_kernel<D> mma.sync (legacy path)",
+ * "gemm_tc_kernel<160,2> tcgen05 stages=5 ..."); tests assert the tcgen05 paths run for every benchmark shape. */
+const char* seer_b200_debug_last_attention(void);
+const char* seer_b200_debug_last_gemm(void);
 
 /* out[M,N] = A[M,K1] (|| A2[M,K2]) * Wt[N,K1+K2]^T + bias[(row/bias_div), :] (+ residual), tcgen05/TMEM/TMA.
  * Replaces nn.Linear / 1x1 InflatedConv3d: seer/models/attention.py:484-489 (to_q/k/v/out), :111,126 (proj_in/out),

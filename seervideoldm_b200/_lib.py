@@ -49,6 +49,8 @@ SIGNATURES = {
     "seer_b200_groupnorm_from_stats": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _i, _vp, _vp]),
     "seer_b200_groupnorm_from_stats_ex": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _i, _vp, _vp]),
     "seer_b200_version": (_c.c_char_p, []),
+    "seer_b200_debug_last_attention": (_c.c_char_p, []),
+    "seer_b200_debug_last_gemm": (_c.c_char_p, []),
     "seer_b200_gemm_bf16": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "seer_b200_conv3x3_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "seer_b200_groupnorm_workspace_floats": (_i, [_i, _i]),

@@ -771,10 +771,7 @@ static int at_map_heads_5d(CUtensorMap* tm, const void* base, uint64_t n_frames,
   return r == CUDA_SUCCESS ? SEER_OK : SEER_EUNSUPPORTED;
 }
 
-static int env_flag(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
+static int env_flag(const char* name, int dflt) { return env_cached(name, dflt); }
 
 }  // namespace seer
 
@@ -817,7 +814,10 @@ extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ld
     }
     if (n_problems > 65535) tc = false;
   }
-  if (!tc) return attention_mma_launch(q, ldq, k, ldk, v, ldv, o, ldo, mode, heads, head_dim, n_outer, Lq, Lk, F, H, W, stream);
+  if (!tc) {
+    debug_note_attention("attention_kernel<D> mma.sync (legacy path)");
+    return attention_mma_launch(q, ldq, k, ldk, v, ldv, o, ldo, mode, heads, head_dim, n_outer, Lq, Lk, F, H, W, stream);
+  }
 
   p.o = (__nv_bfloat16*)o; p.ldo = ldo;
   p.mode = mode; p.heads = heads;
@@ -848,6 +848,7 @@ extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ld
                                   tv, p, n_problems, nq_tiles);
       if (le != cudaSuccess) return (int)le;
       SEER_LAUNCH_CHECK();
+      debug_note_attention("attention_tc_persist_kernel<40> tcgen05");
       return SEER_OK;
     }
     static bool warned = false;
@@ -871,5 +872,6 @@ extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ld
   dim3 grid(nq_tiles, n_problems);
   { cudaError_t le__ = launch_pdl(attention_tc_kernel<40>, grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream, tq, tk, tv, p); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
+  debug_note_attention("attention_tc_kernel<40> tcgen05 (one tile per CTA)");
   return SEER_OK;
 }

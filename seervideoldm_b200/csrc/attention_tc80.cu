@@ -544,6 +544,7 @@ static int a8_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
                               n_problems, nq_tiles);
   if (le != cudaSuccess) return (int)le;
   SEER_LAUNCH_CHECK();
+  debug_note_attention(D == 40 ? "attention_tc80_kernel<40> tcgen05" : (D == 80 ? "attention_tc80_kernel<80> tcgen05" : "attention_tc80_kernel<160> tcgen05"));
   return SEER_OK;
 }
 

@@ -52,6 +52,13 @@ inline bool pdl_enabled() {
   return v != 0;
 }
 
+// Tuning / A-B switches (SEER_*) are read from the environment ONCE per process (first use), not on every launch.
+int env_cached(const char* name, int dflt);
+// Debug hooks (capi.cu): which kernel the dispatchers picked for the calling thread's last launch — tests assert that the
+// tcgen05 paths (not the mma.sync fallback) run for every shape of the benchmark (seer_b200_debug_last_*).
+void debug_note_attention(const char* what);
+void debug_note_gemm(int bn, int cg, int stages, int nepi, int ring, int bstat, int epi_spec, int mode);
+
 // <<<grid, block, smem, stream>>> with the PDL attribute (the kernel must start with pdl_wait())
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

@@ -317,10 +317,7 @@ struct Plan {
   int bn, cg, stages, nepi, ring, slot_bytes, bstat, tiles_n, num_tiles, grid, smem_bytes;
 };
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
+static int env_int(const char* name, int dflt) { return env_cached(name, dflt); }
 
 static inline int conv_ntaps(const SeerGemmDesc& d) {
   return (d.conv_taps_w > 0 && d.conv_taps_h > 0) ? d.conv_taps_w * d.conv_taps_h : 9;
@@ -442,6 +439,7 @@ static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, const Plan&
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, maps[0], maps[1], maps[2], maps[3], p);
   if (e != cudaSuccess) return (int)e;
+  debug_note_gemm(BN, CG, pl.stages, pl.nepi, pl.ring, pl.bstat, p.epi_spec, p.mode);
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

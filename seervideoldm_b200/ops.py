@@ -412,3 +412,12 @@ def rope_ex(qk: torch.Tensor, pos_div: int, pos_mod: int, heads: int, head_dim: 
     _cuda(qk, "qk")
     _ops.rope(qk, int(pos_div), int(pos_mod), int(heads), int(head_dim), int(q_col), int(k_col), freqs)
     _count()
+
+
+def last_attention_kernel() -> str:
+    """Which kernel seer_b200_attention dispatched on this thread's last call (debug hook, include/seer_b200.h)."""
+    return _lib.lib().seer_b200_debug_last_attention().decode()
+
+
+def last_gemm_kernel() -> str:
+    return _lib.lib().seer_b200_debug_last_gemm().decode()

@@ -247,3 +247,34 @@ def test_upsample_phase_weights_equal_nearest2x_conv():
         wk = wp.double().reshape(Co, C // 64, 2, 2, 64).permute(0, 1, 4, 2, 3).reshape(Co, C, 2, 2)
         out[:, :, py::2, px::2] = F.conv2d(xp[:, :, py:py + H + 1, px:px + W + 1], wk)
     assert torch.allclose(out, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_torch_op_library_registration():
+    """the C ABI is registered as a torch custom-op library (`torch.ops.seer_b200.*`): every op has a schema with
+    caller-owned mutable outputs, a CUDA kernel only (CPU tensors fail in the dispatcher — no CPU path) and a fake kernel."""
+    import torch
+    from seervideoldm_b200 import ops, torch_ops  # noqa: F401
+    want = {"gemm_ex", "gemm_row_parts", "groupnorm", "groupnorm_from_stats", "layernorm", "attention", "scta_row_index", "rope",
+            "timestep_embedding", "small_linear", "conv_in", "conv_out", "upsample2x", "im2col3x3", "cast_bf16", "cfg_ddim_update",
+            "split3", "geglu_f32"}
+    assert want <= set(torch_ops.OP_NAMES)
+    for name in want:
+        op = getattr(torch.ops.seer_b200, name).default
+        assert torch._C._dispatch_has_kernel_for_dispatch_key(op.name(), "CUDA"), name
+        assert not torch._C._dispatch_has_kernel_for_dispatch_key(op.name(), "CPU"), name
+    schema = str(torch.ops.seer_b200.gemm_ex.default._schema)
+    assert "Tensor(a!)? out_f32" in schema and "Tensor(d!)? row_stats_out" in schema and schema.endswith("-> int")
+    # a CPU tensor never reaches a kernel: the Python API rejects it, the raw op has no CPU dispatch entry
+    with pytest.raises(ValueError):
+        ops.cast_bf16(torch.zeros(8))
+    with pytest.raises(NotImplementedError):
+        torch.ops.seer_b200.cast_bf16(torch.zeros(8), torch.zeros(8, dtype=torch.bfloat16))
+    # fake (meta) kernels: the ops trace under FakeTensorMode without launching anything
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        a = torch.empty(256, 64, dtype=torch.bfloat16, device="cuda")
+        w = torch.empty(128, 64, dtype=torch.bfloat16, device="cuda")
+        out = torch.empty(256, 128, dtype=torch.float32, device="cuda")
+        rc = torch.ops.seer_b200.gemm_ex(a, None, None, w, None, 0, None, out, None, False, None, None, None, 0.0, None, 1, [], 0)
+        assert rc == 0
+        torch.ops.seer_b200.cast_bf16(torch.empty(8, device="cuda"), torch.empty(8, dtype=torch.bfloat16, device="cuda"))

@@ -291,8 +291,9 @@ def test_upsample_conv_phases(n_img, H, C, Cout):
     assert rel(out, outp.reshape(-1, Cout).float()) < 2e-5
     # statistics: slab s of the output holds 32 consecutive OUTPUT-tensor rows?  No — slab 4*(m/32)+phase holds the phase rows of
     # 32 consecutive low-res pixels; what GroupNorm needs is that each sample's slabs sum to the sample's column sums
-    S = st.double().reshape(n_img, -1, Cout, 2).sum(1)
-    v = out.double().reshape(n_img, -1, Cout)
+    grp = max(1, 32 // (H * H))              # a 32-pixel slab spans `grp` whole images when an image has fewer than 32 pixels
+    S = st.double().reshape(n_img // grp, -1, Cout, 2).sum(1)
+    v = out.double().reshape(n_img // grp, -1, Cout)
     assert torch.allclose(S[..., 0], v.sum(1), rtol=1e-5, atol=1e-2)
     assert torch.allclose(S[..., 1], (v * v).sum(1), rtol=1e-5, atol=1e-2)
 
