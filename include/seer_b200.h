@@ -37,6 +37,9 @@ const char* seer_b200_version(void);
  * "gemm_tc_kernel<160,2> tcgen05 stages=5 ..."); tests assert the tcgen05 paths run for every benchmark shape. */
 const char* seer_b200_debug_last_attention(void);
 const char* seer_b200_debug_last_gemm(void);
+/* The SEER_* tuning switches are read from the environment once per process; tuning tools override (clear = 0) or reset to the
+ * built-in default (clear = 1) a switch inside the running process with this. */
+void seer_b200_debug_setenv(const char* name, int value, int clear);
 
 /* out[M,N] = A[M,K1] (|| A2[M,K2]) * Wt[N,K1+K2]^T + bias[(row/bias_div), :] (+ residual), tcgen05/TMEM/TMA.
  * Replaces nn.Linear / 1x1 InflatedConv3d: seer/models/attention.py:484-489 (to_q/k/v/out), :111,126 (proj_in/out),

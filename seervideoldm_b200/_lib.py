@@ -51,6 +51,7 @@ SIGNATURES = {
     "seer_b200_version": (_c.c_char_p, []),
     "seer_b200_debug_last_attention": (_c.c_char_p, []),
     "seer_b200_debug_last_gemm": (_c.c_char_p, []),
+    "seer_b200_debug_setenv": (None, [_c.c_char_p, _i, _i]),
     "seer_b200_gemm_bf16": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "seer_b200_conv3x3_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "seer_b200_groupnorm_workspace_floats": (_i, [_i, _i]),

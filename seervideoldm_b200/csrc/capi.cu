@@ -6,22 +6,41 @@
 
 namespace seer {
 
+struct EnvEntry { char name[48]; int val; int overridden; };
+static EnvEntry g_env[64];
+static int g_env_n = 0;
+static std::mutex g_env_mu;
+
 int env_cached(const char* name, int dflt) {
-  struct Entry { char name[48]; int val; };
-  static Entry tab[64];
-  static int n = 0;
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lock(mu);
-  for (int i = 0; i < n; ++i)
-    if (strcmp(tab[i].name, name) == 0) return tab[i].val;
+  std::lock_guard<std::mutex> lock(g_env_mu);
+  for (int i = 0; i < g_env_n; ++i)
+    if (strcmp(g_env[i].name, name) == 0) return g_env[i].overridden == 2 ? dflt : g_env[i].val;
   const char* v = getenv(name);
-  const int val = v && *v ? atoi(v) : dflt;
-  if (n < 64 && strlen(name) < sizeof(tab[0].name)) {
-    strcpy(tab[n].name, name);
-    tab[n].val = val;
-    ++n;
+  const bool set = v && *v;
+  if (g_env_n < 64 && strlen(name) < sizeof(g_env[0].name)) {
+    strcpy(g_env[g_env_n].name, name);
+    g_env[g_env_n].val = set ? atoi(v) : 0;
+    g_env[g_env_n].overridden = set ? 1 : 2;      // 2: not set -> every caller's own default applies
+    ++g_env_n;
   }
-  return val;
+  return set ? atoi(v) : dflt;
+}
+
+// tuning tools (tools/gemm_bench.py --sweep): override / clear a cached switch inside the running process
+static void env_override(const char* name, int value, int clear) {
+  std::lock_guard<std::mutex> lock(g_env_mu);
+  for (int i = 0; i < g_env_n; ++i)
+    if (strcmp(g_env[i].name, name) == 0) {
+      g_env[i].val = value;
+      g_env[i].overridden = clear ? 2 : 1;
+      return;
+    }
+  if (g_env_n < 64 && strlen(name) < sizeof(g_env[0].name)) {
+    strcpy(g_env[g_env_n].name, name);
+    g_env[g_env_n].val = value;
+    g_env[g_env_n].overridden = clear ? 2 : 1;
+    ++g_env_n;
+  }
 }
 
 static thread_local char g_last_attention[96] = "none";
@@ -39,3 +58,4 @@ extern "C" const char* seer_b200_version(void) { return "seer_b200 0.3 (sm_100a)
 extern "C" int seer_b200_gemm_desc_size(void) { return (int)sizeof(SeerGemmDesc); }
 extern "C" const char* seer_b200_debug_last_attention(void) { return seer::g_last_attention; }
 extern "C" const char* seer_b200_debug_last_gemm(void) { return seer::g_last_gemm; }
+extern "C" void seer_b200_debug_setenv(const char* name, int value, int clear) { seer::env_override(name, value, clear); }

@@ -27,7 +27,7 @@ constexpr int MAX_RING = 8;
 constexpr int GEMM_MAX_THREADS = 64 + 32 * MAX_EPI_WARPS;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 1024;
-constexpr int EVEC_FLOATS = 256;                       // per-warp staging of the tile's bias / LN column-sum slices (BN <= 256)
+constexpr int EVEC_FLOATS = 320;                       // per-warp staging of the tile's bias / LN column-sum slices (BN <= 320)
 constexpr int EVEC_BYTES_PER_WARP = 2 * EVEC_FLOATS * 4;
 constexpr int BIAS_ONE_ROW = 0x7fffffff;               // GemmParams::bias_div value meaning "a single bias row"
 
@@ -84,12 +84,19 @@ struct GemmParams {
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile — each
 // CTA stages its own 128 A rows and only HALF of the Wt rows, so the L2 -> SM operand traffic per FLOP drops by
 // 64*(128+BN)/BN -> 64*(128+BN/2)/BN bytes per MMA cycle (the measured limiter of the 1-CTA kernel, profiles/).
+// BN = 320 (N = 320 / 640 launches with a long K: the level-0 / level-1 3x3 convs and FF-out GEMMs): the whole 512-column
+// TMEM holds ONE 256 x 320 pair accumulator — each A stage is multiplied by two N = 160 UMMAs, so the A bytes a CTA pulls from
+// L2 per FLOP halve against 160-wide tiles (the measured limiter of those launches: tensor pipe 63 %, L2 -> SM 47 B/clk/SM).
+// The price is a single-buffered accumulator (the epilogue of tile i no longer overlaps the main loop of tile i + 1), which
+// is why the planner only picks it when the main loop is long (K >= 1280).
 template <int BN, int CG>
 struct GemmCfg {
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NBUF = BN <= 256 ? 2 : 1;                          // TMEM accumulator buffers
+  static constexpr int NMMA = BN <= 256 ? 1 : 2;                          // UMMAs per k-step, N = BN / NMMA each
   static constexpr int TBUF = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // TMEM column stride between the 2 buffers
-  static constexpr int TMEM_COLS = 2 * TBUF;
+  static constexpr int TMEM_COLS = BN <= 256 ? 2 * TBUF : 512;
 };
 
 // byte offset of 16-byte chunk `j` of row `r` inside a TMA-swizzled box whose rows are 128 B / 64 B wide
@@ -312,7 +319,8 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
   uint32_t slot_par = 0;                   // parity of the residual barrier of slot `slot_i` = (g / R) & 1
   for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
     const int m0 = (mb * CG + rank) * BM, n0 = nb * BN;
-    const int buf = it & 1;
+    const int buf = C::NBUF == 2 ? (it & 1) : 0;
+    const uint32_t buf_par = C::NBUF == 2 ? (((uint32_t)it >> 1) & 1) : ((uint32_t)it & 1);   // phase parity of this buffer's barriers
     const int row0 = m0 + q * 32;
     const int row = row0 + lane;
     const bool row_ok = row < p.M;
@@ -358,7 +366,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
         __syncwarp();
       }
       if (!have) {                         // first chunk of a tile whose accumulator was not complete one step ago
-        mbar_wait(&tmem_full_bar[buf], ((uint32_t)it >> 1) & 1);
+        mbar_wait(&tmem_full_bar[buf], buf_par);
         tc_fence_after();
         issue_ld(tmem_addr(buf, c));
         wait_ld();
@@ -388,7 +396,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
         issue_ld(tmem_addr(buf, c + nhalf));
         issued = true;
         if (j + 2 == my_nch) rel_buf = buf;
-      } else if (has_next) {
+      } else if (C::NBUF == 2 && has_next) {
         const int nbuf = buf ^ 1;
         if (__all_sync(0xffffffffu, mbar_try_wait(&tmem_full_bar[nbuf], (((uint32_t)it + 1u) >> 1) & 1))) {
           tc_fence_after();

@@ -138,7 +138,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               tma_load_2d(sA, &tmA2, &full_bar[s], (kb - p.kb_main) * BK, m0);
             }
-            if (!p.bstat) tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
+            if (!p.bstat) {
+#pragma unroll
+              for (int h = 0; h < C::NMMA; ++h)
+                tma_load_2d(sB + h * (C::B_BYTES / C::NMMA), &tmB, &full_bar[s], kb * BK, nb * BN + h * (BN / C::NMMA));
+            }
           } else {
             // both CTAs of the pair fill their own stage; all bytes are counted on the LEADER's full barrier
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_tx);
@@ -154,7 +158,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               tma_load_2d_cg2(sA, &tmA2, fb, (kb - p.kb_main) * BK, m0);
             }
-            if (!p.bstat) tma_load_2d_cg2(sB, &tmB, fb, kb * BK, n0);
+            if (!p.bstat) {
+              // NMMA = 2: UMMA h multiplies accumulator columns [h BN/2, (h+1) BN/2), whose Wt rows are split over the pair
+#pragma unroll
+              for (int h = 0; h < C::NMMA; ++h)
+                tma_load_2d_cg2(sB + h * (C::B_BYTES / C::NMMA), &tmB, fb, kb * BK,
+                                nb * BN + h * (BN / C::NMMA) + rank * (BN / C::NMMA / CG));
+            }
           }
           }
           __syncwarp();
@@ -167,14 +177,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer =====================
     // ===== whole warp loops (uniform control flow, descriptors in uniform registers); one elected lane issues =====
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN / C::NMMA);
+      constexpr uint64_t b_half = (uint64_t)((C::B_BYTES / C::NMMA) >> 4);     // descriptor step to the second UMMA's Wt rows
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
       if (p.bstat) mbar_wait(bpanel_bar, 0);
       for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&tmem_empty_bar[buf], (((uint32_t)it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+        const int buf = C::NBUF == 2 ? (it & 1) : 0;
+        const uint32_t buf_par = C::NBUF == 2 ? (((uint32_t)it >> 1) & 1) : ((uint32_t)it & 1);
+        mbar_wait(&tmem_empty_bar[buf], buf_par ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * C::TBUF);
         for (int kb = 0; kb < p.kb_total; ++kb) {
@@ -187,8 +199,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-            if (CG == 2) umma_bf16_cg2(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-            else umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+#pragma unroll
+            for (int h = 0; h < C::NMMA; ++h) {
+              const uint32_t dt = d_tmem + (uint32_t)(h * (BN / C::NMMA));
+              const uint64_t bd = b_desc + (uint64_t)(k * 2) + (uint64_t)h * b_half;
+              if (CG == 2) umma_bf16_cg2(dt, a_desc + (uint64_t)(k * 2), bd, idesc, (kb | k) != 0);
+              else umma_bf16(dt, a_desc + (uint64_t)(k * 2), bd, idesc, (kb | k) != 0);
+            }
           }
           // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
           if (CG == 2) umma_commit_cg2(&empty_bar[s], 3); else umma_commit(&empty_bar[s]);
@@ -348,16 +365,19 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   const int tiles_m = ceil_div(d.M, BM * cg);
   const int nsm = num_sms() / cg;                  // scheduling units: CTAs or CTA pairs
   // tile width: the widest BN that divides N, unless a narrower one fills the SMs with fewer rounds of tiles
-  static const int cand_plain[] = {256, 192, 160, 128, 64};
+  static const int cand_plain[] = {320, 256, 192, 160, 128, 64};
   static const int cand_geglu[] = {256, 128};
   const int* cand = d.geglu ? cand_geglu : cand_plain;
-  const int ncand = d.geglu ? 2 : 5;
+  const int ncand = d.geglu ? 2 : 6;
+  // 320-wide pair tiles (single-buffered 512-column accumulator): N = 320 / 640 launches with a long main loop
+  const bool allow320 = cg == 2 && Kd >= 1280.0 && N % 256 != 0 && env_int("SEER_GEMM_BN320", 1);
   int best = 0;
   double best_cost = 1e30;
   const int forced = env_int("SEER_GEMM_BN", 0);   // tuning hook
   for (int i = 0; i < ncand; ++i) {
     const int bn = cand[i];
     if (N % bn) continue;
+    if (bn == 320 && !(allow320 || (forced == 320 && cg == 2))) continue;
     if (forced && bn != forced) continue;
     const long tiles = (long)tiles_m * (N / bn);
     const long rounds = (tiles + nsm - 1) / nsm;
@@ -366,7 +386,7 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   }
   if (!best) {
     for (int i = 0; i < ncand && !best; ++i)
-      if (N % cand[i] == 0) best = cand[i];
+      if (N % cand[i] == 0 && cand[i] != 320) best = cand[i];
     if (!best) return SEER_EUNSUPPORTED;
   }
   pl.bn = best;
@@ -380,6 +400,8 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   // 8 epilogue warps (two per scheduler, so one warp's dependent-issue latency hides behind the other's) unless a long
   // main loop (big K) hides the epilogue anyway and the smem is better spent on operand stages
   pl.nepi = env_int("SEER_GEMM_NEPI", (d.geglu || !of || Kd <= 1280.0) ? 8 : 4);
+  // 320-wide tiles are single-buffered: the epilogue is exposed, so it gets all 8 warps (and a short residual ring)
+  if (best == 320) pl.nepi = env_int("SEER_GEMM_NEPI320", 8);
   if (pl.nepi != 4 && pl.nepi != 8) pl.nepi = 4;
   if (best / (d.geglu ? 64 : 32) < 2) pl.nepi = 4;   // every epilogue warp needs at least one chunk
   // B-stationary: the CTA keeps the Wt panel of ONE n-block resident (needs grid % tiles_n == 0) and streams only A —
@@ -396,9 +418,9 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   // (epilogue warps, ring depth, operand stages) by score: operand stages matter most (up to 5), then 8 epilogue warps
   // for the latency-bound bf16-only / GEGLU epilogues, then ring depth
   const int want_nepi = pl.nepi;
-  const int want_ring = rm ? env_int("SEER_EPI_RING", 4) : 1;    // no residual: the slot is only a staging buffer
+  const int want_ring = rm ? (best == 320 ? 2 : env_int("SEER_EPI_RING", 4)) : 1;    // no residual: the slot is only a staging buffer
   int best_score = -1;
-  for (int ne = want_nepi; ne >= 4; ne -= 4) {
+  for (int ne = want_nepi; ne >= (best == 320 ? want_nepi : 4); ne -= 4) {
     for (int rg = want_ring; rg >= (rm ? 2 : 1); --rg) {
       int st = (avail - ne * rg * pl.slot_bytes) / stage_bytes;
       if (st < 2) continue;
@@ -568,7 +590,7 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   p.kb_total = Ktot / 64;
   p.ln_inv_dim = 1.0f / (float)(d.X ? 1 : d.K1);
   if (d.K2) { if ((rc = make_map_bf16_k64(&maps[1], d.A2, d.M, d.K2, d.lda2, BM))) return rc; } else maps[1] = maps[0];
-  if ((rc = make_map_bf16_k64(&maps[2], d.Wt, d.N, Ktot, Ktot, pl.bn / pl.cg))) return rc;
+  if ((rc = make_map_bf16_k64(&maps[2], d.Wt, d.N, Ktot, Ktot, pl.bn / pl.cg / (pl.bn > 256 ? 2 : 1)))) return rc;
   const int n_out = d.geglu ? d.N / 2 : d.N;
   maps[3] = maps[0];
   if (d.residual) {
@@ -585,6 +607,7 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
     case 160: return launch_gemm_cg<160>(maps, p, pl, st);
     case 192: return launch_gemm_cg<192>(maps, p, pl, st);
     case 256: return launch_gemm_cg<256>(maps, p, pl, st);
+    case 320: return pl.cg == 2 ? launch_gemm<320, 2>(maps, p, pl, st) : SEER_EUNSUPPORTED;
     default: return SEER_EUNSUPPORTED;
   }
 }

@@ -421,3 +421,8 @@ def last_attention_kernel() -> str:
 
 def last_gemm_kernel() -> str:
     return _lib.lib().seer_b200_debug_last_gemm().decode()
+
+
+def set_tuning(name: str, value: Optional[int]) -> None:
+    """Override (or with None: reset to the built-in default) one of the library's SEER_* tuning switches in this process."""
+    _lib.lib().seer_b200_debug_setenv(name.encode(), int(value or 0), int(value is None))

@@ -298,6 +298,49 @@ def test_upsample_conv_phases(n_img, H, C, Cout):
     assert torch.allclose(S[..., 1], (v * v).sum(1), rtol=1e-5, atol=1e-2)
 
 
+def test_gemm_320_wide_pair_tiles():
+    """BN = 320 plan (one single-buffered 256 x 320 pair accumulator, two N = 160 UMMAs per A stage) — forced through the
+    tuning hook on small shapes, and as the planner picks it at the level-0 / level-1 shapes of the benchmark."""
+    from seervideoldm_b200.packing import pack_conv3x3
+    try:
+        ops.set_tuning("SEER_GEMM_BN", 320)
+        for (M, N, K) in [(3000, 320, 1280), (2048 + 40, 640, 2560), (512, 640, 128)]:
+            a = rn(58, M, K).bfloat16()
+            w = rn(59, N, K, scale=K ** -0.5).bfloat16()
+            bias, res = rn(60, N), rn(61, M, N)
+            r = ops.gemm_ex(a, w, bias=bias, residual=res, col_stats=True, row_stats=True, also_bf16=True)
+            assert "gemm_tc_kernel<320,2>" in ops.last_gemm_kernel(), ops.last_gemm_kernel()
+            ref = a.float() @ w.float().t() + bias + res
+            assert rel(r.out, ref) < 2e-5 and torch.equal(r.out16, r.out.bfloat16())
+            v = r.out.double()
+            assert torch.allclose(r.row_stats.double().sum(0)[:, 0], v.sum(1), rtol=1e-5, atol=1e-3)
+            S = (M + 31) // 32
+            pad = torch.zeros(S * 32, N, dtype=torch.double, device=DEV)
+            pad[:M] = v
+            assert torch.allclose(r.col_stats[..., 0].double(), pad.reshape(S, 32, N).sum(1), rtol=1e-5, atol=1e-3)
+            r16 = ops.gemm_ex(a, w, bias=bias, residual=res.bfloat16(), out_dtype=torch.bfloat16)
+            assert rel(r16.out.float(), ref - res + res.bfloat16().float()) < 4e-3
+        n_img, H, Cin, Cout, Csc = 12, 16, 128, 320, 192
+        x = rn(62, n_img, H, H, Cin).bfloat16()
+        raw = rn(63, n_img * H * H, Csc).bfloat16()
+        w, wsc = rn(64, Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5), rn(65, Cout, Csc, 1, 1, scale=Csc ** -0.5)
+        b = rn(66, Cout)
+        r = ops.conv3x3_ex(x, pack_conv3x3(w, wsc).to(DEV), a2=raw, bias=b, col_stats=True)
+        assert "gemm_tc_kernel<320,2>" in ops.last_gemm_kernel()
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+        ref = ref + raw.float() @ wsc.reshape(Cout, Csc).bfloat16().float().t()
+        assert rel(r.out, ref) < 2e-5
+    finally:
+        ops.set_tuning("SEER_GEMM_BN", None)
+    # the planner's own choice at a benchmark shape (M = 65536 rows is enough for the persistent loop to wrap many times)
+    M, N, K = 65536, 320, 1280
+    a = rn(67, M, K).bfloat16()
+    w = rn(68, N, K, scale=K ** -0.5).bfloat16()
+    r = ops.gemm_ex(a, w, bias=rn(69, N), out_dtype=torch.bfloat16)
+    print("planner at M=65536 N=320 K=1280:", ops.last_gemm_kernel())
+    assert rel(r.out.float(), a.float() @ w.float().t() + rn(69, N)) < 4e-3
+
+
 def test_gemm_rejects_bad_shapes():
     a = rn(1, 128, 100).bfloat16()
     w = rn(2, 160, 100).bfloat16()

@@ -92,7 +92,7 @@ def main():
     ap.add_argument("--cg", type=int, default=0, help="force CTA-group size 1 or 2 (tuning hook SEER_GEMM_CG)")
     args = ap.parse_args()
     if args.cg:
-        os.environ["SEER_GEMM_CG"] = str(args.cg)
+        ops.set_tuning("SEER_GEMM_CG", args.cg)
     flush = torch.empty(256 * 1024 * 1024, device=DEV, dtype=torch.uint8)
     rows = []
     for name, cfg in shapes():
@@ -101,13 +101,10 @@ def main():
         variants = [0]
         if args.sweep:
             N = cfg.get("N", cfg.get("Cout"))
-            cands = [256, 128] if cfg["kind"] == "geglu" else [256, 192, 160, 128]
+            cands = [256, 128] if cfg["kind"] == "geglu" else [320, 256, 192, 160, 128]
             variants = [0] + [bn for bn in cands if N % bn == 0]
         for bn in variants:
-            if bn:
-                os.environ["SEER_GEMM_BN"] = str(bn)
-            else:
-                os.environ.pop("SEER_GEMM_BN", None)
+            ops.set_tuning("SEER_GEMM_BN", bn if bn else None)
             try:
                 r = run_one(cfg, args.reps, flush)
             except Exception as e:  # noqa: BLE001
@@ -117,7 +114,7 @@ def main():
             rows.append(r)
             print(f"{name:34s} BN={r['bn']!s:>4}  {r['ms'] * 1e3:9.1f} us  {r['tflops']:7.1f} TF/s  {r['gbs']:7.0f} GB/s   "
                   f"({r['gflop']:.0f} GFLOP, {r['mbytes']:.0f} MB)", flush=True)
-    os.environ.pop("SEER_GEMM_BN", None)
+    ops.set_tuning("SEER_GEMM_BN", None)
     if args.out:
         with open(args.out, "w") as f:
             json.dump(rows, f, indent=1)
