@@ -367,7 +367,6 @@ def run_ours(args):
     roof = None
     cpu_base = None
     attention = None
-    eager_base = None
     if rank == 0:
         x_T, x0, c, uc = resident[0]
         x_in = torch.cat([torch.cat([x0, x_T], 2)] * 2)
@@ -420,8 +419,6 @@ def run_ours(args):
             dt = statistics.median(ts)
             cpu_base = {"value": 1.0 / (EVALS * dt), "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                         "sample": cpu_sample_desc() + "; median of 3 after 1 warm-up", "s_per_eval": dt, "nproc": os.cpu_count()}
-            if args.gpu_eager_baseline:
-                eager_base = gpu_eager_baseline(dev)
 
     if rank == 0:
         evals_per_s = EVALS * args.steps * len(batches) / (ms * 1e-3)
@@ -446,8 +443,6 @@ def run_ours(args):
                 "gpu_launches": launches, "roofline": roof, "attention": attention}
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
-        if eager_base is not None:
-            line["gpu_eager_baseline"] = eager_base
         if verify is not None:
             line["verify"] = verify
         print(json.dumps(line))
@@ -455,36 +450,6 @@ def run_ours(args):
         dist.destroy_process_group()
     if verify is not None and not verify["bit_identical"]:
         raise SystemExit("--verify: sharded result differs from the single-GPU recomputation")
-
-
-def gpu_eager_baseline(dev):
-    """Informational (SURVEY §2a's on-box comparison point): the reference algorithm as plain eager PyTorch on the SAME GPU
-    under bf16 autocast — the oracle port with its tensors on CUDA (cuDNN / cuBLAS / eager attention, no fusion, no graph).
-    One CFG evaluation of one clip, median of 3 after 1 warm-up."""
-    import torch
-    from oracle import seer_oracle as so
-    from seervideoldm_b200.config import sd15_config
-    from seervideoldm_b200.weights import random_state_dict
-    try:
-        sd = {k: v.to(dev) for k, v in random_state_dict(sd15_config(sample_size=32), seed=0).items()}
-        x_T, x0, c, uc = (t.to(dev) for t in batch_inputs([0]))
-        x_in = torch.cat([torch.cat([x0, x_T], 2)] * 2)
-        t_in = torch.full((2,), 991, dtype=torch.long, device=dev)
-        c_in = torch.cat([uc, c])
-        ts = []
-        with torch.no_grad(), torch.device(dev), torch.autocast("cuda", dtype=torch.bfloat16):
-            for i in range(4):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                so.unet_forward(sd, x_in, t_in, c_in, 0)
-                torch.cuda.synchronize()
-                if i:
-                    ts.append(time.perf_counter() - t0)
-        dt = statistics.median(ts)
-        return {"value": 1.0 / (EVALS * dt), "unit": UNIT, "s_per_eval": dt, "what": "oracle port on cuda, eager PyTorch under bf16 autocast, "
-                "1 CFG evaluation of 1 clip x 31; informational"}
-    except Exception as e:                                  # informational only: never fail the bench over it
-        return {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
 
 
 def main():
@@ -498,7 +463,6 @@ def main():
                          "stress (attention micro-benchmark at 64x64 latents)")
     ap.add_argument("--verify", action="store_true", help="rank 0 recomputes another rank's clips and requires bit-identity")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gpu-eager-baseline", action="store_true", help="also time the oracle port on the GPU under bf16 autocast (informational)")
     args = ap.parse_args()
     if args.config == "stress":
         if args.impl == "reference":

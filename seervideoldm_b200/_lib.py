@@ -36,6 +36,7 @@ class GemmDesc(ctypes.Structure):
         ("row_stats_in", _vp), ("row_parts_in", _i), ("ln_eps", _f), ("ln_colsum", _vp),
         ("conv_stride", _i), ("conv_taps_w", _i), ("conv_taps_h", _i), ("conv_off_x", _i), ("conv_off_y", _i),
         ("out_up_phase", _i),
+        ("rope_tab", _vp), ("rope_T", _i), ("rope_cols", _i), ("rope_d", _i),
     ]
 
 
@@ -60,6 +61,7 @@ SIGNATURES = {
     "seer_b200_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "seer_b200_scta_row_index": (_i, [_i, _i, _i, _i, _vp, _ip, _ip, _vp]),
     "seer_b200_rope_inplace": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "seer_b200_rope_table": (_i, [_vp, _i, _i, _vp, _vp]),
     "seer_b200_timestep_embedding": (_i, [_vp, _vp, _i, _i, _f, _i, _vp]),
     "seer_b200_small_linear": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "seer_b200_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -62,6 +62,17 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qk, int ld, int M, int t
   }
 }
 
+// (cos, sin) table for the RoPE fused into the q/k/v projection's epilogue: tab[pos][j] = sincosf(pos * freqs[j])
+__global__ void rope_table_kernel(const float* __restrict__ freqs, int half, int T, float2* __restrict__ tab) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * half) return;
+  const int pos = i / half, j = i - pos * half;
+  float sn, cs;
+  sincosf((float)pos * __ldg(freqs + j), &sn, &cs);
+  tab[i] = make_float2(cs, sn);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Timestep embedding (diffusers 0.10.2 Timesteps, flip_sin_to_cos): out[b] = [cos(t*f_i) | sin(t*f_i)],
 // f_i = exp(-ln(10000) * i / (half - shift)).   Call site unet_3d_condition.py:307.
@@ -384,6 +395,13 @@ extern "C" int seer_b200_rope_inplace(void* qk_bf16, int ld, int M, int tokens_p
   SEER_CHECK_ARG(2 * n_freqs <= head_dim && ld % 2 == 0 && q_col % 2 == 0 && k_col % 2 == 0 && head_dim % 2 == 0);
   { cudaError_t le__ = launch_pdl(rope_kernel, grid_for((size_t)M * n_freqs, 256), 256, 0, (cudaStream_t)stream, (__nv_bfloat16*)qk_bf16, ld, M, tokens_per_clip,
                                                                                    heads, head_dim, q_col, k_col, freqs, n_freqs); if (le__ != cudaSuccess) return (int)le__; }
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_rope_table(const float* freqs, int n_freqs, int T, float* out, void* stream) {
+  SEER_CHECK_ARG(freqs && out && n_freqs > 0 && T > 0);
+  { cudaError_t le__ = launch_pdl(rope_table_kernel, ceil_div(T * n_freqs, 256), 256, 0, (cudaStream_t)stream, freqs, n_freqs, T, (float2*)out); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

@@ -32,7 +32,8 @@ constexpr int EVEC_BYTES_PER_WARP = 2 * EVEC_FLOATS * 4;
 constexpr int BIAS_ONE_ROW = 0x7fffffff;               // GemmParams::bias_div value meaning "a single bias row"
 
 // epilogue option bits (template parameter SPEC of the epilogue; -1 = decide at run time from GemmParams)
-enum : int { EF_LN = 1, EF_GEGLU = 2, EF_RES32 = 4, EF_OUT32 = 8, EF_OUT16 = 16, EF_CSTAT = 32, EF_RSTAT = 64, EF_RES16 = 128 };
+enum : int { EF_LN = 1, EF_GEGLU = 2, EF_RES32 = 4, EF_OUT32 = 8, EF_OUT16 = 16, EF_CSTAT = 32, EF_RSTAT = 64, EF_RES16 = 128,
+             EF_ROPE = 256 };
 // the combinations one UNet evaluation issues (all with a bias vector)
 constexpr int EK_PIN = EF_OUT32 | EF_OUT16 | EF_RSTAT;               // proj_in: fp32 + bf16 token stream, LN row sums
 constexpr int EK_QKV = EF_LN | EF_OUT16;                              // LN-folded q / qkv projections
@@ -49,6 +50,11 @@ constexpr int EK_PIN16 = EF_OUT16 | EF_RSTAT;                         // proj_in
 constexpr int EK_ATTN_OUT16 = EF_RES16 | EF_OUT16 | EF_RSTAT;         // to_out + bf16 residual
 constexpr int EK_FF2_16 = EF_RES16 | EF_OUT16;                        // FF out + bf16 residual
 constexpr int EK_CONV16 = EF_OUT16 | EF_CSTAT;                        // conv1: bf16 out (only GroupNorm 2 reads it) + column sums
+// SCTA's q/k/v projection: LayerNorm fold + rotary embedding of the Q and K heads (attention.py:649-651) applied to the fp32
+// accumulators before the single bf16 rounding — the separate read-modify-write RoPE pass over [M, 2C] disappears
+constexpr int EK_QKV_ROPE = EF_LN | EF_OUT16 | EF_ROPE;
+constexpr int ROPE_PAIRS = 16;                                        // rotary dim 32 = 16 (cos, sin) pairs per row (rotary_emb dim=32)
+constexpr int ROPE_BYTES_PER_WARP = 2 * 32 * ROPE_PAIRS * 8;          // double-buffered [32 rows][16 x float2]
 
 struct GemmParams {
   int M, N;            // N = accumulator columns (GEGLU: twice the output columns)
@@ -79,6 +85,10 @@ struct GemmParams {
   int row_parts_in;
   float ln_inv_dim, ln_eps;
   const float* ln_colsum;
+  // rotary embedding in the epilogue (EK_QKV_ROPE): rope_tab[pos][16] = (cos, sin)(pos * freq_j), pos = row % rope_T; output
+  // columns [0, rope_cols) are heads of width rope_d whose first 32 channels rotate as interleaved pairs
+  const float2* rope_tab;
+  int rope_T, rope_cols, rope_d;
 };
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile — each
@@ -186,6 +196,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
                                                    int nunits) {
   using C = GemmCfg<BN, CG>;
   constexpr bool S = SPEC >= 0;
+  constexpr bool ROPE = S && (SPEC & EF_ROPE) != 0;        // only as a specialisation (the host rejects anything else)
   constexpr bool GEGLU = S && (SPEC & EF_GEGLU) != 0;      // the host routes every GEGLU launch to a specialisation
   const bool f_ln = S ? (SPEC & EF_LN) != 0 : p.row_stats_in != nullptr;
   const int res_mode = S ? ((SPEC & EF_RES32) ? 1 : ((SPEC & EF_RES16) ? 2 : 0)) : p.res_mode;
@@ -215,6 +226,17 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
   const uint32_t res_bytes = res_mode == 1 ? 4096u : 2048u;
   float* vb = evec_base + ew * (2 * EVEC_FLOATS);
   float* vc = vb + EVEC_FLOATS;
+  // RoPE: this lane's row of the (cos, sin) table, cp.async'ed one tile ahead into a double-buffered per-warp smem area
+  // (128 B per row, 16-byte quads XOR-swizzled by the row so the per-lane 16-byte reads are bank-conflict free)
+  uint8_t* rope_buf = reinterpret_cast<uint8_t*>(evec_base + MAX_EPI_WARPS * 2 * EVEC_FLOATS) + ew * ROPE_BYTES_PER_WARP;
+  auto rope_prefetch = [&](int t_mb, int bufi) {
+    const int row = min((t_mb * CG + rank) * BM + q * 32 + lane, p.M - 1);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.rope_tab + (size_t)(row % p.rope_T) * ROPE_PAIRS);
+    uint8_t* dst = rope_buf + bufi * (32 * ROPE_PAIRS * 8);
+#pragma unroll
+    for (int jq = 0; jq < 8; ++jq) cp_async_16(dst + sw128(lane, jq), src + jq * 16, true);
+    cp_async_commit();
+  };
 
   // tile -> (m block, n block), advanced incrementally (tile += nunits)
   const int dm = nunits / p.tiles_n, dn = nunits - dm * p.tiles_n;
@@ -283,6 +305,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
     }
   };
   prefetch_vecs(mb, nb);
+  if constexpr (ROPE) rope_prefetch(mb, 0);
 
   auto tmem_addr = [&](int buf, int c) {
     return tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * C::TBUF + c * CW);
@@ -354,6 +377,10 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
     if (nb_n >= p.tiles_n) { nb_n -= p.tiles_n; ++mb_n; }
     const bool has_next = tile + nunits < p.num_tiles;
     if (has_next) prefetch_vecs(mb_n, nb_n);
+    const uint8_t* rope_cur = rope_buf + (it & 1) * (32 * ROPE_PAIRS * 8);
+    if constexpr (ROPE) {
+      if (has_next) { rope_prefetch(mb_n, (it & 1) ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    }
 
     f2_t rs2 = 0, rq2 = 0;                 // packed (sum, sumsq) accumulators of this lane's row (bit pattern 0 = +0.f pair)
 
@@ -376,6 +403,28 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
       f2_t f[16];
       if constexpr (!GEGLU) {
         epi_affine_dispatch(f, v, f_ln, f_bias, bias_smem, vc + c * 32, vb + c * 32, bias_row + n0 + c * 32, rstd2, nmean2);
+        if constexpr (ROPE) {
+          const int gc0 = n0 + c * 32;                       // first output column of this chunk (warp-uniform)
+          if (gc0 < p.rope_cols) {
+            const int within0 = gc0 % p.rope_d;              // channel of that column inside its head (a multiple of 8)
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {                 // 8-column groups = 4 rotary pairs
+              int w = within0 + 8 * g8;
+              if (w >= p.rope_d) w -= p.rope_d;
+              if (w < 2 * ROPE_PAIRS) {                      // warp-uniform: channels >= 32 of a head pass through
+                const float4 t0 = lds128(rope_cur + sw128(lane, w >> 2));           // (c, s) of pairs w/2, w/2 + 1
+                const float4 t1 = lds128(rope_cur + sw128(lane, (w >> 2) + 1));     //            pairs w/2 + 2, w/2 + 3
+                const float cs[4] = {t0.x, t0.z, t1.x, t1.z}, sn[4] = {t0.y, t0.w, t1.y, t1.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float x0, x1;
+                  f2_unpack(f[4 * g8 + i], x0, x1);
+                  f[4 * g8 + i] = f2_pack(fmaf(x0, cs[i], -(x1 * sn[i])), fmaf(x1, cs[i], x0 * sn[i]));
+                }
+              }
+            }
+          }
+        }
       } else {
         // GEGLU: accumulator columns [c*64, +32) are "value", [c*64+32, +64) the matching "gate" (bias is staged)
         f2_t fg[16];

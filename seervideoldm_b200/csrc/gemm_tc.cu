@@ -236,6 +236,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       case EK_ATTN_OUT16: SEER_EPI(EK_ATTN_OUT16); break;
       case EK_FF2_16: SEER_EPI(EK_FF2_16); break;
       case EK_CONV16: SEER_EPI(EK_CONV16); break;
+      case EK_QKV_ROPE:
+        if constexpr (BN != 320) SEER_EPI(EK_QKV_ROPE);
+        break;
       case EK_FF1:
         if constexpr (BN == 128 || BN == 256) SEER_EPI(EK_FF1);
         break;
@@ -370,7 +373,9 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   const int* cand = d.geglu ? cand_geglu : cand_plain;
   const int ncand = d.geglu ? 2 : 6;
   // 320-wide pair tiles (single-buffered 512-column accumulator): N = 320 / 640 launches with a long main loop
-  const bool allow320 = cg == 2 && Kd >= 1280.0 && N % 256 != 0 && env_int("SEER_GEMM_BN320", 1);
+  // (measured, profiles/r2_gemm_sweep_320.txt: concat convs K >= 8640 1250 -> 1600+ TF/s, K = 2880 +4 %; K <= 2560 linear
+  // launches with an fp32 residual lose 5-10 % to the exposed epilogue)
+  const bool allow320 = cg == 2 && Kd >= 2880.0 && N % 256 != 0 && !d.rope_tab && env_int("SEER_GEMM_BN320", 1);
   int best = 0;
   double best_cost = 1e30;
   const int forced = env_int("SEER_GEMM_BN", 0);   // tuning hook
@@ -413,7 +418,8 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   pl.bstat = bstat_ok && panel_bytes <= 120 * 1024 && units_bs > 0 && pl.num_tiles >= 2 * units_bs;
   if (pl.bstat) pl.grid = units_bs * cg;
   const int stage_bytes = pl.bstat ? A_BYTES : A_BYTES + (best / cg) * BK * 2;
-  const int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - BAR_BYTES - MAX_EPI_WARPS * EVEC_BYTES_PER_WARP -
+  const int rope_bytes = d.rope_tab ? MAX_EPI_WARPS * ROPE_BYTES_PER_WARP : 0;
+  const int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - BAR_BYTES - MAX_EPI_WARPS * EVEC_BYTES_PER_WARP - rope_bytes -
                     (pl.bstat ? panel_bytes : 0);
   // (epilogue warps, ring depth, operand stages) by score: operand stages matter most (up to 5), then 8 epilogue warps
   // for the latency-bound bf16-only / GEGLU epilogues, then ring depth
@@ -435,7 +441,7 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   const int fs = env_int("SEER_GEMM_STAGES", 0);
   if (fs >= 2 && fs <= pl.stages) pl.stages = fs;
   pl.smem_bytes = (pl.bstat ? panel_bytes : 0) + pl.stages * stage_bytes + pl.nepi * pl.ring * pl.slot_bytes + BAR_BYTES +
-                  pl.nepi * EVEC_BYTES_PER_WARP + 1024;
+                  MAX_EPI_WARPS * EVEC_BYTES_PER_WARP + rope_bytes + 1024;
   // > half of the SM's shared memory, so two CTAs (2 x TMEM_COLS could exceed 512 columns) never share an SM
   if (pl.smem_bytes < 120 * 1024) pl.smem_bytes = 120 * 1024;
   return SEER_OK;
@@ -494,6 +500,10 @@ static int check_desc(const SeerGemmDesc& d) {
   if (d.geglu) SEER_CHECK_ARG(d.bias_div <= 0 && d.N % 128 == 0 && d.out_bf16 && !d.out_f32 && d.bias && !d.residual && !d.col_stats && !d.row_stats_out);
   SEER_CHECK_ARG(!d.col_stats || d.out_f32 || d.out_bf16);
   if (d.row_stats_in) SEER_CHECK_ARG(d.row_parts_in > 0 && d.ln_colsum && !d.X);
+  if (d.rope_tab)
+    SEER_CHECK_ARG(!d.X && !d.geglu && d.out_bf16 && !d.out_f32 && !d.residual && !d.col_stats && !d.row_stats_out && d.row_stats_in && d.bias &&
+                   d.rope_T > 0 && d.rope_T % 32 == 0 && d.M % d.rope_T == 0 && d.rope_d >= 32 && d.rope_d % 8 == 0 &&
+                   d.rope_cols > 0 && d.rope_cols % 32 == 0 && d.rope_cols <= d.N && d.rope_cols % d.rope_d == 0);
   return SEER_OK;
 }
 
@@ -525,15 +535,15 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
     const int flags = (d.row_stats_in ? EF_LN : 0) | (d.geglu ? EF_GEGLU : 0) | ((d.residual && !d.residual_bf16) ? EF_RES32 : 0) |
                       ((d.residual && d.residual_bf16) ? EF_RES16 : 0) |
                       (d.out_f32 ? EF_OUT32 : 0) | (d.out_bf16 ? EF_OUT16 : 0) | (d.col_stats ? EF_CSTAT : 0) |
-                      (d.row_stats_out ? EF_RSTAT : 0);
+                      (d.row_stats_out ? EF_RSTAT : 0) | (d.rope_tab ? EF_ROPE : 0);
     static const int kinds[] = {EK_PIN, EK_QKV, EK_ATTN_OUT, EK_FF1, EK_FF1_PLAIN, EK_FF2, EK_POUT, EK_CONV, EK_BF16,
-                                EK_PIN16, EK_ATTN_OUT16, EK_FF2_16, EK_CONV16};
+                                EK_PIN16, EK_ATTN_OUT16, EK_FF2_16, EK_CONV16, EK_QKV_ROPE};
     p.epi_spec = -1;
     const bool generic_forced = env_int("SEER_GEMM_GENERIC", 0) != 0 && !d.geglu;    // A/B hook
     if (d.bias && !generic_forced)
       for (int k : kinds)
         if (k == flags) p.epi_spec = k;
-    if (d.geglu && p.epi_spec < 0) return SEER_EUNSUPPORTED;
+    if ((d.geglu || d.rope_tab) && p.epi_spec < 0) return SEER_EUNSUPPORTED;
   }
   p.bstat = pl.bstat;
   p.stages = pl.stages; p.nepi = pl.nepi; p.ring = pl.ring; p.slot_bytes = pl.slot_bytes;
@@ -544,6 +554,7 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   p.geglu = d.geglu ? 1 : 0;
   p.col_stats = d.col_stats; p.row_stats_out = d.row_stats_out;
   p.row_stats_in = d.row_stats_in; p.row_parts_in = d.row_parts_in; p.ln_eps = d.ln_eps; p.ln_colsum = d.ln_colsum;
+  p.rope_tab = reinterpret_cast<const float2*>(d.rope_tab); p.rope_T = d.rope_T; p.rope_cols = d.rope_cols; p.rope_d = d.rope_d;
 
   CUtensorMap maps[4];
   int Ktot;

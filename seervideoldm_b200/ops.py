@@ -82,7 +82,8 @@ def gemm_ex(a: Optional[torch.Tensor], wt: torch.Tensor, *, x_img: Optional[torc
             residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
             out_dtype: torch.dtype = torch.float32, also_bf16=False, geglu: bool = False, col_stats=False,
             row_stats: bool = False, ln: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None, conv_stride: int = 1,
-            conv_taps: Optional[Tuple[int, int, int, int]] = None, up_phase: int = 0) -> Optional[GemmOut]:
+            conv_taps: Optional[Tuple[int, int, int, int]] = None, up_phase: int = 0,
+            rope: Optional[Tuple[torch.Tensor, int, int]] = None) -> Optional[GemmOut]:
     """One tcgen05 GEMM / implicit-GEMM conv launch (SeerGemmDesc, include/seer_b200.h; torch.ops.seer_b200.gemm_ex).
 
     acc = [a | a2] @ wt.T   (a:[M,K1] bf16, or x_img:[n_img,H,W,Cin] bf16 for the 3x3/pad-1 conv; a2:[M,K2] bf16)
@@ -93,6 +94,9 @@ def gemm_ex(a: Optional[torch.Tensor], wt: torch.Tensor, *, x_img: Optional[torc
     Conv variants (x_img only): `conv_stride` 2 = Downsample3D read through a strided TMA box; `conv_taps` =
     (taps_w, taps_h, off_x, off_y) replaces the 3x3 / offset -1 tap set; `up_phase` 1 + (2 py + px) scatters the rows to the
     (py, px) phase of the 2x upsampled output (out / col_stats then have 4x the GEMM's rows).
+    `rope` = (table [T, 16, 2] from rope_table(), rotated columns, head dim): rotary embedding of the leading `cols` output
+    columns (heads of width `head dim`, first 32 channels of each) by the row's position r % T, fused into the epilogue (needs
+    `ln`, a bias and a bf16 output).
     Returns None when an x_img geometry is outside the TMA-box tiling (the caller falls back to im2col + GEMM)."""
     _cuda(wt, "wt")
     if wt.dim() != 2:
@@ -135,8 +139,10 @@ def gemm_ex(a: Optional[torch.Tensor], wt: torch.Tensor, *, x_img: Optional[torc
         cs = torch.empty(((M_out + 31) // 32, N, 2), device=dev, dtype=torch.float32) if col_stats is True else col_stats
     rs_in, colsum, eps = ln if ln is not None else (None, None, 0.0)
     taps = list(conv_taps) if conv_taps is not None else []
+    rope_tab, rope_cols, rope_d = rope if rope is not None else (None, 0, 0)
     args = [a if x_img is None else None, x_img, a2, wt, bias, int(bias_div), residual, o32, o16, bool(geglu), cs, None, rs_in,
-            float(eps), colsum, int(conv_stride), taps, int(up_phase)]
+            float(eps), colsum, int(conv_stride), taps, int(up_phase), rope_tab, (rope_tab.shape[0] if rope is not None else 0),
+            int(rope_cols), int(rope_d)]
     rs = None
     if row_stats:
         rs = torch.empty((_ops.gemm_row_parts(*args), M, 2), device=dev, dtype=torch.float32)
@@ -258,6 +264,15 @@ def scta_row_index(B: int, F: int, H: int, W: int, device="cuda") -> torch.Tenso
     _lib.check(_lib.lib().seer_b200_scta_row_index(B, F, H, W, None, ctypes.byref(nwin), ctypes.byref(L), None), "scta_row_index")
     out = torch.empty((B, nwin.value, L.value), device=device, dtype=torch.int32)
     _ops.scta_row_index(out, B, F, H, W)
+    return out
+
+
+def rope_table(freqs: torch.Tensor, T: int) -> torch.Tensor:
+    """[T, n_freqs, 2] fp32 (cos, sin)(pos * freqs[j]) — the table the q/k/v GEMM's fused rotary epilogue reads."""
+    _cuda(freqs, "freqs")
+    out = torch.empty((T, freqs.numel(), 2), device=freqs.device, dtype=torch.float32)
+    _ops.rope_table(freqs, out)
+    _count()
     return out
 
 

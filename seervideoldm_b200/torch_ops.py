@@ -89,11 +89,12 @@ def _define(schema: str, impl, fake=None) -> None:
 # --------------------------------------------------------------------------------------------------------------------
 _GEMM_ARGS = ("Tensor? a, Tensor? x_img, Tensor? a2, Tensor wt, Tensor? bias, int bias_div, Tensor? residual, "
               "Tensor(a!)? out_f32, Tensor(b!)? out_bf16, bool geglu, Tensor(c!)? col_stats, Tensor(d!)? row_stats_out, "
-              "Tensor? row_stats_in, float ln_eps, Tensor? ln_colsum, int conv_stride, int[] conv_taps, int up_phase")
+              "Tensor? row_stats_in, float ln_eps, Tensor? ln_colsum, int conv_stride, int[] conv_taps, int up_phase, "
+              "Tensor? rope_tab, int rope_T, int rope_cols, int rope_d")
 
 
 def _gemm_desc(a, x_img, a2, wt, bias, bias_div, residual, out_f32, out_bf16, geglu, col_stats, row_stats_out, row_stats_in,
-               ln_eps, ln_colsum, conv_stride, conv_taps, up_phase) -> "_lib.GemmDesc":
+               ln_eps, ln_colsum, conv_stride, conv_taps, up_phase, rope_tab, rope_T, rope_cols, rope_d) -> "_lib.GemmDesc":
     dev = wt.device
     _chk(wt, "wt", bf16, 2, contiguous=True)
     d = _lib.GemmDesc()
@@ -169,6 +170,11 @@ def _gemm_desc(a, x_img, a2, wt, bias, bias_div, residual, out_f32, out_bf16, ge
         if row_stats_out.shape[1] != M or row_stats_out.shape[2] != 2:
             raise ValueError("row_stats_out must be [parts, M, 2]")
         d.row_stats_out = row_stats_out.data_ptr()
+    if rope_tab is not None:
+        _chk(rope_tab, "rope_tab", f32, 3, contiguous=True, dev=dev)
+        if tuple(rope_tab.shape) != (rope_T, 16, 2):
+            raise ValueError(f"rope_tab must be [rope_T = {rope_T}, 16, 2] (seer_b200.rope_table)")
+        d.rope_tab, d.rope_T, d.rope_cols, d.rope_d = rope_tab.data_ptr(), rope_T, rope_cols, rope_d
     return d
 
 
@@ -436,6 +442,16 @@ def _geglu_f32(h, out) -> None:
     _lib.check(rc, "geglu_f32")
 
 
+def _rope_table(freqs, out) -> None:
+    _chk(freqs, "freqs", f32, 1); _chk(out, "out", f32, 3, contiguous=True, dev=freqs.device)
+    if out.shape[1] != freqs.numel() or out.shape[2] != 2:
+        raise ValueError("rope_table: out must be [T, n_freqs, 2]")
+    with _Dev(freqs) as stream:
+        rc = _lib.lib().seer_b200_rope_table(_p(freqs), freqs.numel(), out.shape[0], _p(out), stream)
+    _lib.check(rc, "rope_table")
+
+
+_define("rope_table(Tensor freqs, Tensor(a!) out) -> ()", _rope_table)
 _define("rope(Tensor(a!) qk, int pos_div, int pos_mod, int heads, int head_dim, int q_col, int k_col, Tensor freqs) -> ()", _rope)
 _define("timestep_embedding(Tensor t, Tensor(a!) out, float shift, bool flip_sin_to_cos) -> ()", _timestep_embedding)
 _define("small_linear(Tensor x, Tensor w, Tensor? bias, Tensor? add, Tensor(a!) out, bool silu_in, bool silu_out) -> ()", _small_linear)

@@ -342,9 +342,18 @@ class SeerUNet(nn.Module):
         xt, xs = x[:2]
         hn = ops.groupnorm(xt, None, B, t["gn_g"], t["gn_b"], 1e-6, False, stats1=xs)
         r = ops.gemm_ex(hn, t["pin_w"], bias=t["pin_b"], out_dtype=bf, row_stats=True)
-        qkv = ops.gemm_ex(r.out, t["qkv_w"], bias=t["qkv_b"], out_dtype=bf, ln=(r.row_stats, t["qkv_cs"], 1e-5)).out     # [M, 3C]
+        rope = None
+        if t["temporal"] and T % 32 == 0 and t["freqs"].numel() == 16:
+            # rotary embedding of q and k (attention.py:649-651) fused into the projection's epilogue; the (cos, sin) table of
+            # this clip length is built once per layer (outside any graph capture: the warm-up evaluations fill the cache)
+            tab = t.setdefault("rope_tabs", {}).get(T)
+            if tab is None:
+                tab = t["rope_tabs"][T] = ops.rope_table(t["freqs"], T)
+            rope = (tab, 2 * C, d)
+        qkv = ops.gemm_ex(r.out, t["qkv_w"], bias=t["qkv_b"], out_dtype=bf, ln=(r.row_stats, t["qkv_cs"], 1e-5), rope=rope).out   # [M, 3C]
         if t["temporal"]:
-            ops.rope_inplace(qkv, T, heads, d, 0, C, t["freqs"])
+            if rope is None:
+                ops.rope_inplace(qkv, T, heads, d, 0, C, t["freqs"])
             att = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], mode=ops.ATTN_SCTA, heads=heads, n_outer=B,
                                 F=F, H=H, W=W)
         else:

@@ -256,7 +256,7 @@ def test_torch_op_library_registration():
     from seervideoldm_b200 import ops, torch_ops  # noqa: F401
     want = {"gemm_ex", "gemm_row_parts", "groupnorm", "groupnorm_from_stats", "layernorm", "attention", "scta_row_index", "rope",
             "timestep_embedding", "small_linear", "conv_in", "conv_out", "upsample2x", "im2col3x3", "cast_bf16", "cfg_ddim_update",
-            "split3", "geglu_f32"}
+            "split3", "geglu_f32", "rope_table"}
     assert want <= set(torch_ops.OP_NAMES)
     for name in want:
         op = getattr(torch.ops.seer_b200, name).default
@@ -275,6 +275,7 @@ def test_torch_op_library_registration():
         a = torch.empty(256, 64, dtype=torch.bfloat16, device="cuda")
         w = torch.empty(128, 64, dtype=torch.bfloat16, device="cuda")
         out = torch.empty(256, 128, dtype=torch.float32, device="cuda")
-        rc = torch.ops.seer_b200.gemm_ex(a, None, None, w, None, 0, None, out, None, False, None, None, None, 0.0, None, 1, [], 0)
+        rc = torch.ops.seer_b200.gemm_ex(a, None, None, w, None, 0, None, out, None, False, None, None, None, 0.0, None, 1, [], 0,
+                                         None, 0, 0, 0)
         assert rc == 0
         torch.ops.seer_b200.cast_bf16(torch.empty(8, device="cuda"), torch.empty(8, dtype=torch.bfloat16, device="cuda"))

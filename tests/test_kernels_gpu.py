@@ -341,6 +341,41 @@ def test_gemm_320_wide_pair_tiles():
     assert rel(r.out.float(), a.float() @ w.float().t() + rn(69, N)) < 4e-3
 
 
+@pytest.mark.parametrize("d,Fr,hw,B", [(40, 4, 64, 2), (80, 2, 256, 1), (160, 4, 32, 3), (40, 16, 1024, 2)])
+def test_gemm_qkv_rope_fused(d, Fr, hw, B):
+    """RoPE (attention.py:649-651) fused into the LN-folded q/k/v projection's epilogue == the unfused projection followed by
+    the stand-alone rotary pass, up to one bf16 rounding (the fused path rotates the fp32 accumulators)."""
+    heads = 8
+    C = heads * d
+    T = Fr * hw
+    M = B * T
+    prod = ops.gemm_ex(rn(70, M, C).bfloat16(), (torch.eye(C, device=DEV) + rn(71, C, C, scale=0.02)).bfloat16(), bias=rn(72, C) * 0.1,
+                       out_dtype=torch.bfloat16, row_stats=True)
+    gamma, beta = rn(73, C) * 0.2 + 1.0, rn(74, C) * 0.1
+    W = rn(75, 3 * C, C, scale=C ** -0.5)
+    wf = (W * gamma[None, :]).bfloat16().contiguous()
+    colsum, bias_f = wf.float().sum(1).contiguous(), (W @ beta).contiguous()
+    freqs = (1.0 / (10000.0 ** (torch.arange(0, 32, 2).float() / 32))).to(DEV)
+    tab = ops.rope_table(freqs, T)
+    ang = torch.arange(T, device=DEV).float()[:, None] * freqs[None, :]
+    assert torch.allclose(tab[..., 0], ang.cos(), atol=2e-6) and torch.allclose(tab[..., 1], ang.sin(), atol=2e-6)
+    fused = ops.gemm_ex(prod.out, wf, bias=bias_f, out_dtype=torch.bfloat16, ln=(prod.row_stats, colsum, 1e-5), rope=(tab, 2 * C, d)).out
+    assert "spec=273" in ops.last_gemm_kernel(), ops.last_gemm_kernel()        # EK_QKV_ROPE = LN | OUT16 | ROPE
+    # reference: the same projection in fp32, rotated in fp64 with the oracle's rotary statement
+    plain32 = ops.gemm_ex(prod.out, wf, bias=bias_f, ln=(prod.row_stats, colsum, 1e-5)).out
+    ref = plain32.clone().double().reshape(B, T, 3, heads, d)
+    pos = torch.arange(T)
+    for which in (0, 1):
+        r = so.rope_interleaved(ref[:, :, which].permute(0, 2, 1, 3).cpu(), pos, 32)
+        ref[:, :, which] = r.permute(0, 2, 1, 3).to(DEV)
+    ref = ref.reshape(M, 3 * C).float()
+    assert rel(fused.float(), ref) < 4e-3
+    assert torch.equal(fused[:, 2 * C:], plain32[:, 2 * C:].bfloat16())                   # V untouched
+    unfused = ops.gemm_ex(prod.out, wf, bias=bias_f, out_dtype=torch.bfloat16, ln=(prod.row_stats, colsum, 1e-5)).out
+    ops.rope_inplace(unfused, T, heads, d, 0, C, freqs)
+    assert rel(fused.float(), unfused.float()) < 6e-3
+
+
 def test_gemm_rejects_bad_shapes():
     a = rn(1, 128, 100).bfloat16()
     w = rn(2, 160, 100).bfloat16()
