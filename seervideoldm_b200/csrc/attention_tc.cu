@@ -413,7 +413,9 @@ static int at_map_4d(CUtensorMap* tm, const void* base, uint64_t n_frames, uint6
 // Item order: non-causal = query tiles of a problem adjacent (K/V stay in L2); causal = longest items (highest query tile)
 // first, round-robin over the CTAs, so every CTA receives the same mix of lengths.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int D>
+// PT: P is handed to the P V MMA through TENSOR MEMORY (tcgen05.st by the softmax warps, tcgen05.mma with a TMEM A operand):
+// no swizzled smem tile, no generic -> async proxy fence on the softmax warps' critical chain (measured ~250 clk per tile).
+template <int D, bool PT>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                             const __grid_constant__ CUtensorMap tmV, const AttnTcParams p, const int n_problems,
@@ -469,6 +471,7 @@ attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base;           // 128 columns
   const uint32_t tO = tmem_base + 128;     // 64 columns
+  const uint32_t tP = tmem_base + 192;     // 64 columns: P as bf16 pairs (PT)
   pdl_wait();                              // PDL secondary: the prologue above overlapped the previous kernel's tail
 
   // work item -> (problem, query tile)
@@ -562,8 +565,12 @@ attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < AT_BN / 16; ++k) {
-            const uint64_t a = (k < 4 ? p_desc0 : p_desc1) + (uint64_t)((k & 3) * 2);
-            umma_bf16(tO, a, v_desc + (uint64_t)(k * 128), idesc_o, (j | k) != 0);
+            if (PT) {
+              umma_bf16_ts(tO, tP + (uint32_t)(k * 8), v_desc + (uint64_t)(k * 128), idesc_o, (j | k) != 0);   // 16 keys = 8 columns
+            } else {
+              const uint64_t a = (k < 4 ? p_desc0 : p_desc1) + (uint64_t)((k & 3) * 2);
+              umma_bf16(tO, a, v_desc + (uint64_t)(k * 128), idesc_o, (j | k) != 0);
+            }
           }
           umma_commit(o_full);
           umma_commit(v_empty);
@@ -645,10 +652,12 @@ attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint8_t* prow = sP + (c >> 1) * (AT_BM * 128) + r * 128;
+            uint32_t pk[16];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (c * 32 + 8 * g >= k_vis) {                         // warp-uniform: P = 0, no exp2
-                sts128u(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4), make_uint4(0, 0, 0, 0));
+                if (PT) { pk[4 * g] = pk[4 * g + 1] = pk[4 * g + 2] = pk[4 * g + 3] = 0u; }
+                else sts128u(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4), make_uint4(0, 0, 0, 0));
                 continue;
               }
               float e[8];
@@ -663,8 +672,10 @@ attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
               o.y = pack_bf16(e[2], e[3]);
               o.z = pack_bf16(e[4], e[5]);
               o.w = pack_bf16(e[6], e[7]);
-              sts128u(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4), o);
+              if (PT) { pk[4 * g] = o.x; pk[4 * g + 1] = o.y; pk[4 * g + 2] = o.z; pk[4 * g + 3] = o.w; }
+              else sts128u(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4), o);
             }
+            if (PT) tmem_st_32x16(tP + lane_addr + c * 16, pk);
           }
         } else {
           const f2_t sl22 = f2_pack(sl2, sl2), nmsc2 = f2_pack(-msc, -msc);
@@ -672,6 +683,7 @@ attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint8_t* prow = sP + (c >> 1) * (AT_BM * 128) + r * 128;
+            uint32_t pk[16];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint32_t o[4];
@@ -684,16 +696,18 @@ attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
                 sum2[k & 1] = f2_add(sum2[k & 1], f2_pack(e0, e1));
                 o[k] = pack_bf16(e0, e1);
               }
-              sts128u(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+              if (PT) { pk[4 * g] = o[0]; pk[4 * g + 1] = o[1]; pk[4 * g + 2] = o[2]; pk[4 * g + 3] = o[3]; }
+              else sts128u(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
             }
+            if (PT) tmem_st_32x16(tP + lane_addr + c * 16, pk);
           }
           float s0, s1;
           f2_unpack(f2_add(sum2[0], sum2[1]), s0, s1);
           sum = s0 + s1;
         }
         l_run += sum;
+        if (PT) tmem_st_wait(); else fence_proxy_async_smem();
         tc_fence_before();
-        fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
       }
@@ -837,18 +851,20 @@ extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ld
            at_map_2d(&tk, k, (uint64_t)n_outer * Lk, C, ldk) == SEER_OK && at_map_2d(&tv, v, (uint64_t)n_outer * Lk, C, ldv) == SEER_OK;
     }
     if (ok) {
-      static SmemAttrOnce smem_attr_attr_done_p;
-  { cudaError_t e = smem_attr_attr_done_p.ensure(attention_tc_persist_kernel<40>, AT_SMEM); if (e != cudaSuccess) return (int)e; }
+      const bool pt = env_flag("SEER_ATTN_P_TMEM", 1) != 0;
+      auto kern = pt ? attention_tc_persist_kernel<40, true> : attention_tc_persist_kernel<40, false>;
+      static SmemAttrOnce smem_attr_attr_done_p[2];
+  { cudaError_t e = smem_attr_attr_done_p[pt].ensure(kern, AT_SMEM); if (e != cudaSuccess) return (int)e; }
       int dev = 0, nsm = 148;
       if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0)
         nsm = 148;
       const long total = (long)n_problems * nq_tiles;
       const int grid = (int)(total < 2L * nsm ? total : 2L * nsm);
-      cudaError_t le = launch_pdl(attention_tc_persist_kernel<40>, dim3(grid), dim3(AT_THREADS), (size_t)AT_SMEM, (cudaStream_t)stream, tq, tk,
+      cudaError_t le = launch_pdl(kern, dim3(grid), dim3(AT_THREADS), (size_t)AT_SMEM, (cudaStream_t)stream, tq, tk,
                                   tv, p, n_problems, nq_tiles);
       if (le != cudaSuccess) return (int)le;
       SEER_LAUNCH_CHECK();
-      debug_note_attention("attention_tc_persist_kernel<40> tcgen05");
+      debug_note_attention(pt ? "attention_tc_persist_kernel<40> tcgen05 (P in TMEM)" : "attention_tc_persist_kernel<40> tcgen05");
       return SEER_OK;
     }
     static bool warned = false;

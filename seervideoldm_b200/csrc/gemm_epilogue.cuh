@@ -27,8 +27,10 @@ constexpr int MAX_RING = 8;
 constexpr int GEMM_MAX_THREADS = 64 + 32 * MAX_EPI_WARPS;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 1024;
-constexpr int EVEC_FLOATS = 320;                       // per-warp staging of the tile's bias / LN column-sum slices (BN <= 320)
+constexpr int EVEC_FLOATS = 256;                       // per-warp staging of the tile's bias / LN column-sum slices (BN <= 256) ...
+constexpr int EVEC_FLOATS_320 = 320;                   // ... and for the 320-wide tiles (GemmParams::evec_floats says which)
 constexpr int EVEC_BYTES_PER_WARP = 2 * EVEC_FLOATS * 4;
+constexpr int EVEC_BYTES_PER_WARP_320 = 2 * EVEC_FLOATS_320 * 4;
 constexpr int BIAS_ONE_ROW = 0x7fffffff;               // GemmParams::bias_div value meaning "a single bias row"
 
 // epilogue option bits (template parameter SPEC of the epilogue; -1 = decide at run time from GemmParams)
@@ -54,7 +56,7 @@ constexpr int EK_CONV16 = EF_OUT16 | EF_CSTAT;                        // conv1: 
 // accumulators before the single bf16 rounding — the separate read-modify-write RoPE pass over [M, 2C] disappears
 constexpr int EK_QKV_ROPE = EF_LN | EF_OUT16 | EF_ROPE;
 constexpr int ROPE_PAIRS = 16;                                        // rotary dim 32 = 16 (cos, sin) pairs per row (rotary_emb dim=32)
-constexpr int ROPE_BYTES_PER_WARP = 2 * 32 * ROPE_PAIRS * 8;          // double-buffered [32 rows][16 x float2]
+constexpr int ROPE_BYTES_PER_WARP = 32 * ROPE_PAIRS * 8;              // [32 rows][16 x float2] per epilogue warp
 
 struct GemmParams {
   int M, N;            // N = accumulator columns (GEGLU: twice the output columns)
@@ -68,6 +70,7 @@ struct GemmParams {
   int ntaps, taps_w, taps_h, off_x, off_y, cstride;   // conv taps: tap t reads pixel (s*y + t / taps_w + off_y, s*x + t % taps_w + off_x)
   int up_phase;        // 0: output row = GEMM row; 1 + (2 py + px): rows are the (py, px) phase of a nearest-2x upsampled image
   int up_wshift;       //    (low-res width = 1 << up_wshift): out row = ((m >> ws) << (ws + 2)) + py * 2W + 2 (m & (W - 1)) + px
+  int evec_floats;     // floats per staged per-tile vector (bias / LN column sums) and warp: EVEC_FLOATS or EVEC_FLOATS_320
   int bstat;           // 1: the whole Wt panel of this CTA's (fixed) n-block is resident in smem; only A is streamed
   int epi_spec;        // EK_* combination compiled as a specialisation, or -1 (generic runtime-flag epilogue)
   const float* bias;
@@ -224,17 +227,18 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
   uint8_t* ring = ring_base + (size_t)ew * R * p.slot_bytes;
   uint64_t* rfull = res_full_bar + ew * MAX_RING;
   const uint32_t res_bytes = res_mode == 1 ? 4096u : 2048u;
-  float* vb = evec_base + ew * (2 * EVEC_FLOATS);
-  float* vc = vb + EVEC_FLOATS;
-  // RoPE: this lane's row of the (cos, sin) table, cp.async'ed one tile ahead into a double-buffered per-warp smem area
-  // (128 B per row, 16-byte quads XOR-swizzled by the row so the per-lane 16-byte reads are bank-conflict free)
-  uint8_t* rope_buf = reinterpret_cast<uint8_t*>(evec_base + MAX_EPI_WARPS * 2 * EVEC_FLOATS) + ew * ROPE_BYTES_PER_WARP;
-  auto rope_prefetch = [&](int t_mb, int bufi) {
+  float* vb = evec_base + ew * (2 * p.evec_floats);
+  float* vc = vb + p.evec_floats;
+  // RoPE: this lane's row of the (cos, sin) table lives in a per-warp smem area (128 B per row, 16-byte quads XOR-swizzled by
+  // the row: the per-lane 16-byte reads are bank-conflict free).  It is cp.async'ed for the NEXT tile as soon as the last
+  // rotated chunk of the current tile is done, so the L2 round trip hides behind the tile switch; a lane only ever reads the
+  // row it copied itself, so cp.async.wait_group is all the synchronisation needed.
+  uint8_t* rope_buf = reinterpret_cast<uint8_t*>(evec_base + MAX_EPI_WARPS * 2 * p.evec_floats) + ew * ROPE_BYTES_PER_WARP;
+  auto rope_prefetch = [&](int t_mb) {
     const int row = min((t_mb * CG + rank) * BM + q * 32 + lane, p.M - 1);
     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.rope_tab + (size_t)(row % p.rope_T) * ROPE_PAIRS);
-    uint8_t* dst = rope_buf + bufi * (32 * ROPE_PAIRS * 8);
 #pragma unroll
-    for (int jq = 0; jq < 8; ++jq) cp_async_16(dst + sw128(lane, jq), src + jq * 16, true);
+    for (int jq = 0; jq < 8; ++jq) cp_async_16(rope_buf + sw128(lane, jq), src + jq * 16, true);
     cp_async_commit();
   };
 
@@ -305,7 +309,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
     }
   };
   prefetch_vecs(mb, nb);
-  if constexpr (ROPE) rope_prefetch(mb, 0);
+  if constexpr (ROPE) rope_prefetch(mb);
 
   auto tmem_addr = [&](int buf, int c) {
     return tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * C::TBUF + c * CW);
@@ -377,9 +381,11 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
     if (nb_n >= p.tiles_n) { nb_n -= p.tiles_n; ++mb_n; }
     const bool has_next = tile + nunits < p.num_tiles;
     if (has_next) prefetch_vecs(mb_n, nb_n);
-    const uint8_t* rope_cur = rope_buf + (it & 1) * (32 * ROPE_PAIRS * 8);
+    // channel (inside its head) of the first column of this warp's first chunk; advanced incrementally per chunk
+    int rope_within = 0;
     if constexpr (ROPE) {
-      if (has_next) { rope_prefetch(mb_n, (it & 1) ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+      rope_within = (n0 + half * 32) % p.rope_d;
+      cp_async_wait<0>();                  // this tile's (cos, sin) rows have landed (issued at the end of the previous tile)
     }
 
     f2_t rs2 = 0, rq2 = 0;                 // packed (sum, sumsq) accumulators of this lane's row (bit pattern 0 = +0.f pair)
@@ -406,14 +412,13 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
         if constexpr (ROPE) {
           const int gc0 = n0 + c * 32;                       // first output column of this chunk (warp-uniform)
           if (gc0 < p.rope_cols) {
-            const int within0 = gc0 % p.rope_d;              // channel of that column inside its head (a multiple of 8)
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {                 // 8-column groups = 4 rotary pairs
-              int w = within0 + 8 * g8;
+              int w = rope_within + 8 * g8;                  // channel of the group's first column inside its head (multiple of 8)
               if (w >= p.rope_d) w -= p.rope_d;
               if (w < 2 * ROPE_PAIRS) {                      // warp-uniform: channels >= 32 of a head pass through
-                const float4 t0 = lds128(rope_cur + sw128(lane, w >> 2));           // (c, s) of pairs w/2, w/2 + 1
-                const float4 t1 = lds128(rope_cur + sw128(lane, (w >> 2) + 1));     //            pairs w/2 + 2, w/2 + 3
+                const float4 t0 = lds128(rope_buf + sw128(lane, w >> 2));           // (c, s) of pairs w/2, w/2 + 1
+                const float4 t1 = lds128(rope_buf + sw128(lane, (w >> 2) + 1));     //            pairs w/2 + 2, w/2 + 3
                 const float cs[4] = {t0.x, t0.z, t1.x, t1.z}, sn[4] = {t0.y, t0.w, t1.y, t1.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -424,6 +429,9 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
               }
             }
           }
+          rope_within += 32 * nhalf;                          // next chunk of this warp
+          while (rope_within >= p.rope_d) rope_within -= p.rope_d;
+          if (j + 1 == my_nch && has_next) rope_prefetch(mb_n);   // every lane has read its row for the last time this tile
         }
       } else {
         // GEGLU: accumulator columns [c*64, +32) are "value", [c*64+32, +64) the matching "gate" (bias is staged)

@@ -419,8 +419,8 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   if (pl.bstat) pl.grid = units_bs * cg;
   const int stage_bytes = pl.bstat ? A_BYTES : A_BYTES + (best / cg) * BK * 2;
   const int rope_bytes = d.rope_tab ? MAX_EPI_WARPS * ROPE_BYTES_PER_WARP : 0;
-  const int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - BAR_BYTES - MAX_EPI_WARPS * EVEC_BYTES_PER_WARP - rope_bytes -
-                    (pl.bstat ? panel_bytes : 0);
+  const int evec_bytes = MAX_EPI_WARPS * (best == 320 ? EVEC_BYTES_PER_WARP_320 : EVEC_BYTES_PER_WARP);
+  const int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - BAR_BYTES - evec_bytes - rope_bytes - (pl.bstat ? panel_bytes : 0);
   // (epilogue warps, ring depth, operand stages) by score: operand stages matter most (up to 5), then 8 epilogue warps
   // for the latency-bound bf16-only / GEGLU epilogues, then ring depth
   const int want_nepi = pl.nepi;
@@ -441,7 +441,7 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   const int fs = env_int("SEER_GEMM_STAGES", 0);
   if (fs >= 2 && fs <= pl.stages) pl.stages = fs;
   pl.smem_bytes = (pl.bstat ? panel_bytes : 0) + pl.stages * stage_bytes + pl.nepi * pl.ring * pl.slot_bytes + BAR_BYTES +
-                  MAX_EPI_WARPS * EVEC_BYTES_PER_WARP + rope_bytes + 1024;
+                  evec_bytes + rope_bytes + 1024;
   // > half of the SM's shared memory, so two CTAs (2 x TMEM_COLS could exceed 512 columns) never share an SM
   if (pl.smem_bytes < 120 * 1024) pl.smem_bytes = 120 * 1024;
   return SEER_OK;
@@ -546,6 +546,7 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
     if ((d.geglu || d.rope_tab) && p.epi_spec < 0) return SEER_EUNSUPPORTED;
   }
   p.bstat = pl.bstat;
+  p.evec_floats = pl.bn == 320 ? EVEC_FLOATS_320 : EVEC_FLOATS;
   p.stages = pl.stages; p.nepi = pl.nepi; p.ring = pl.ring; p.slot_bytes = pl.slot_bytes;
   p.bias = d.bias; p.ldb = d.ldb > 0 ? d.ldb : d.N; p.bias_div = d.bias_div > 0 ? d.bias_div : BIAS_ONE_ROW;
   p.res_mode = d.residual ? (d.residual_bf16 ? 2 : 1) : 0;
