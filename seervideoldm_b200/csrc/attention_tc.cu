@@ -851,7 +851,9 @@ extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ld
            at_map_2d(&tk, k, (uint64_t)n_outer * Lk, C, ldk) == SEER_OK && at_map_2d(&tv, v, (uint64_t)n_outer * Lk, C, ldv) == SEER_OK;
     }
     if (ok) {
-      const bool pt = env_flag("SEER_ATTN_P_TMEM", 1) != 0;
+      // (measured, profiles/r2_attn_bench_p_tmem.txt: 870 vs 854 us spatial, 655 vs 616 us SCTA — the TMEM store + wait costs more
+      //  than the smem store + proxy fence it replaces at 168 registers; kept as an A/B switch, off by default)
+      const bool pt = env_flag("SEER_ATTN_P_TMEM", 0) != 0;
       auto kern = pt ? attention_tc_persist_kernel<40, true> : attention_tc_persist_kernel<40, false>;
       static SmemAttrOnce smem_attr_attr_done_p[2];
   { cudaError_t e = smem_attr_attr_done_p[pt].ensure(kern, AT_SMEM); if (e != cudaSuccess) return (int)e; }

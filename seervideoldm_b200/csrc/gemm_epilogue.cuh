@@ -385,8 +385,8 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
     int rope_within = 0;
     if constexpr (ROPE) {
       rope_within = (n0 + half * 32) % p.rope_d;
-      cp_async_wait<0>();                  // this tile's (cos, sin) rows have landed (issued at the end of the previous tile)
     }
+    bool rope_landed = false;              // cp.async.wait_group is deferred to the first rotated chunk of the tile
 
     f2_t rs2 = 0, rq2 = 0;                 // packed (sum, sumsq) accumulators of this lane's row (bit pattern 0 = +0.f pair)
 
@@ -412,6 +412,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
         if constexpr (ROPE) {
           const int gc0 = n0 + c * 32;                       // first output column of this chunk (warp-uniform)
           if (gc0 < p.rope_cols) {
+            if (!rope_landed) { cp_async_wait<0>(); rope_landed = true; }   // rows issued at the end of the previous tile
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {                 // 8-column groups = 4 rotary pairs
               int w = rope_within + 8 * g8;                  // channel of the group's first column inside its head (multiple of 8)
@@ -431,7 +432,10 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
           }
           rope_within += 32 * nhalf;                          // next chunk of this warp
           while (rope_within >= p.rope_d) rope_within -= p.rope_d;
-          if (j + 1 == my_nch && has_next) rope_prefetch(mb_n);   // every lane has read its row for the last time this tile
+          if (j + 1 == my_nch && has_next) {                  // every lane has read its row for the last time this tile
+            if (!rope_landed) cp_async_wait<0>();             // (a tile of V columns only never waited: drain before re-issuing)
+            rope_prefetch(mb_n);
+          }
         }
       } else {
         // GEGLU: accumulator columns [c*64, +32) are "value", [c*64+32, +64) the matching "gate" (bias is staged)

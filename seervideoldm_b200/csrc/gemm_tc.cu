@@ -29,7 +29,10 @@
 
 namespace seer {
 
-template <int BN, int CG>
+// GRP: which epilogue specialisations this instantiation carries — 0: everything except the two register-heavy families,
+// 1: the GEGLU kinds, 2: the RoPE kind.  One kernel holding all of them let the heaviest path dictate the register
+// allocation (and the spills) of every other one (measured: adding the RoPE kind slowed the GEGLU launches by 12 %).
+template <int BN, int CG, int GRP>
 __global__ void __launch_bounds__(GEMM_MAX_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmRes, const GemmParams p) {
@@ -224,28 +227,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #define SEER_EPI(SPEC)                                                                                                  \
   gemm_epilogue_warp<BN, CG, SPEC>(p, &tmRes, ring_base, tmem_full_bar, tmem_empty_bar, res_full_bar, evec_base, tmem_base, \
                                    warp, lane, rank, unit, nunits)
-    switch (p.epi_spec) {
-      case EK_PIN: SEER_EPI(EK_PIN); break;
-      case EK_QKV: SEER_EPI(EK_QKV); break;
-      case EK_ATTN_OUT: SEER_EPI(EK_ATTN_OUT); break;
-      case EK_FF2: SEER_EPI(EK_FF2); break;
-      case EK_POUT: SEER_EPI(EK_POUT); break;
-      case EK_CONV: SEER_EPI(EK_CONV); break;
-      case EK_BF16: SEER_EPI(EK_BF16); break;
-      case EK_PIN16: SEER_EPI(EK_PIN16); break;
-      case EK_ATTN_OUT16: SEER_EPI(EK_ATTN_OUT16); break;
-      case EK_FF2_16: SEER_EPI(EK_FF2_16); break;
-      case EK_CONV16: SEER_EPI(EK_CONV16); break;
-      case EK_QKV_ROPE:
-        if constexpr (BN != 320) SEER_EPI(EK_QKV_ROPE);
-        break;
-      case EK_FF1:
-        if constexpr (BN == 128 || BN == 256) SEER_EPI(EK_FF1);
-        break;
-      case EK_FF1_PLAIN:
-        if constexpr (BN == 128 || BN == 256) SEER_EPI(EK_FF1_PLAIN);
-        break;
-      default: SEER_EPI(-1); break;
+    if constexpr (GRP == 1) {
+      if constexpr (BN == 128 || BN == 256) {
+        if (p.epi_spec == EK_FF1) SEER_EPI(EK_FF1); else SEER_EPI(EK_FF1_PLAIN);
+      }
+    } else if constexpr (GRP == 2) {
+      if constexpr (BN != 320) SEER_EPI(EK_QKV_ROPE);
+    } else {
+      switch (p.epi_spec) {
+        case EK_PIN: SEER_EPI(EK_PIN); break;
+        case EK_QKV: SEER_EPI(EK_QKV); break;
+        case EK_ATTN_OUT: SEER_EPI(EK_ATTN_OUT); break;
+        case EK_FF2: SEER_EPI(EK_FF2); break;
+        case EK_POUT: SEER_EPI(EK_POUT); break;
+        case EK_CONV: SEER_EPI(EK_CONV); break;
+        case EK_BF16: SEER_EPI(EK_BF16); break;
+        case EK_PIN16: SEER_EPI(EK_PIN16); break;
+        case EK_ATTN_OUT16: SEER_EPI(EK_ATTN_OUT16); break;
+        case EK_FF2_16: SEER_EPI(EK_FF2_16); break;
+        case EK_CONV16: SEER_EPI(EK_CONV16); break;
+        default: SEER_EPI(-1); break;
+      }
     }
 #undef SEER_EPI
   }
@@ -447,10 +449,10 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   return SEER_OK;
 }
 
-template <int BN, int CG>
-static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, const Plan& pl, cudaStream_t stream) {
+template <int BN, int CG, int GRP>
+static int launch_gemm_grp(const CUtensorMap* maps, const GemmParams& p, const Plan& pl, cudaStream_t stream) {
   static SmemAttrOnce smem_attr;
-  { cudaError_t e = smem_attr.ensure(gemm_tc_kernel<BN, CG>, SMEM_LIMIT); if (e != cudaSuccess) return (int)e; }
+  { cudaError_t e = smem_attr.ensure(gemm_tc_kernel<BN, CG, GRP>, SMEM_LIMIT); if (e != cudaSuccess) return (int)e; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(pl.grid);
   cfg.blockDim = dim3(64 + 32 * pl.nepi);
@@ -465,11 +467,24 @@ static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, const Plan&
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, maps[0], maps[1], maps[2], maps[3], p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, GRP>, maps[0], maps[1], maps[2], maps[3], p);
   if (e != cudaSuccess) return (int)e;
   debug_note_gemm(BN, CG, pl.stages, pl.nepi, pl.ring, pl.bstat, p.epi_spec, p.mode);
   SEER_LAUNCH_CHECK();
   return SEER_OK;
+}
+
+template <int BN, int CG>
+static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, const Plan& pl, cudaStream_t stream) {
+  if (p.epi_spec == EK_FF1 || p.epi_spec == EK_FF1_PLAIN) {
+    if constexpr (BN == 128 || BN == 256) return launch_gemm_grp<BN, CG, 1>(maps, p, pl, stream);
+    else return SEER_EUNSUPPORTED;
+  }
+  if (p.epi_spec == EK_QKV_ROPE) {
+    if constexpr (BN != 320 && BN != 64) return launch_gemm_grp<BN, CG, 2>(maps, p, pl, stream);
+    else return SEER_EUNSUPPORTED;
+  }
+  return launch_gemm_grp<BN, CG, 0>(maps, p, pl, stream);
 }
 
 template <int BN>
