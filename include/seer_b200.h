@@ -172,9 +172,15 @@ int seer_b200_conv_in(const float* x, const float* w, const float* bias, float* 
  * statistics pass; col_stats may be NULL.  Needs B*F*H*W % 32 == 0 when given. */
 int seer_b200_conv_in_stats(const float* x, const float* w, const float* bias, float* out, float* col_stats, int B, int Cin, int F,
                             int H, int W, int Cout, void* stream);
-/* conv_out (3x3, Cin -> <=4, fp32): x [B*F*H*W, Cin] -> out (B,Cout,F,H,W); w_packed[co][tap][Cin].  :205,370. */
+/* conv_out (3x3, Cin -> <=4, fp32): x [B*F*H*W, Cin] -> out (B,Cout,F,H,W); w_packed[co][tap][Cin].  :205,370.  Any W (rows are
+ * processed in 64-pixel segments); also the VAE decoder's 128 -> 3 output conv at 256x256. */
 int seer_b200_conv_out(const float* x, const float* w_packed, const float* bias, float* out, int B, int Cin, int F, int H,
                        int W, int Cout, void* stream);
+
+/* P[r, :] = softmax(scale * S[r, :]) (fp32 in, bf16 out), one row per warp.  The row softmax of the VAE's single-head d = 512
+ * attention (diffusers 0.10.2 AttentionBlock behind vae.decode / vae.encode, utils/ddim_sampling_utils.py:39, inference.py:186):
+ * scores and P V run as tcgen05 GEMMs around it. */
+int seer_b200_softmax_rows(const float* S, int lds, long long rows, int L, float scale, void* P_bf16, int ldp, void* stream);
 
 /* nearest 2x upsample fp32 [n,H,W,C] -> bf16 [n,2H,2W,C] (resnet.py:52). */
 int seer_b200_upsample2x_to_bf16(const float* x, void* y, int n_img, int H, int W, int C, void* stream);

@@ -5,6 +5,7 @@ Public surface mirrors the reference (seervideodiffusion/SeerVideoLDM):
     FSTextTransformer <- seer/models/unet_3d_condition.py: FSTextTransformer
     DDIMSampler     <- ldm/models/diffusion/ddim_video.py: DDIMSampler
     ddim_sample     <- utils/ddim_sampling_utils.py: ddim_sample
+    AutoencoderKL   <- diffusers 0.10.2 AutoencoderKL as the reference calls it (vae.decode / vae.encode, SD-1.5 VAE)
 """
 from .config import UNetConfig, sd15_config  # noqa: F401
 
@@ -19,6 +20,9 @@ def __getattr__(name):  # lazy: importing the package must not require CUDA or t
     if name == "DDIMSampler":
         from .ddim import DDIMSampler
         return DDIMSampler
+    if name == "AutoencoderKL":
+        from .vae import AutoencoderKL
+        return AutoencoderKL
     if name in ("ddim_sample", "ddim_sample_latents"):
         from . import pipeline
         return getattr(pipeline, name)

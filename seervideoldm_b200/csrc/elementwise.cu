@@ -200,18 +200,22 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
 constexpr int CO_CK = 64;        // channels per chunk
 constexpr int CO_PIX = 4;        // output pixels per half-warp pass
 constexpr int CO_THREADS = 128;
+constexpr int CO_SEG = 64;       // output pixels of one image row per block (wider rows are split into segments: blockIdx.y)
 __global__ void __launch_bounds__(CO_THREADS) conv_out_kernel(const float* __restrict__ x, const float* __restrict__ wp,
                                                               const float* __restrict__ bias, float* __restrict__ out, int B,
                                                               int Cin, int F, int H, int W, int Cout) {
   pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   extern __shared__ __align__(16) float co_smem[];
-  float* sx = co_smem;                       // [3][W][CO_CK]
-  float* sw = sx + 3 * W * CO_CK;            // [9][4][CO_CK]
+  const int seg0 = blockIdx.y * CO_SEG;
+  const int segw = min(CO_SEG, W - seg0);
+  const int sw_ = segw + 2;                  // staged pixels per row: the segment plus a one-pixel halo on each side
+  float* sx = co_smem;                       // [3][segw + 2][CO_CK]
+  float* sw = sx + 3 * (CO_SEG + 2) * CO_CK; // [9][4][CO_CK]
   const int bf = blockIdx.x / H, y = blockIdx.x - bf * H;
   const int tid = threadIdx.x;
   const int hw = tid >> 4, l = tid & 15;     // half-warp index (0..7), channel quad
-  const int n_groups = (W + CO_PIX - 1) / CO_PIX;
-  constexpr int MAX_G = 2;                   // pixel groups per half-warp (W <= 64)
+  const int n_groups = (segw + CO_PIX - 1) / CO_PIX;
+  constexpr int MAX_G = 2;                   // pixel groups per half-warp (segment <= 64 pixels)
   float acc[MAX_G][CO_PIX][4];
 #pragma unroll
   for (int g = 0; g < MAX_G; ++g)
@@ -220,12 +224,12 @@ __global__ void __launch_bounds__(CO_THREADS) conv_out_kernel(const float* __res
 
   for (int c0 = 0; c0 < Cin; c0 += CO_CK) {
     __syncthreads();                         // previous chunk consumed
-    for (int i = tid; i < 3 * W * (CO_CK / 4); i += CO_THREADS) {
-      const int q = i % (CO_CK / 4), px = (i / (CO_CK / 4)) % W, rr = i / ((CO_CK / 4) * W);
-      const int yy = y + rr - 1;
+    for (int i = tid; i < 3 * sw_ * (CO_CK / 4); i += CO_THREADS) {
+      const int q = i % (CO_CK / 4), px = (i / (CO_CK / 4)) % sw_, rr = i / ((CO_CK / 4) * sw_);
+      const int yy = y + rr - 1, xx = seg0 + px - 1;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (yy >= 0 && yy < H) v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)bf * H + yy) * W + px) * Cin + c0) + q);
-      reinterpret_cast<float4*>(sx)[i] = v;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)bf * H + yy) * W + xx) * Cin + c0) + q);
+      reinterpret_cast<float4*>(sx)[(rr * sw_ + px) * (CO_CK / 4) + q] = v;
     }
     for (int i = tid; i < 9 * 4 * (CO_CK / 4); i += CO_THREADS) {
       const int q = i % (CO_CK / 4), co = (i / (CO_CK / 4)) % 4, tap = i / ((CO_CK / 4) * 4);
@@ -240,15 +244,15 @@ __global__ void __launch_bounds__(CO_THREADS) conv_out_kernel(const float* __res
       if (grp >= n_groups) break;
       const int x0 = grp * CO_PIX;
       for (int tap = 0; tap < 9; ++tap) {
-        const int rr = tap / 3, dx = tap % 3 - 1;
+        const int rr = tap / 3, dx = tap % 3;          // staged pixel of output pixel x and tap dx: x + dx (halo offset folded in)
         float4 wv[4];
 #pragma unroll
         for (int co = 0; co < 4; ++co) wv[co] = reinterpret_cast<const float4*>(sw)[(tap * 4 + co) * (CO_CK / 4) + l];
 #pragma unroll
         for (int p = 0; p < CO_PIX; ++p) {
-          const int xx = x0 + p + dx;
-          if (xx < 0 || xx >= W) continue;
-          const float4 v = reinterpret_cast<const float4*>(sx)[(rr * W + xx) * (CO_CK / 4) + l];
+          const int xs = x0 + p + dx;
+          if (xs >= sw_) continue;                     // ragged last pixel group of the segment
+          const float4 v = reinterpret_cast<const float4*>(sx)[(rr * sw_ + xs) * (CO_CK / 4) + l];
 #pragma unroll
           for (int co = 0; co < 4; ++co)
             acc[g][p][co] += (v.x * wv[co].x + v.y * wv[co].y) + (v.z * wv[co].z + v.w * wv[co].w);
@@ -269,9 +273,45 @@ __global__ void __launch_bounds__(CO_THREADS) conv_out_kernel(const float* __res
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);    // within the 16-lane half
         const int xq = grp * CO_PIX + p;
-        if (l == 0 && co < Cout && xq < W) out[((((size_t)b * Cout + co) * F + f) * H + y) * W + xq] = v + bias[co];
+        if (l == 0 && co < Cout && xq < segw) out[((((size_t)b * Cout + co) * F + f) * H + y) * W + seg0 + xq] = v + bias[co];
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Row softmax for the VAE's single-head d = 512 attention (diffusers 0.10.2 AttentionBlock, call site
+// utils/ddim_sampling_utils.py:39 through vae.decode): P[r, :] = softmax(scale * S[r, :]) as bf16, one warp per row.
+// The scores come from a tcgen05 GEMM (Q K^T) and P feeds another one (P V): at d = 512 the two contractions dominate.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, int lds_, long long rows, int L, float scale,
+                                                           __nv_bfloat16* __restrict__ P, int ldp) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(S + row * lds_);
+  const int n4 = L / 4;
+  const float sl2 = scale * 1.4426950408889634f;
+  float mx = -INFINITY;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = src[i];
+    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = src[i];
+    sum += (exp2f((v.x - mx) * sl2) + exp2f((v.y - mx) * sl2)) + (exp2f((v.z - mx) * sl2) + exp2f((v.w - mx) * sl2));
+  }
+  const float inv = 1.0f / warp_sum(sum);
+  uint2* dst = reinterpret_cast<uint2*>(P + row * ldp);
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = src[i];
+    uint2 o;
+    o.x = pack_bf16(exp2f((v.x - mx) * sl2) * inv, exp2f((v.y - mx) * sl2) * inv);
+    o.y = pack_bf16(exp2f((v.z - mx) * sl2) * inv, exp2f((v.w - mx) * sl2) * inv);
+    dst[i] = o;
   }
 }
 
@@ -442,11 +482,18 @@ extern "C" int seer_b200_conv_in_stats(const float* x, const float* w, const flo
 
 extern "C" int seer_b200_conv_out(const float* x, const float* w_packed, const float* bias, float* out, int B, int Cin, int F,
                                   int H, int W, int Cout, void* stream) {
-  SEER_CHECK_ARG(x && w_packed && bias && out && Cout <= 4 && Cin % CO_CK == 0 && W >= 1 && W <= 64);
-  const size_t smem = (size_t)(3 * W * CO_CK + 9 * 4 * CO_CK) * sizeof(float);
+  SEER_CHECK_ARG(x && w_packed && bias && out && Cout <= 4 && Cin % CO_CK == 0 && W >= 1);
+  const size_t smem = (size_t)(3 * (CO_SEG + 2) * CO_CK + 9 * 4 * CO_CK) * sizeof(float);
   static SmemAttrOnce smem_attr;
   if (smem > 48 * 1024) { cudaError_t e = smem_attr.ensure(conv_out_kernel, (int)smem); if (e != cudaSuccess) return (int)e; }
-  { cudaError_t le__ = launch_pdl(conv_out_kernel, (unsigned)(B * F * H), CO_THREADS, smem, (cudaStream_t)stream, x, w_packed, bias, out, B, Cin, F, H, W, Cout); if (le__ != cudaSuccess) return (int)le__; }
+  { cudaError_t le__ = launch_pdl(conv_out_kernel, dim3((unsigned)(B * F * H), (unsigned)ceil_div(W, CO_SEG)), CO_THREADS, smem, (cudaStream_t)stream, x, w_packed, bias, out, B, Cin, F, H, W, Cout); if (le__ != cudaSuccess) return (int)le__; }
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_softmax_rows(const float* S, int lds, long long rows, int L, float scale, void* P_bf16, int ldp, void* stream) {
+  SEER_CHECK_ARG(S && P_bf16 && rows > 0 && L > 0 && L % 4 == 0 && lds % 4 == 0 && ldp % 4 == 0);
+  { cudaError_t le__ = launch_pdl(softmax_rows_kernel, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, S, lds, rows, L, scale, (__nv_bfloat16*)P_bf16, ldp); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

@@ -229,16 +229,21 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
   const uint32_t res_bytes = res_mode == 1 ? 4096u : 2048u;
   float* vb = evec_base + ew * (2 * p.evec_floats);
   float* vc = vb + p.evec_floats;
-  // RoPE: this lane's row of the (cos, sin) table lives in a per-warp smem area (128 B per row, 16-byte quads XOR-swizzled by
-  // the row: the per-lane 16-byte reads are bank-conflict free).  It is cp.async'ed for the NEXT tile as soon as the last
-  // rotated chunk of the current tile is done, so the L2 round trip hides behind the tile switch; a lane only ever reads the
-  // row it copied itself, so cp.async.wait_group is all the synchronisation needed.
+  // RoPE: the (cos, sin) rows of this warp's 32 token rows live in a per-warp smem area (128 B per row, 16-byte quads
+  // XOR-swizzled by the row: the per-lane 16-byte reads are bank-conflict free).  The 32 rows are consecutive positions of one
+  // clip (rope_T % 32 == 0), i.e. ONE contiguous 4 KB block of the table: it is fetched with fully coalesced cp.async (a lane
+  // copies pieces of other lanes' rows — 16-byte pieces of 32 different rows per instruction cost 32 L1 wavefronts each and
+  // doubled the kernel's time) for the NEXT tile as soon as the last rotated chunk of the current one is done, so the L2 /
+  // DRAM round trip hides behind the tile switch.
   uint8_t* rope_buf = reinterpret_cast<uint8_t*>(evec_base + MAX_EPI_WARPS * 2 * p.evec_floats) + ew * ROPE_BYTES_PER_WARP;
   auto rope_prefetch = [&](int t_mb) {
-    const int row = min((t_mb * CG + rank) * BM + q * 32 + lane, p.M - 1);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.rope_tab + (size_t)(row % p.rope_T) * ROPE_PAIRS);
+    const int r0 = (t_mb * CG + rank) * BM + q * 32;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.rope_tab + (size_t)(r0 % p.rope_T) * ROPE_PAIRS);
 #pragma unroll
-    for (int jq = 0; jq < 8; ++jq) cp_async_16(rope_buf + sw128(lane, jq), src + jq * 16, true);
+    for (int i = 0; i < 8; ++i) {
+      const int k = i * 32 + lane;           // 16-byte piece k of the block = quad (k & 7) of row (k >> 3)
+      cp_async_16(rope_buf + sw128(k >> 3, k & 7), src + k * 16, true);
+    }
     cp_async_commit();
   };
 
@@ -412,7 +417,11 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
         if constexpr (ROPE) {
           const int gc0 = n0 + c * 32;                       // first output column of this chunk (warp-uniform)
           if (gc0 < p.rope_cols) {
-            if (!rope_landed) { cp_async_wait<0>(); rope_landed = true; }   // rows issued at the end of the previous tile
+            if (!rope_landed) {              // rows issued at the end of the previous tile; pieces were copied by other lanes
+              cp_async_wait<0>();
+              __syncwarp();
+              rope_landed = true;
+            }
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {                 // 8-column groups = 4 rotary pairs
               int w = rope_within + 8 * g8;                  // channel of the group's first column inside its head (multiple of 8)
@@ -434,6 +443,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
           while (rope_within >= p.rope_d) rope_within -= p.rope_d;
           if (j + 1 == my_nch && has_next) {                  // every lane has read its row for the last time this tile
             if (!rope_landed) cp_async_wait<0>();             // (a tile of V columns only never waited: drain before re-issuing)
+            __syncwarp();                                     // every lane is done reading: the block may be overwritten
             rope_prefetch(mb_n);
           }
         }

@@ -115,11 +115,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = unit; tile < p.num_tiles; tile += nunits) {
         const int mb = tile / p.tiles_n, nb = tile - mb * p.tiles_n;
         const int m0 = (mb * CG + rank) * BM, n0 = nb * BN + rank * (BN / CG);
-        int img0 = 0, y0 = 0;
+        int img0 = 0, y0 = 0, x0 = 0;
         if (p.mode == 1) {
           const int hw = p.H * p.W;
           img0 = m0 / hw;
-          y0 = (m0 % hw) / p.W;
+          const int rem = m0 - img0 * hw;
+          y0 = rem / p.W;
+          x0 = rem - y0 * p.W;               // 0 unless the image is wider than a 128-pixel tile (W > 128: row segments)
         }
         // conv tap cursor, advanced incrementally (no division by the run-time tap count on the producer's critical path)
         int t_kx = 0, t_ky = 0, t_c0 = 0;
@@ -136,7 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               } else {
                 // K order [Cin/64][tap][64]: the 9 shifted views of one 64-channel slab are fetched back to back, so
                 // the slab (and its halo) is served from L2 while it is hot instead of being re-read 9 x Cin/64 k-blocks apart
-                tma_load_4d(sA, &tmA, &full_bar[s], t_c0, t_kx + p.off_x, p.cstride * y0 + t_ky + p.off_y, img0);
+                tma_load_4d(sA, &tmA, &full_bar[s], t_c0, p.cstride * x0 + t_kx + p.off_x, p.cstride * y0 + t_ky + p.off_y, img0);
               }
             } else {
               tma_load_2d(sA, &tmA2, &full_bar[s], (kb - p.kb_main) * BK, m0);
@@ -156,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               } else {
                 // K order [Cin/64][tap][64]: the 9 shifted views of one 64-channel slab are fetched back to back, so
                 // the slab (and its halo) is served from L2 while it is hot instead of being re-read 9 x Cin/64 k-blocks apart
-                tma_load_4d_cg2(sA, &tmA, fb, t_c0, t_kx + p.off_x, p.cstride * y0 + t_ky + p.off_y, img0);
+                tma_load_4d_cg2(sA, &tmA, fb, t_c0, p.cstride * x0 + t_kx + p.off_x, p.cstride * y0 + t_ky + p.off_y, img0);
               }
             } else {
               tma_load_2d_cg2(sA, &tmA2, fb, (kb - p.kb_main) * BK, m0);
@@ -481,7 +483,7 @@ static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, const Plan&
     else return SEER_EUNSUPPORTED;
   }
   if (p.epi_spec == EK_QKV_ROPE) {
-    if constexpr (BN != 320 && BN != 64) return launch_gemm_grp<BN, CG, 2>(maps, p, pl, stream);
+    if constexpr (BN != 320) return launch_gemm_grp<BN, CG, 2>(maps, p, pl, stream);
     else return SEER_EUNSUPPORTED;
   }
   return launch_gemm_grp<BN, CG, 0>(maps, p, pl, stream);
@@ -579,15 +581,22 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
     // straddles an image boundary mid-row.
     const int cs = d.conv_stride > 1 ? d.conv_stride : 1;
     const int W = d.W / cs, H = d.H / cs;          // OUTPUT geometry: an M tile is whole output rows
-    if (W > 128 || 128 % W != 0) return SEER_EUNSUPPORTED;
-    const int rows = 128 / W;
-    int bh, bn_img;
-    if (rows <= H) {
-      if (H % rows != 0) return SEER_EUNSUPPORTED;
-      bh = rows; bn_img = 1;
+    int bw, bh, bn_img;
+    if (W > 128) {
+      // images wider than one 128-pixel tile (the VAE decoder's 256x256 level): a tile is a 128-pixel row segment
+      if (W % 128 != 0) return SEER_EUNSUPPORTED;
+      bw = 128; bh = 1; bn_img = 1;
     } else {
-      if (rows % H != 0) return SEER_EUNSUPPORTED;
-      bh = H; bn_img = rows / H;
+      if (128 % W != 0) return SEER_EUNSUPPORTED;
+      const int rows = 128 / W;
+      bw = W;
+      if (rows <= H) {
+        if (H % rows != 0) return SEER_EUNSUPPORTED;
+        bh = rows; bn_img = 1;
+      } else {
+        if (rows % H != 0) return SEER_EUNSUPPORTED;
+        bh = H; bn_img = rows / H;
+      }
     }
     p.mode = 1;
     p.cblk = d.Cin / 64;
@@ -605,7 +614,7 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
       p.up_wshift = 0;
       while ((1 << p.up_wshift) < W) ++p.up_wshift;
     }
-    if ((rc = make_map_4d(&maps[0], d.X, d.n_img, d.H, d.W, d.Cin, W, bh, bn_img, cs))) return rc;
+    if ((rc = make_map_4d(&maps[0], d.X, d.n_img, d.H, d.W, d.Cin, bw, bh, bn_img, cs))) return rc;
   } else {
     p.mode = 0;
     p.cblk = 1; p.H = 1; p.W = 1;

@@ -267,6 +267,17 @@ def scta_row_index(B: int, F: int, H: int, W: int, device="cuda") -> torch.Tenso
     return out
 
 
+@_timed_op
+def softmax_rows(S: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 softmax(scale * S) along the last dim of an fp32 [rows, L] matrix (VAE attention block)."""
+    _cuda(S, "S")
+    if out is None:
+        out = torch.empty(tuple(S.shape), device=S.device, dtype=torch.bfloat16)
+    _ops.softmax_rows(S, float(scale), out)
+    _count()
+    return out
+
+
 def rope_table(freqs: torch.Tensor, T: int) -> torch.Tensor:
     """[T, n_freqs, 2] fp32 (cos, sin)(pos * freqs[j]) — the table the q/k/v GEMM's fused rotary epilogue reads."""
     _cuda(freqs, "freqs")

@@ -451,6 +451,16 @@ def _rope_table(freqs, out) -> None:
     _lib.check(rc, "rope_table")
 
 
+def _softmax_rows(S, scale, out) -> None:
+    _chk(S, "S", f32, 2); _chk(out, "out", bf16, 2, dev=S.device)
+    if tuple(out.shape) != tuple(S.shape):
+        raise ValueError("softmax_rows: out must have the shape of S")
+    with _Dev(S) as stream:
+        rc = _lib.lib().seer_b200_softmax_rows(_p(S), S.stride(0), S.shape[0], S.shape[1], float(scale), _p(out), out.stride(0), stream)
+    _lib.check(rc, "softmax_rows")
+
+
+_define("softmax_rows(Tensor S, float scale, Tensor(a!) out) -> ()", _softmax_rows)
 _define("rope_table(Tensor freqs, Tensor(a!) out) -> ()", _rope_table)
 _define("rope(Tensor(a!) qk, int pos_div, int pos_mod, int heads, int head_dim, int q_col, int k_col, Tensor freqs) -> ()", _rope)
 _define("timestep_embedding(Tensor t, Tensor(a!) out, float shift, bool flip_sin_to_cos) -> ()", _timestep_embedding)

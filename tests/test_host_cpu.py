@@ -279,3 +279,29 @@ def test_torch_op_library_registration():
                                          None, 0, 0, 0)
         assert rc == 0
         torch.ops.seer_b200.cast_bf16(torch.empty(8, device="cuda"), torch.empty(8, dtype=torch.bfloat16, device="cuda"))
+
+
+def test_vae_schema_and_oracle_cpu():
+    """The AutoencoderKL state-dict schema is the published SD-1.5 VAE's (83 653 863 parameters, diffusers key names) and the CPU
+    oracle runs both directions on it; known-answer: encode/decode shapes and the x8 geometry."""
+    import math
+    from oracle import vae_oracle as vo
+    from seervideoldm_b200.vae import AutoencoderKL, random_vae_state_dict, vae_schema
+    schema = vae_schema()
+    assert sum(math.prod(v) for v in schema.values()) == 83_653_863 and len(schema) == 248
+    for k in ("encoder.down_blocks.1.resnets.0.conv_shortcut.weight", "decoder.up_blocks.2.resnets.0.conv_shortcut.weight",
+              "decoder.mid_block.attentions.0.proj_attn.bias", "encoder.down_blocks.2.downsamplers.0.conv.weight",
+              "decoder.up_blocks.0.upsamplers.0.conv.bias", "quant_conv.weight", "post_quant_conv.bias"):
+        assert k in schema, k
+    assert "encoder.down_blocks.3.downsamplers.0.conv.weight" not in schema and "decoder.up_blocks.3.upsamplers.0.conv.weight" not in schema
+    sd = random_vae_state_dict(seed=0)
+    vae = AutoencoderKL()
+    vae.load_state_dict(sd, strict=True)                      # same keys / shapes as the module tree
+    assert list(vae.state_dict().keys()) == list(schema.keys())
+    z = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(0))
+    img = vo.decode(sd, z)
+    assert img.shape == (1, 3, 64, 64)
+    m = vo.encode_moments(sd, img)
+    assert m.shape == (1, 8, 8, 8)
+    with pytest.raises(RuntimeError):
+        vae.decode(z)                                         # CPU module: no CPU path
