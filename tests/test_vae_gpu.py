@@ -63,7 +63,7 @@ def test_conv_out_wide_rows():
         h = gen(5, n * H * W, cin).to(DEV)
         wo, bo = gen(6, cout, cin, 3, 3) * 0.05, gen(7, cout).to(DEV)
         out = ops.conv_out(h, pack_conv_out(wo).to(DEV), bo, n, 1, H, W)
-        ref = F.conv2d(h.reshape(n, H, W, cin).permute(0, 3, 1, 2), wo.to(DEV), bo, padding=1)
+        ref = F.conv2d(h.double().reshape(n, H, W, cin).permute(0, 3, 1, 2), wo.to(DEV).double(), bo.double(), padding=1).float()
         assert out.shape == (n, cout, 1, H, W) and so.rel_l2(out[:, :, 0].cpu(), ref.cpu()) < 1e-5, (n, H, W, cin, cout)
 
 
