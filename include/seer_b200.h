@@ -90,9 +90,9 @@ typedef struct SeerGemmDesc {
   int conv_stride; int conv_taps_w, conv_taps_h, conv_off_x, conv_off_y; int out_up_phase;
   /* rotary embedding fused into the epilogue (rope_tab != NULL; needs the LayerNorm fold, a bias and a bf16-only output):
    * output columns [0, rope_cols) are heads of width rope_d whose first 32 channels are rotated as interleaved pairs
-   * (2j, 2j+1) by the angle of row position (r % rope_T): rope_tab[pos][16][2] = (cos, sin) from seer_b200_rope_table.
+   * (2j, 2j+1) by the angle of row position (r % rope_T): rope_tab[pos][16][2] = fp16 (cos, sin) from seer_b200_rope_table.
    * Replaces rotary_emb.rotate_queries_or_keys on q and k, attention.py:649-651, applied before the bf16 rounding. */
-  const float* rope_tab; int rope_T; int rope_cols; int rope_d;
+  const void* rope_tab; int rope_T; int rope_cols; int rope_d;
 } SeerGemmDesc;
 int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream);
 /* sizeof(SeerGemmDesc) as compiled into the library (binding sanity check) */
@@ -152,9 +152,10 @@ int seer_b200_scta_row_index(int B, int F, int H, int W, int* out_dev, int* out_
 int seer_b200_rope_inplace(void* qk_bf16, int ld, int M, int tokens_per_clip, int heads, int head_dim, int q_col, int k_col,
                            const float* freqs, int n_freqs, void* stream);
 
-/* out[pos][j] = (cos, sin)(pos * freqs[j]) for pos < T, j < n_freqs (fp32, sincosf of the fp32 product — the same angles
- * seer_b200_rope_inplace uses): the table SeerGemmDesc::rope_tab points at.  out: T * n_freqs * 2 floats. */
-int seer_b200_rope_table(const float* freqs, int n_freqs, int T, float* out, void* stream);
+/* out[pos][j] = fp16 pair (cos, sin)(pos * freqs[j]) for pos < T, j < n_freqs (sincosf of the fp32 product — the same angles
+ * seer_b200_rope_inplace uses — rounded to fp16: 11 significant bits in [-1, 1]): the table SeerGemmDesc::rope_tab points at.
+ * out: T * n_freqs * 2 halves. */
+int seer_b200_rope_table(const float* freqs, int n_freqs, int T, void* out, void* stream);
 
 /* diffusers Timesteps(dim, flip_sin_to_cos, shift): t[B] (fp32) -> out[B, dim].  unet_3d_condition.py:307. */
 int seer_b200_timestep_embedding(const float* t, float* out, int B, int dim, float shift, int flip_sin_to_cos, void* stream);

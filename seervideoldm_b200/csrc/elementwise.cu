@@ -62,15 +62,15 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qk, int ld, int M, int t
   }
 }
 
-// (cos, sin) table for the RoPE fused into the q/k/v projection's epilogue: tab[pos][j] = sincosf(pos * freqs[j])
-__global__ void rope_table_kernel(const float* __restrict__ freqs, int half, int T, float2* __restrict__ tab) {
+// (cos, sin) table for the RoPE fused into the q/k/v projection's epilogue: tab[pos][j] = half2(sincosf(pos * freqs[j]))
+__global__ void rope_table_kernel(const float* __restrict__ freqs, int half, int T, __half2* __restrict__ tab) {
   pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T * half) return;
   const int pos = i / half, j = i - pos * half;
   float sn, cs;
   sincosf((float)pos * __ldg(freqs + j), &sn, &cs);
-  tab[i] = make_float2(cs, sn);
+  tab[i] = __floats2half2_rn(cs, sn);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -439,9 +439,9 @@ extern "C" int seer_b200_rope_inplace(void* qk_bf16, int ld, int M, int tokens_p
   return SEER_OK;
 }
 
-extern "C" int seer_b200_rope_table(const float* freqs, int n_freqs, int T, float* out, void* stream) {
+extern "C" int seer_b200_rope_table(const float* freqs, int n_freqs, int T, void* out, void* stream) {
   SEER_CHECK_ARG(freqs && out && n_freqs > 0 && T > 0);
-  { cudaError_t le__ = launch_pdl(rope_table_kernel, ceil_div(T * n_freqs, 256), 256, 0, (cudaStream_t)stream, freqs, n_freqs, T, (float2*)out); if (le__ != cudaSuccess) return (int)le__; }
+  { cudaError_t le__ = launch_pdl(rope_table_kernel, ceil_div(T * n_freqs, 256), 256, 0, (cudaStream_t)stream, freqs, n_freqs, T, (__half2*)out); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

@@ -56,7 +56,7 @@ constexpr int EK_CONV16 = EF_OUT16 | EF_CSTAT;                        // conv1: 
 // accumulators before the single bf16 rounding — the separate read-modify-write RoPE pass over [M, 2C] disappears
 constexpr int EK_QKV_ROPE = EF_LN | EF_OUT16 | EF_ROPE;
 constexpr int ROPE_PAIRS = 16;                                        // rotary dim 32 = 16 (cos, sin) pairs per row (rotary_emb dim=32)
-constexpr int ROPE_BYTES_PER_WARP = 32 * ROPE_PAIRS * 8;              // [32 rows][16 x float2] per epilogue warp
+constexpr int ROPE_BYTES_PER_WARP = 32 * ROPE_PAIRS * 4;              // [32 rows][16 x half2 (cos, sin)] per epilogue warp
 
 struct GemmParams {
   int M, N;            // N = accumulator columns (GEGLU: twice the output columns)
@@ -70,6 +70,7 @@ struct GemmParams {
   int ntaps, taps_w, taps_h, off_x, off_y, cstride;   // conv taps: tap t reads pixel (s*y + t / taps_w + off_y, s*x + t % taps_w + off_x)
   int up_phase;        // 0: output row = GEMM row; 1 + (2 py + px): rows are the (py, px) phase of a nearest-2x upsampled image
   int up_wshift;       //    (low-res width = 1 << up_wshift): out row = ((m >> ws) << (ws + 2)) + py * 2W + 2 (m & (W - 1)) + px
+  int l2_prefetch;     // > 0: the producer prefetches the A rows / residual tile of the tile this many iterations ahead into L2
   int evec_floats;     // floats per staged per-tile vector (bias / LN column sums) and warp: EVEC_FLOATS or EVEC_FLOATS_320
   int bstat;           // 1: the whole Wt panel of this CTA's (fixed) n-block is resident in smem; only A is streamed
   int epi_spec;        // EK_* combination compiled as a specialisation, or -1 (generic runtime-flag epilogue)
@@ -88,9 +89,10 @@ struct GemmParams {
   int row_parts_in;
   float ln_inv_dim, ln_eps;
   const float* ln_colsum;
-  // rotary embedding in the epilogue (EK_QKV_ROPE): rope_tab[pos][16] = (cos, sin)(pos * freq_j), pos = row % rope_T; output
-  // columns [0, rope_cols) are heads of width rope_d whose first 32 channels rotate as interleaved pairs
-  const float2* rope_tab;
+  // rotary embedding in the epilogue (EK_QKV_ROPE): rope_tab[pos][16] = half2 (cos, sin)(pos * freq_j), pos = row % rope_T;
+  // output columns [0, rope_cols) are heads of width rope_d whose first 32 channels rotate as interleaved pairs.  (cos, sin)
+  // in fp16: 11 significant bits in [-1, 1] — a quarter of the bf16 rounding of the rotated output, half the smem / L2 bytes
+  const __half2* rope_tab;
   int rope_T, rope_cols, rope_d;
 };
 
@@ -229,9 +231,9 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
   const uint32_t res_bytes = res_mode == 1 ? 4096u : 2048u;
   float* vb = evec_base + ew * (2 * p.evec_floats);
   float* vc = vb + p.evec_floats;
-  // RoPE: the (cos, sin) rows of this warp's 32 token rows live in a per-warp smem area (128 B per row, 16-byte quads
+  // RoPE: the (cos, sin) rows of this warp's 32 token rows live in a per-warp smem area (64 B per row, 16-byte quads
   // XOR-swizzled by the row: the per-lane 16-byte reads are bank-conflict free).  The 32 rows are consecutive positions of one
-  // clip (rope_T % 32 == 0), i.e. ONE contiguous 4 KB block of the table: it is fetched with fully coalesced cp.async (a lane
+  // clip (rope_T % 32 == 0), i.e. ONE contiguous 2 KB block of the table: it is fetched with fully coalesced cp.async (a lane
   // copies pieces of other lanes' rows — 16-byte pieces of 32 different rows per instruction cost 32 L1 wavefronts each and
   // doubled the kernel's time) for the NEXT tile as soon as the last rotated chunk of the current one is done, so the L2 /
   // DRAM round trip hides behind the tile switch.
@@ -240,9 +242,9 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
     const int r0 = (t_mb * CG + rank) * BM + q * 32;
     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.rope_tab + (size_t)(r0 % p.rope_T) * ROPE_PAIRS);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = i * 32 + lane;           // 16-byte piece k of the block = quad (k & 7) of row (k >> 3)
-      cp_async_16(rope_buf + sw128(k >> 3, k & 7), src + k * 16, true);
+    for (int i = 0; i < 4; ++i) {
+      const int k = i * 32 + lane;           // 16-byte piece k of the block = quad (k & 3) of row (k >> 2)
+      cp_async_16(rope_buf + sw64(k >> 2, k & 3), src + k * 16, true);
     }
     cp_async_commit();
   };
@@ -403,6 +405,26 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
         advance_pf();
         __syncwarp();
       }
+      // RoPE: the chunk's (cos, sin) quads are requested BEFORE the accumulator wait / affine, so the shared-memory latency is
+      // off the chunk's dependent chain (the epilogue warps are latency-bound: two warps per scheduler)
+      uint4 rope_q[4] = {};
+      bool rope_on[4] = {false, false, false, false};
+      if constexpr (ROPE) {
+        if (n0 + c * 32 < p.rope_cols) {   // warp-uniform
+          if (!rope_landed) {              // rows issued at the end of the previous tile; pieces were copied by other lanes
+            cp_async_wait<0>();
+            __syncwarp();
+            rope_landed = true;
+          }
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) { // 8-column groups = 4 rotary pairs = one 16-byte quad of half2 (cos, sin)
+            int w = rope_within + 8 * g8;  // channel of the group's first column inside its head (a multiple of 8)
+            if (w >= p.rope_d) w -= p.rope_d;
+            rope_on[g8] = w < 2 * ROPE_PAIRS;      // warp-uniform: channels >= 32 of a head pass through
+            if (rope_on[g8]) rope_q[g8] = lds128u(rope_buf + sw64(lane, w >> 3));
+          }
+        }
+      }
       if (!have) {                         // first chunk of a tile whose accumulator was not complete one step ago
         mbar_wait(&tmem_full_bar[buf], buf_par);
         tc_fence_after();
@@ -415,27 +437,16 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
       if constexpr (!GEGLU) {
         epi_affine_dispatch(f, v, f_ln, f_bias, bias_smem, vc + c * 32, vb + c * 32, bias_row + n0 + c * 32, rstd2, nmean2);
         if constexpr (ROPE) {
-          const int gc0 = n0 + c * 32;                       // first output column of this chunk (warp-uniform)
-          if (gc0 < p.rope_cols) {
-            if (!rope_landed) {              // rows issued at the end of the previous tile; pieces were copied by other lanes
-              cp_async_wait<0>();
-              __syncwarp();
-              rope_landed = true;
-            }
 #pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {                 // 8-column groups = 4 rotary pairs
-              int w = rope_within + 8 * g8;                  // channel of the group's first column inside its head (multiple of 8)
-              if (w >= p.rope_d) w -= p.rope_d;
-              if (w < 2 * ROPE_PAIRS) {                      // warp-uniform: channels >= 32 of a head pass through
-                const float4 t0 = lds128(rope_buf + sw128(lane, w >> 2));           // (c, s) of pairs w/2, w/2 + 1
-                const float4 t1 = lds128(rope_buf + sw128(lane, (w >> 2) + 1));     //            pairs w/2 + 2, w/2 + 3
-                const float cs[4] = {t0.x, t0.z, t1.x, t1.z}, sn[4] = {t0.y, t0.w, t1.y, t1.w};
+          for (int g8 = 0; g8 < 4; ++g8) {
+            if (rope_on[g8]) {
+              const uint32_t qw[4] = {rope_q[g8].x, rope_q[g8].y, rope_q[g8].z, rope_q[g8].w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float x0, x1;
-                  f2_unpack(f[4 * g8 + i], x0, x1);
-                  f[4 * g8 + i] = f2_pack(fmaf(x0, cs[i], -(x1 * sn[i])), fmaf(x1, cs[i], x0 * sn[i]));
-                }
+              for (int i = 0; i < 4; ++i) {
+                const float2 cs = __half22float2(*reinterpret_cast<const __half2*>(&qw[i]));     // (cos, sin) of pair i
+                float x0, x1;
+                f2_unpack(f[4 * g8 + i], x0, x1);
+                f[4 * g8 + i] = f2_pack(fmaf(x0, cs.x, -(x1 * cs.y)), fmaf(x1, cs.x, x0 * cs.y));
               }
             }
           }

@@ -123,6 +123,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           y0 = rem / p.W;
           x0 = rem - y0 * p.W;               // 0 unless the image is wider than a 128-pixel tile (W > 128: row segments)
         }
+        if (p.l2_prefetch) {
+          // streaming (small-K) launch: pull the operand rows and the residual tile of a later tile of this CTA into L2 now
+          const int t2 = tile + p.l2_prefetch * nunits;
+          if (t2 < p.num_tiles && elect_one()) {
+            const int mb2 = t2 / p.tiles_n, nb2 = t2 - mb2 * p.tiles_n;
+            const int m2 = (mb2 * CG + rank) * BM;
+            for (int kb = 0; kb < p.kb_main; ++kb) tma_prefetch_2d(&tmA, kb * BK, m2);
+            for (int kb = p.kb_main; kb < p.kb_total; ++kb) tma_prefetch_2d(&tmA2, (kb - p.kb_main) * BK, m2);
+            if (p.res_mode) {
+              const int cpb = p.res_mode == 1 ? 32 : 32;      // residual map boxes are 32 x 32 elements
+              for (int ry = 0; ry < BM / 32; ++ry)
+                for (int cx = 0; cx < BN / 32; ++cx) tma_prefetch_2d(&tmRes, nb2 * BN + cx * cpb, m2 + ry * 32);
+            }
+          }
+          __syncwarp();
+        }
         // conv tap cursor, advanced incrementally (no division by the run-time tap count on the producer's critical path)
         int t_kx = 0, t_ky = 0, t_c0 = 0;
         for (int kb = 0; kb < p.kb_total; ++kb) {
@@ -434,14 +450,17 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
     for (int rg = want_ring; rg >= (rm ? 2 : 1); --rg) {
       int st = (avail - ne * rg * pl.slot_bytes) / stage_bytes;
       if (st < 2) continue;
-      if (st > 6) st = 6;      // (7 / 8 stages on the long-K launches measured no gain: 82.3 ms per evaluation either way)
-      const int score = (st > 5 ? 5 : st) * 100 + (ne == 8 ? 30 : 0) + rg * 5;
+      // (7 / 8 stages on the long-K launches measured no gain: 82.3 ms per evaluation either way; the streaming small-K
+      //  launches are bound by bytes in flight — their rings go to MAX_STAGES)
+      const int st_cap = (!d.X && Kd <= 640.0) ? env_int("SEER_GEMM_STAGES_SMALLK", MAX_STAGES) : 6;
+      if (st > st_cap) st = st_cap;
+      const int score = (st > 5 ? 5 : st) * 100 + (ne == 8 ? 30 : 0) + rg * 5 + (st > 5 ? st - 5 : 0);
       if (score > best_score) { best_score = score; pl.nepi = ne; pl.ring = rg; pl.stages = st; }
     }
   }
   if (best_score < 0) return SEER_EUNSUPPORTED;
   if (pl.stages < 2) return SEER_EUNSUPPORTED;
-  if (pl.stages > 6) pl.stages = 6;
+  if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
   const int fs = env_int("SEER_GEMM_STAGES", 0);
   if (fs >= 2 && fs <= pl.stages) pl.stages = fs;
   pl.smem_bytes = (pl.bstat ? panel_bytes : 0) + pl.stages * stage_bytes + pl.nepi * pl.ring * pl.slot_bytes + BAR_BYTES +
@@ -564,6 +583,8 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   }
   p.bstat = pl.bstat;
   p.evec_floats = pl.bn == 320 ? EVEC_FLOATS_320 : EVEC_FLOATS;
+  // L2 prefetch distance (tiles of this CTA) for the streaming launches: plain GEMM with K <= 640
+  p.l2_prefetch = (!d.X && d.K1 + d.K2 <= 640) ? env_int("SEER_GEMM_L2PF", 2) : 0;
   p.stages = pl.stages; p.nepi = pl.nepi; p.ring = pl.ring; p.slot_bytes = pl.slot_bytes;
   p.bias = d.bias; p.ldb = d.ldb > 0 ? d.ldb : d.N; p.bias_div = d.bias_div > 0 ? d.bias_div : BIAS_ONE_ROW;
   p.res_mode = d.residual ? (d.residual_bf16 ? 2 : 1) : 0;
@@ -572,7 +593,7 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   p.geglu = d.geglu ? 1 : 0;
   p.col_stats = d.col_stats; p.row_stats_out = d.row_stats_out;
   p.row_stats_in = d.row_stats_in; p.row_parts_in = d.row_parts_in; p.ln_eps = d.ln_eps; p.ln_colsum = d.ln_colsum;
-  p.rope_tab = reinterpret_cast<const float2*>(d.rope_tab); p.rope_T = d.rope_T; p.rope_cols = d.rope_cols; p.rope_d = d.rope_d;
+  p.rope_tab = reinterpret_cast<const __half2*>(d.rope_tab); p.rope_T = d.rope_T; p.rope_cols = d.rope_cols; p.rope_d = d.rope_d;
 
   CUtensorMap maps[4];
   int Ktot;

@@ -279,9 +279,9 @@ def softmax_rows(S: torch.Tensor, scale: float, out: Optional[torch.Tensor] = No
 
 
 def rope_table(freqs: torch.Tensor, T: int) -> torch.Tensor:
-    """[T, n_freqs, 2] fp32 (cos, sin)(pos * freqs[j]) — the table the q/k/v GEMM's fused rotary epilogue reads."""
+    """[T, n_freqs, 2] fp16 (cos, sin)(pos * freqs[j]) — the table the q/k/v GEMM's fused rotary epilogue reads."""
     _cuda(freqs, "freqs")
-    out = torch.empty((T, freqs.numel(), 2), device=freqs.device, dtype=torch.float32)
+    out = torch.empty((T, freqs.numel(), 2), device=freqs.device, dtype=torch.float16)
     _ops.rope_table(freqs, out)
     _count()
     return out

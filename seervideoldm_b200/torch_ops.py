@@ -171,7 +171,7 @@ def _gemm_desc(a, x_img, a2, wt, bias, bias_div, residual, out_f32, out_bf16, ge
             raise ValueError("row_stats_out must be [parts, M, 2]")
         d.row_stats_out = row_stats_out.data_ptr()
     if rope_tab is not None:
-        _chk(rope_tab, "rope_tab", f32, 3, contiguous=True, dev=dev)
+        _chk(rope_tab, "rope_tab", torch.float16, 3, contiguous=True, dev=dev)
         if tuple(rope_tab.shape) != (rope_T, 16, 2):
             raise ValueError(f"rope_tab must be [rope_T = {rope_T}, 16, 2] (seer_b200.rope_table)")
         d.rope_tab, d.rope_T, d.rope_cols, d.rope_d = rope_tab.data_ptr(), rope_T, rope_cols, rope_d
@@ -443,7 +443,7 @@ def _geglu_f32(h, out) -> None:
 
 
 def _rope_table(freqs, out) -> None:
-    _chk(freqs, "freqs", f32, 1); _chk(out, "out", f32, 3, contiguous=True, dev=freqs.device)
+    _chk(freqs, "freqs", f32, 1); _chk(out, "out", torch.float16, 3, contiguous=True, dev=freqs.device)
     if out.shape[1] != freqs.numel() or out.shape[2] != 2:
         raise ValueError("rope_table: out must be [T, n_freqs, 2]")
     with _Dev(freqs) as stream:

@@ -358,7 +358,8 @@ def test_gemm_qkv_rope_fused(d, Fr, hw, B):
     freqs = (1.0 / (10000.0 ** (torch.arange(0, 32, 2).float() / 32))).to(DEV)
     tab = ops.rope_table(freqs, T)
     ang = torch.arange(T, device=DEV).float()[:, None] * freqs[None, :]
-    assert torch.allclose(tab[..., 0], ang.cos(), atol=2e-6) and torch.allclose(tab[..., 1], ang.sin(), atol=2e-6)
+    assert tab.dtype == torch.float16
+    assert torch.allclose(tab[..., 0].float(), ang.cos(), atol=6e-4) and torch.allclose(tab[..., 1].float(), ang.sin(), atol=6e-4)
     fused = ops.gemm_ex(prod.out, wf, bias=bias_f, out_dtype=torch.bfloat16, ln=(prod.row_stats, colsum, 1e-5), rope=(tab, 2 * C, d)).out
     assert "spec=273" in ops.last_gemm_kernel(), ops.last_gemm_kernel()        # EK_QKV_ROPE = LN | OUT16 | ROPE
     # reference: the same projection in fp32, rotated in fp64 with the oracle's rotary statement
