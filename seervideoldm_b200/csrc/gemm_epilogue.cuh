@@ -56,7 +56,7 @@ constexpr int EK_CONV16 = EF_OUT16 | EF_CSTAT;                        // conv1: 
 // accumulators before the single bf16 rounding — the separate read-modify-write RoPE pass over [M, 2C] disappears
 constexpr int EK_QKV_ROPE = EF_LN | EF_OUT16 | EF_ROPE;
 constexpr int ROPE_PAIRS = 16;                                        // rotary dim 32 = 16 (cos, sin) pairs per row (rotary_emb dim=32)
-constexpr int ROPE_BYTES_PER_WARP = 32 * ROPE_PAIRS * 4;              // [32 rows][16 x half2 (cos, sin)] per epilogue warp
+constexpr int ROPE_BYTES_PER_WARP = 2 * 32 * ROPE_PAIRS * 4;          // double-buffered [32 rows][16 x half2 (cos, sin)] per epilogue warp
 
 struct GemmParams {
   int M, N;            // N = accumulator columns (GEGLU: twice the output columns)
@@ -231,20 +231,21 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
   const uint32_t res_bytes = res_mode == 1 ? 4096u : 2048u;
   float* vb = evec_base + ew * (2 * p.evec_floats);
   float* vc = vb + p.evec_floats;
-  // RoPE: the (cos, sin) rows of this warp's 32 token rows live in a per-warp smem area (64 B per row, 16-byte quads
-  // XOR-swizzled by the row: the per-lane 16-byte reads are bank-conflict free).  The 32 rows are consecutive positions of one
-  // clip (rope_T % 32 == 0), i.e. ONE contiguous 2 KB block of the table: it is fetched with fully coalesced cp.async (a lane
-  // copies pieces of other lanes' rows — 16-byte pieces of 32 different rows per instruction cost 32 L1 wavefronts each and
-  // doubled the kernel's time) for the NEXT tile as soon as the last rotated chunk of the current one is done, so the L2 /
-  // DRAM round trip hides behind the tile switch.
+  // RoPE: the (cos, sin) rows of this warp's 32 token rows live in a double-buffered per-warp smem area (64 B per row, 16-byte
+  // quads XOR-swizzled by the row: the per-lane 16-byte reads are bank-conflict free).  The 32 rows are consecutive positions of
+  // one clip (rope_T % 32 == 0), i.e. ONE contiguous 2 KB block of the table: it is fetched with fully coalesced cp.async (a
+  // lane copies pieces of other lanes' rows) a WHOLE TILE ahead — measured on the way here: per-lane 16-byte pieces of 32
+  // different rows cost 32 L1 wavefronts per instruction and doubled the kernel's time; a single buffer refilled at the tile
+  // switch exposed the full L2 / DRAM round trip (~2 us) on every tile.
   uint8_t* rope_buf = reinterpret_cast<uint8_t*>(evec_base + MAX_EPI_WARPS * 2 * p.evec_floats) + ew * ROPE_BYTES_PER_WARP;
-  auto rope_prefetch = [&](int t_mb) {
+  auto rope_prefetch = [&](int t_mb, int bufi) {
     const int r0 = (t_mb * CG + rank) * BM + q * 32;
     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.rope_tab + (size_t)(r0 % p.rope_T) * ROPE_PAIRS);
+    uint8_t* dst = rope_buf + bufi * (ROPE_BYTES_PER_WARP / 2);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int k = i * 32 + lane;           // 16-byte piece k of the block = quad (k & 3) of row (k >> 2)
-      cp_async_16(rope_buf + sw64(k >> 2, k & 3), src + k * 16, true);
+      cp_async_16(dst + sw64(k >> 2, k & 3), src + k * 16, true);
     }
     cp_async_commit();
   };
@@ -316,7 +317,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
     }
   };
   prefetch_vecs(mb, nb);
-  if constexpr (ROPE) rope_prefetch(mb);
+  if constexpr (ROPE) rope_prefetch(mb, 0);
 
   auto tmem_addr = [&](int buf, int c) {
     return tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * C::TBUF + c * CW);
@@ -393,7 +394,14 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
     if constexpr (ROPE) {
       rope_within = (n0 + half * 32) % p.rope_d;
     }
-    bool rope_landed = false;              // cp.async.wait_group is deferred to the first rotated chunk of the tile
+    const uint8_t* rope_cur = rope_buf + (it & 1) * (ROPE_BYTES_PER_WARP / 2);
+    if constexpr (ROPE) {
+      // the other buffer was last read during the previous tile (program order + the __syncwarp below cover every lane):
+      // refill it for the NEXT tile now, then make sure THIS tile's block (issued one tile ago) has landed
+      __syncwarp();
+      if (has_next) { rope_prefetch(mb_n, (it & 1) ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+      __syncwarp();                        // pieces were copied by other lanes
+    }
 
     f2_t rs2 = 0, rq2 = 0;                 // packed (sum, sumsq) accumulators of this lane's row (bit pattern 0 = +0.f pair)
 
@@ -411,17 +419,12 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
       bool rope_on[4] = {false, false, false, false};
       if constexpr (ROPE) {
         if (n0 + c * 32 < p.rope_cols) {   // warp-uniform
-          if (!rope_landed) {              // rows issued at the end of the previous tile; pieces were copied by other lanes
-            cp_async_wait<0>();
-            __syncwarp();
-            rope_landed = true;
-          }
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) { // 8-column groups = 4 rotary pairs = one 16-byte quad of half2 (cos, sin)
             int w = rope_within + 8 * g8;  // channel of the group's first column inside its head (a multiple of 8)
             if (w >= p.rope_d) w -= p.rope_d;
             rope_on[g8] = w < 2 * ROPE_PAIRS;      // warp-uniform: channels >= 32 of a head pass through
-            if (rope_on[g8]) rope_q[g8] = lds128u(rope_buf + sw64(lane, w >> 3));
+            if (rope_on[g8]) rope_q[g8] = lds128u(rope_cur + sw64(lane, w >> 3));
           }
         }
       }
@@ -452,11 +455,6 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
           }
           rope_within += 32 * nhalf;                          // next chunk of this warp
           while (rope_within >= p.rope_d) rope_within -= p.rope_d;
-          if (j + 1 == my_nch && has_next) {                  // every lane has read its row for the last time this tile
-            if (!rope_landed) cp_async_wait<0>();             // (a tile of V columns only never waited: drain before re-issuing)
-            __syncwarp();                                     // every lane is done reading: the block may be overwritten
-            rope_prefetch(mb_n);
-          }
         }
       } else {
         // GEGLU: accumulator columns [c*64, +32) are "value", [c*64+32, +64) the matching "gate" (bias is staged)

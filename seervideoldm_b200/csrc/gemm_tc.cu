@@ -451,8 +451,8 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
       int st = (avail - ne * rg * pl.slot_bytes) / stage_bytes;
       if (st < 2) continue;
       // (7 / 8 stages on the long-K launches measured no gain: 82.3 ms per evaluation either way; the streaming small-K
-      //  launches are bound by bytes in flight — their rings go to MAX_STAGES)
-      const int st_cap = (!d.X && Kd <= 640.0) ? env_int("SEER_GEMM_STAGES_SMALLK", MAX_STAGES) : 6;
+      //  launches measured the same with 6 and 8: profiles/r2_gemm_probe.txt)
+      const int st_cap = (!d.X && Kd <= 640.0) ? env_int("SEER_GEMM_STAGES_SMALLK", 6) : 6;
       if (st > st_cap) st = st_cap;
       const int score = (st > 5 ? 5 : st) * 100 + (ne == 8 ? 30 : 0) + rg * 5 + (st > 5 ? st - 5 : 0);
       if (score > best_score) { best_score = score; pl.nepi = ne; pl.ring = rg; pl.stages = st; }
@@ -583,8 +583,10 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   }
   p.bstat = pl.bstat;
   p.evec_floats = pl.bn == 320 ? EVEC_FLOATS_320 : EVEC_FLOATS;
-  // L2 prefetch distance (tiles of this CTA) for the streaming launches: plain GEMM with K <= 640
-  p.l2_prefetch = (!d.X && d.K1 + d.K2 <= 640) ? env_int("SEER_GEMM_L2PF", 2) : 0;
+  // L2 prefetch distance (tiles of this CTA) for the streaming launches (plain GEMM with K <= 640).  OFF by default: measured
+  // slower at every distance (profiles/r2_gemm_probe.txt: proj_out 161 -> 239 us, to_out 125 -> 136 us at distance 2) — these
+  // launches are not short of bytes in flight
+  p.l2_prefetch = (!d.X && d.K1 + d.K2 <= 640) ? env_int("SEER_GEMM_L2PF", 0) : 0;
   p.stages = pl.stages; p.nepi = pl.nepi; p.ring = pl.ring; p.slot_bytes = pl.slot_bytes;
   p.bias = d.bias; p.ldb = d.ldb > 0 ? d.ldb : d.N; p.bias_div = d.bias_div > 0 ? d.bias_div : BIAS_ONE_ROW;
   p.res_mode = d.residual ? (d.residual_bf16 ? 2 : 1) : 0;

@@ -26,10 +26,11 @@ PROFILE = None         # bench.py sets this to a list: (name, algorithmic flops,
 
 
 class _Timed:
-    """CUDA events on the launching stream around one kernel launch (only while ops.PROFILE is a list)."""
+    """CUDA events on the launching stream around one kernel launch (only while ops.PROFILE is a list).  Records
+    (name, executed FLOPs, start event, end event, algorithmic bytes = every operand / output tensor counted once)."""
 
-    def __init__(self, name: str, flops: float):
-        self.name, self.flops = name, flops
+    def __init__(self, name: str, flops: float, nbytes: float = 0.0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
 
     def __enter__(self):
         if PROFILE is not None:
@@ -40,7 +41,7 @@ class _Timed:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.e1.record()
-            PROFILE.append((self.name, self.flops, self.e0, self.e1))
+            PROFILE.append((self.name, self.flops, self.e0, self.e1, self.nbytes))
         return False
 
 
@@ -153,7 +154,13 @@ def gemm_ex(a: Optional[torch.Tensor], wt: torch.Tensor, *, x_img: Optional[torc
         name = f"conv{'2x2up' if up_phase else '3x3s2'} M={M} N={N} K={K1 + K2}"
     else:
         name = f"conv3x3 M={M} N={N} K={K1 + K2}"
-    with _Timed(name, 2.0 * M * N * (K1 + K2)):
+    nbytes = 0.0
+    if PROFILE is not None:          # algorithmic bytes of this launch: operands, weights, outputs, statistics — each once
+        src = x_img if x_img is not None else a
+        nbytes = sum(t.numel() * t.element_size() for t in (src, a2, wt, o32, o16, residual, cs, rs, rs_in) if t is not None)
+        if up_phase:                 # a phase launch fills a quarter of the shared output / statistics tensors
+            nbytes -= 0.75 * sum(t.numel() * t.element_size() for t in (o32, o16, cs) if t is not None)
+    with _Timed(name, 2.0 * M * N * (K1 + K2), nbytes):
         rc = _ops.gemm_ex(*args)
     if rc != 0:
         return None          # geometry not tileable by TMA boxes: caller falls back to explicit im2col

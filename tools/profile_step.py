@@ -10,7 +10,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from seervideoldm_b200 import SeerUNet  # noqa: E402
+from seervideoldm_b200 import SeerUNet, ops  # noqa: E402
 from seervideoldm_b200.config import sd15_config  # noqa: E402
 from seervideoldm_b200.weights import random_state_dict  # noqa: E402
 
@@ -19,6 +19,7 @@ ap.add_argument("--clips", type=int, default=8)
 ap.add_argument("--frames", type=int, default=16)
 ap.add_argument("--latent", type=int, default=32)
 ap.add_argument("--fast-init", action="store_true", help="skip the seeded weight factory (profiling only)")
+ap.add_argument("--list-gemm", default=None, help="write the ordered GEMM / conv launch list of the profiled evaluation (name, FLOPs, algorithmic bytes) as JSON")
 args = ap.parse_args()
 
 net = SeerUNet(sample_size=32, cross_attention_dim=768)
@@ -38,6 +39,16 @@ t = torch.full((B,), 496, device="cuda")
 for _ in range(2):
     net(x, t, c)
 torch.cuda.synchronize()
+if args.list_gemm:
+    import json
+    ops.PROFILE = []
+    net(x, t, c)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    rows = [dict(name=p[0], flops=p[1], bytes=p[4], ms=p[2].elapsed_time(p[3])) for p in prof if p[0].startswith(("gemm ", "conv"))]
+    with open(args.list_gemm, "w") as f:
+        json.dump(rows, f, indent=0)
+    print(f"wrote {len(rows)} GEMM / conv launches to {args.list_gemm}")
 torch.cuda.profiler.start()
 net(x, t, c)
 torch.cuda.synchronize()
