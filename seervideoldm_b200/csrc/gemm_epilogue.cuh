@@ -70,6 +70,7 @@ struct GemmParams {
   int ntaps, taps_w, taps_h, off_x, off_y, cstride;   // conv taps: tap t reads pixel (s*y + t / taps_w + off_y, s*x + t % taps_w + off_x)
   int up_phase;        // 0: output row = GEMM row; 1 + (2 py + px): rows are the (py, px) phase of a nearest-2x upsampled image
   int up_wshift;       //    (low-res width = 1 << up_wshift): out row = ((m >> ws) << (ws + 2)) + py * 2W + 2 (m & (W - 1)) + px
+  int direct16;        // bf16 output rows are stored straight from the registers (thread = row) instead of through the smem slot
   int l2_prefetch;     // > 0: the producer prefetches the A rows / residual tile of the tile this many iterations ahead into L2
   int evec_floats;     // floats per staged per-tile vector (bias / LN column sums) and warp: EVEC_FLOATS or EVEC_FLOATS_320
   int bstat;           // 1: the whole Wt panel of this CTA's (fixed) n-block is resident in smem; only A is streamed
@@ -134,18 +135,16 @@ __device__ __forceinline__ void ldg128_f2(const float* p, f2_t& a, f2_t& b) {
   asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
 }
 
-// erf-GELU of a pair through the odd tanh fit erf(z) ~ tanh(z (1.12812423 + z^2 (0.10414107 - 0.00181363 z^2))), z = x/sqrt 2
-// (same fit and accuracy as gelu_erf_tanhfit in common.cuh: 1.9e-4 rel-L2 on N(0, 1.5) gates, below the bf16 rounding of the
-// stored product).  The SIGNED argument keeps everything on the packed pipe: gelu = hx + hx * erf(z), hx = x / 2.
+// erf-GELU of a pair through gelu(x) = hx + hx tanh(x (0.79788456 + 0.03567741 x^2)), hx = x / 2 (the classic tanh form:
+// 1.8e-4 rel-L2 from the exact erf form on N(0, 1.5) gates, max abs 4.7e-4 — an order of magnitude below the bf16 rounding
+// of the stored product).  Its cubic argument is monotone, so no clamp is needed and everything but the two MUFU.TANH stays
+// on the packed fp32x2 pipe: 5 packed + 2 MUFU per pair (the quintic erf fit used before needed a clamp — unpack, 2 FMNMX,
+// pack — and one more FFMA2; the GEGLU launches of the 32x32 level are bound by this epilogue's instruction count).
 __device__ __forceinline__ f2_t f2_gelu_erf(f2_t x) {
-  const f2_t z = f2_mul(x, f2_pack(0.70710678118654752440f, 0.70710678118654752440f));
-  f2_t z2 = f2_mul(z, z);
+  const f2_t x2 = f2_mul(x, x);
+  const f2_t pz = f2_fma(x2, f2_pack(0.0356774081f, 0.0356774081f), f2_pack(0.7978845608f, 0.7978845608f));
   float a, b;
-  f2_unpack(z2, a, b);
-  z2 = f2_pack(fminf(a, 25.0f), fminf(b, 25.0f));      // the cubic's coefficient turns negative beyond |z| ~ 7.6
-  f2_t pz = f2_fma(z2, f2_pack(-0.00181363f, -0.00181363f), f2_pack(0.10414107f, 0.10414107f));
-  pz = f2_fma(z2, pz, f2_pack(1.12812423f, 1.12812423f));
-  f2_unpack(f2_mul(z, pz), a, b);
+  f2_unpack(f2_mul(x, pz), a, b);
   float ta, tb;
   asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(a));
   asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(b));
@@ -554,7 +553,22 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
         }
         __syncwarp();
       }
-      if (f_o16) {
+      if (f_o16 && p.direct16) {
+        // thread = row: each lane stores its own 64 contiguous bytes with four fire-and-forget 16-byte stores (two full 32-byte
+        // sectors per row; L2 merges them) — no smem round trip and no warp barriers on the chunk's dependent chain
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + out_row(row) * p.ldo_bf16 + ocol);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 o;
+            o.x = f2_to_bf16x2(f[4 * k]);
+            o.y = f2_to_bf16x2(f[4 * k + 1]);
+            o.z = f2_to_bf16x2(f[4 * k + 2]);
+            o.w = f2_to_bf16x2(f[4 * k + 3]);
+            dst[k] = o;
+          }
+        }
+      } else if (f_o16) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           uint4 o;

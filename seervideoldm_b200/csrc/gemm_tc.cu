@@ -583,6 +583,7 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   }
   p.bstat = pl.bstat;
   p.evec_floats = pl.bn == 320 ? EVEC_FLOATS_320 : EVEC_FLOATS;
+  p.direct16 = env_int("SEER_GEMM_DIRECT16", 0);
   // L2 prefetch distance (tiles of this CTA) for the streaming launches (plain GEMM with K <= 640).  OFF by default: measured
   // slower at every distance (profiles/r2_gemm_probe.txt: proj_out 161 -> 239 us, to_out 125 -> 136 us at distance 2) — these
   // launches are not short of bytes in flight

@@ -71,6 +71,7 @@ class SeerUNet(nn.Module):
         self.sample_size = sample_size
         self._packed: Optional[dict] = None
         self._packed32: Optional[dict] = None
+        self.rope_fuse_min_channels = 640
         self._weights_version = 0       # bumped whenever the packed weights are dropped (captured CUDA graphs check it)
         self._kv_key = None
         self._kv: List[torch.Tensor] = []
@@ -343,9 +344,12 @@ class SeerUNet(nn.Module):
         hn = ops.groupnorm(xt, None, B, t["gn_g"], t["gn_b"], 1e-6, False, stats1=xs)
         r = ops.gemm_ex(hn, t["pin_w"], bias=t["pin_b"], out_dtype=bf, row_stats=True)
         rope = None
-        if t["temporal"] and T % 32 == 0 and t["freqs"].numel() == 16:
+        if t["temporal"] and T % 32 == 0 and t["freqs"].numel() == 16 and C >= self.rope_fuse_min_channels:
             # rotary embedding of q and k (attention.py:649-651) fused into the projection's epilogue; the (cos, sin) table of
-            # this clip length is built once per layer (outside any graph capture: the warm-up evaluations fill the cache)
+            # this clip length is built once per layer (outside any graph capture: the warm-up evaluations fill the cache).
+            # Only where the GEMM's main loop hides the extra epilogue work (K = C >= 640): at the 320-channel level the
+            # projection is epilogue-bound and the fused form measured SLOWER than the separate pass (+119 us vs 94 us,
+            # profiles/r2_gemm_probe.txt), so level 0 keeps `rope_inplace`.
             tab = t.setdefault("rope_tabs", {}).get(T)
             if tab is None:
                 tab = t["rope_tabs"][T] = ops.rope_table(t["freqs"], T)
