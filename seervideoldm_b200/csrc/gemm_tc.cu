@@ -414,6 +414,13 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
       if (N % cand[i] == 0 && cand[i] != 320) best = cand[i];
     if (!best) return SEER_EUNSUPPORTED;
   }
+  if (d.row_stats_out && !forced) {
+    // LayerNorm row-statistic producers: the number and the column extent of the per-row partial sums must not depend on M,
+    // or a clip evaluated alone and inside a batch would sum its (sum, sumsq) in different orders (one fp32 ulp in mean / rstd,
+    // a handful of bf16 outputs rounding the other way: profiles/r1_batch_dependence_probe.txt).  The tile width is therefore
+    // a function of N alone here, and the launch always runs 8 epilogue warps (two partials per tile).
+    best = (N % 256 == 0 && N >= 1024) ? 256 : (N % 160 == 0 ? 160 : (N % 128 == 0 ? 128 : 64));
+  }
   pl.bn = best;
   pl.tiles_n = N / best;
   pl.num_tiles = tiles_m * pl.tiles_n;
@@ -427,6 +434,8 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   pl.nepi = env_int("SEER_GEMM_NEPI", (d.geglu || !of || Kd <= 1280.0) ? 8 : 4);
   // 320-wide tiles are single-buffered: the epilogue is exposed, so it gets all 8 warps (and a short residual ring)
   if (best == 320) pl.nepi = env_int("SEER_GEMM_NEPI320", 8);
+  const bool fixed_nepi = best == 320 || (d.row_stats_out && best >= 64 && !forced);
+  if (d.row_stats_out && !forced) pl.nepi = best >= 64 ? 8 : 4;
   if (pl.nepi != 4 && pl.nepi != 8) pl.nepi = 4;
   if (best / (d.geglu ? 64 : 32) < 2) pl.nepi = 4;   // every epilogue warp needs at least one chunk
   // B-stationary: the CTA keeps the Wt panel of ONE n-block resident (needs grid % tiles_n == 0) and streams only A —
@@ -446,7 +455,7 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   const int want_nepi = pl.nepi;
   const int want_ring = rm ? (best == 320 ? 2 : env_int("SEER_EPI_RING", 4)) : 1;    // no residual: the slot is only a staging buffer
   int best_score = -1;
-  for (int ne = want_nepi; ne >= (best == 320 ? want_nepi : 4); ne -= 4) {
+  for (int ne = want_nepi; ne >= (fixed_nepi ? want_nepi : 4); ne -= 4) {
     for (int rg = want_ring; rg >= (rm ? 2 : 1); --rg) {
       int st = (avail - ne * rg * pl.slot_bytes) / stage_bytes;
       if (st < 2) continue;
