@@ -558,8 +558,10 @@ using namespace seer;
 
 extern "C" int seer_b200_gemm_row_parts(const SeerGemmDesc* desc) {
   if (!desc) return SEER_EINVAL;
+  SeerGemmDesc d = *desc;
+  if (!d.row_stats_out) d.row_stats_out = reinterpret_cast<float*>(sizeof(float));   // plan as the launch that WILL write them
   Plan pl{};
-  int rc = make_plan(*desc, pl);
+  int rc = make_plan(d, pl);
   if (rc) return rc;
   return pl.tiles_n * (pl.nepi >> 2);
 }
