@@ -9,19 +9,23 @@
 //   attention.py:781-793 (GEGLU proj), attention.py:742 (FF out); and absorbs the statistics passes of
 //   nn.GroupNorm (resnet.py:179,197) and nn.LayerNorm (attention.py:198-200) into the producing / consuming GEMM.
 //
-// Structure (one persistent CTA per SM, static round-robin over 128 x BN output tiles, n fastest so the CTAs that
-// share an A row-block run at the same time and A is read from HBM once):
-//   warp 0      TMA producer: A (2-D box, or 9 shifted 4-D boxes for the 3x3 conv; OOB zero fill = padding) and
-//               Wt tiles into a `stages`-deep SWIZZLE_128B smem ring, mbarrier full/empty.
-//   warp 1      TMEM allocator + tcgen05.mma issuer (one lane): 128 x BN x 16 UMMAs into one of TWO TMEM
-//               accumulator buffers, so the epilogue of tile i overlaps the main loop of tile i+1.
-//   warps 2..   epilogue warps (4 or 8).  Each owns one TMEM lane quarter (32 rows) and a private ring of smem
-//               slots: the fp32/bf16 residual chunk (32 rows x 32 cols) is PREFETCHED into the slot by TMA one or
-//               two chunks ahead, the warp adds accumulator + bias in place (thread = row, 128B/64B-swizzled so the
-//               16-byte accesses are bank-conflict free) and a TMA store writes the slot back with full-line
-//               transactions.  No epilogue global load/store is issued by the LSU except the bias vector.
+// Structure (one persistent CTA — or cta_group::2 CTA pair, 256-row tiles — per SM, static round-robin over output tiles,
+// n fastest so the CTAs that share an A row-block run at the same time and A is read from HBM once):
+//   warp 0      TMA producer: A (2-D box; for the convs shifted 4-D boxes, OOB zero fill = padding; a traversal stride of 2
+//               for Downsample3D; 2x2 tap sets for the four phases of Upsample3D) and Wt tiles into a `stages`-deep
+//               SWIZZLE_128B smem ring, mbarrier full/empty.  B-stationary mode (K <= 320) keeps the Wt panel resident.
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one lane): (128 | 256) x BN x 16 UMMAs into one of TWO TMEM accumulator
+//               buffers, so the epilogue of tile i overlaps the main loop of tile i+1 (BN = 320: one 512-column buffer, two
+//               N = 160 UMMAs per A stage — half the A bytes per FLOP for the long-K N = 320 / 640 convs).
+//   warps 2..   epilogue warps (4 or 8).  Each owns one TMEM lane quarter (32 rows) and a private ring of smem slots: the
+//               fp32 / bf16 residual chunk (32 rows x 32 cols) is PREFETCHED into the slot by TMA one to three chunks ahead,
+//               the warp adds accumulator + bias (+ LayerNorm fold, GEGLU, RoPE) in registers (thread = row), stages the
+//               chunk in the slot (XOR-swizzled 16-byte pieces, bank-conflict free) and copies it out with coalesced
+//               128-bit LSU stores — TMA stores were measured slower here (fence.proxy.async + bulk-group round trip per
+//               chunk, tools/tma_store_bench.cu), as were direct per-row stores (SEER_GEMM_DIRECT16, profiles/r2_gemm_probe.txt).
 //
-// Epilogue options (all warp-uniform runtime branches): see SeerGemmDesc in include/seer_b200.h.
+// Epilogue options: see SeerGemmDesc in include/seer_b200.h; the combinations the UNet issues are compiled as straight-line
+// specialisations (gemm_epilogue.cuh EK_*), grouped into three kernel instantiations per tile shape (GRP below).
 #include "gemm_epilogue.cuh"
 #include "seer_b200.h"
 
@@ -419,7 +423,8 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
     // or a clip evaluated alone and inside a batch would sum its (sum, sumsq) in different orders (one fp32 ulp in mean / rstd,
     // a handful of bf16 outputs rounding the other way: profiles/r1_batch_dependence_probe.txt).  The tile width is therefore
     // a function of N alone here, and the launch always runs 8 epilogue warps (two partials per tile).
-    best = (N % 256 == 0 && N >= 1024) ? 256 : (N % 160 == 0 ? 160 : (N % 128 == 0 ? 128 : 64));
+    // (160 is also what the cost model picks for N = 320 / 640 / 1280 at the benchmark's M)
+    best = N % 160 == 0 ? 160 : (N % 128 == 0 ? 128 : 64);
   }
   pl.bn = best;
   pl.tiles_n = N / best;

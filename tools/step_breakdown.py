@@ -55,7 +55,7 @@ def main():
     prof, ops.PROFILE = ops.PROFILE, None
     wall = e0.elapsed_time(e1)
     agg = collections.OrderedDict()
-    for name, flops, a, b in prof:
+    for name, flops, a, b, *_ in prof:
         d = agg.setdefault(name, [0, 0.0, 0.0])
         d[0] += 1
         d[1] += a.elapsed_time(b)
