@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libseer_b200.so")
+LIB_PATH = os.environ.get("SEER_B200_LIB") or os.path.join(_HERE, "libseer_b200.so")     # SEER_B200_LIB: an A/B build of the kernels
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
 _c = ctypes

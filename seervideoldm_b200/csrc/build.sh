@@ -3,17 +3,18 @@
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 ROOT="$(cd "$HERE/../.." && pwd)"
-OUT="$HERE/../libseer_b200.so"
+OUT="${SEER_B200_OUT:-$HERE/../libseer_b200.so}"      # SEER_B200_OUT / SEER_B200_BUILD / EXTRA_NVCC_FLAGS: A/B builds of kernel variants
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I$ROOT/include -I$HERE"
-mkdir -p "$HERE/build"
+BUILD="${SEER_B200_BUILD:-$HERE/build}"
+mkdir -p "$BUILD"
 pids=()
 for f in gemm_tc attention attention_tc attention_tc80 norm elementwise fp32_path capi; do
-  if [ ! -f "$HERE/build/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/build/$f.o" ] || [ "$HERE/common.cuh" -nt "$HERE/build/$f.o" ] || [ "$HERE/gemm_epilogue.cuh" -nt "$HERE/build/$f.o" ] || [ "$ROOT/include/seer_b200.h" -nt "$HERE/build/$f.o" ]; then
-    $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c "$HERE/$f.cu" -o "$HERE/build/$f.o" &
+  if [ ! -f "$BUILD/$f.o" ] || [ "$HERE/$f.cu" -nt "$BUILD/$f.o" ] || [ "$HERE/common.cuh" -nt "$BUILD/$f.o" ] || [ "$HERE/gemm_epilogue.cuh" -nt "$BUILD/$f.o" ] || [ "$ROOT/include/seer_b200.h" -nt "$BUILD/$f.o" ]; then
+    $NVCC $FLAGS $EXTRA_NVCC_FLAGS ${PTXAS_V:+-Xptxas -v} -c "$HERE/$f.cu" -o "$BUILD/$f.o" &
     pids+=($!)
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE"/build/*.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$BUILD"/*.o -lcudart
 echo "built $OUT"

@@ -70,7 +70,6 @@ struct GemmParams {
   int ntaps, taps_w, taps_h, off_x, off_y, cstride;   // conv taps: tap t reads pixel (s*y + t / taps_w + off_y, s*x + t % taps_w + off_x)
   int up_phase;        // 0: output row = GEMM row; 1 + (2 py + px): rows are the (py, px) phase of a nearest-2x upsampled image
   int up_wshift;       //    (low-res width = 1 << up_wshift): out row = ((m >> ws) << (ws + 2)) + py * 2W + 2 (m & (W - 1)) + px
-  int direct16;        // bf16 output rows are stored straight from the registers (thread = row) instead of through the smem slot
   int l2_prefetch;     // > 0: the producer prefetches the A rows / residual tile of the tile this many iterations ahead into L2
   int evec_floats;     // floats per staged per-tile vector (bias / LN column sums) and warp: EVEC_FLOATS or EVEC_FLOATS_320
   int bstat;           // 1: the whole Wt panel of this CTA's (fixed) n-block is resident in smem; only A is streamed
@@ -139,6 +138,17 @@ __device__ __forceinline__ void ldg128_f2(const float* p, f2_t& a, f2_t& b) {
 // (same fit and accuracy as gelu_erf_tanhfit in common.cuh: 1.9e-4 rel-L2 on N(0, 1.5) gates, below the bf16 rounding of the
 // stored product).  The SIGNED argument keeps everything on the packed pipe: gelu = hx + hx * erf(z), hx = x / 2.
 __device__ __forceinline__ f2_t f2_gelu_erf(f2_t x) {
+#ifdef SEER_GELU_TANH_CUBIC
+  // the classic clamp-free form hx + hx tanh(x (0.79788456 + 0.03567741 x^2)): 1.8e-4 rel-L2 from the erf form (A/B build)
+  const f2_t x2c = f2_mul(x, x);
+  const f2_t pzc = f2_fma(x2c, f2_pack(0.0356774081f, 0.0356774081f), f2_pack(0.7978845608f, 0.7978845608f));
+  float ac, bc, tac, tbc;
+  f2_unpack(f2_mul(x, pzc), ac, bc);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(tac) : "f"(ac));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(tbc) : "f"(bc));
+  const f2_t hxc = f2_mul(x, f2_pack(0.5f, 0.5f));
+  return f2_fma(hxc, f2_pack(tac, tbc), hxc);
+#endif
   const f2_t z = f2_mul(x, f2_pack(0.70710678118654752440f, 0.70710678118654752440f));
   f2_t z2 = f2_mul(z, z);
   float a, b;
@@ -153,8 +163,6 @@ __device__ __forceinline__ f2_t f2_gelu_erf(f2_t x) {
   const f2_t hx = f2_mul(x, f2_pack(0.5f, 0.5f));
   return f2_fma(hx, f2_pack(ta, tb), hx);
 }
-// (The classic clamp-free form gelu(x) = hx + hx tanh(x (0.79788456 + 0.03567741 x^2)) has three fewer instructions per pair
-//  but MEASURED SLOWER in the GEGLU epilogue: 562 vs 463 us on the level-0 launch, profiles/r2_gemm_probe.txt — kept out.)
 
 // tcgen05.wait::ld that also names the destination registers of the outstanding load, so no use of them can be
 // scheduled above the wait (the load is issued a whole chunk earlier than it is consumed)
@@ -557,22 +565,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
         }
         __syncwarp();
       }
-      if (f_o16 && p.direct16) {
-        // thread = row: each lane stores its own 64 contiguous bytes with four fire-and-forget 16-byte stores (two full 32-byte
-        // sectors per row; L2 merges them) — no smem round trip and no warp barriers on the chunk's dependent chain
-        if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + out_row(row) * p.ldo_bf16 + ocol);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint4 o;
-            o.x = f2_to_bf16x2(f[4 * k]);
-            o.y = f2_to_bf16x2(f[4 * k + 1]);
-            o.z = f2_to_bf16x2(f[4 * k + 2]);
-            o.w = f2_to_bf16x2(f[4 * k + 3]);
-            dst[k] = o;
-          }
-        }
-      } else if (f_o16) {
+      if (f_o16) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           uint4 o;

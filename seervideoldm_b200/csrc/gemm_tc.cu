@@ -22,7 +22,8 @@
 //               the warp adds accumulator + bias (+ LayerNorm fold, GEGLU, RoPE) in registers (thread = row), stages the
 //               chunk in the slot (XOR-swizzled 16-byte pieces, bank-conflict free) and copies it out with coalesced
 //               128-bit LSU stores — TMA stores were measured slower here (fence.proxy.async + bulk-group round trip per
-//               chunk, tools/tma_store_bench.cu), as were direct per-row stores (SEER_GEMM_DIRECT16, profiles/r2_gemm_probe.txt).
+//               chunk, tools/tma_store_bench.cu), as were direct per-row stores (thread = row, four 16-byte
+//               stores: qkv 220 -> 288 us, profiles/r2_gemm_probe.txt).
 //
 // Epilogue options: see SeerGemmDesc in include/seer_b200.h; the combinations the UNet issues are compiled as straight-line
 // specialisations (gemm_epilogue.cuh EK_*), grouped into three kernel instantiations per tile shape (GRP below).
@@ -599,7 +600,6 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
   }
   p.bstat = pl.bstat;
   p.evec_floats = pl.bn == 320 ? EVEC_FLOATS_320 : EVEC_FLOATS;
-  p.direct16 = env_int("SEER_GEMM_DIRECT16", 0);
   // L2 prefetch distance (tiles of this CTA) for the streaming launches (plain GEMM with K <= 640).  OFF by default: measured
   // slower at every distance (profiles/r2_gemm_probe.txt: proj_out 161 -> 239 us, to_out 125 -> 136 us at distance 2) — these
   // launches are not short of bytes in flight
