@@ -183,6 +183,10 @@ int seer_b200_conv_out(const float* x, const float* w_packed, const float* bias,
  * scores and P V run as tcgen05 GEMMs around it. */
 int seer_b200_softmax_rows(const float* S, int lds, long long rows, int L, float scale, void* P_bf16, int ldp, void* stream);
 
+/* Token-major x [B*F*HW, ld] fp32 (first C columns) -> out (B, C, F, H, W) fp32: the layout change after conv_out when it runs
+ * as a tensor-core implicit GEMM with zero-padded output channels (unet_3d_condition.py:370 returns (B, 4, F, H, W)). */
+int seer_b200_tokens_to_nchw(const float* x, int ld, float* out, int B, int C, int F, int HW, void* stream);
+
 /* nearest 2x upsample fp32 [n,H,W,C] -> bf16 [n,2H,2W,C] (resnet.py:52). */
 int seer_b200_upsample2x_to_bf16(const float* x, void* y, int n_img, int H, int W, int C, void* stream);
 /* pad-1 3x3 im2col, stride 1 or 2: [n,H,W,C] (fp32, or bf16 if in_is_bf16) -> bf16 [n*(H/s)*(W/s), 9*C], K order [C/64][tap][64]; C % 64 == 0.

@@ -316,6 +316,23 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Token-major [B*F*HW, ld] fp32 (first C columns) -> the reference's (B, C, F, H, W) layout: the 4-channel epsilon that leaves the
+// UNet when conv_out runs as a tensor-core implicit GEMM with its output channels zero-padded to one 64-column tile.
+// ---------------------------------------------------------------------------------------------------
+__global__ void tokens_to_nchw_kernel(const float* __restrict__ x, int ld, float* __restrict__ out, int B, int C, int F, int HW) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
+  const size_t total = (size_t)B * C * F * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    size_t r = i / HW;
+    const int f = (int)(r % F); r /= F;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    out[i] = x[(((size_t)b * F + f) * HW + p) * ld + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // nearest 2x upsample, fp32 [n_img, H, W, C] -> bf16 [n_img, 2H, 2W, C]   (resnet.py:52, conv input operand)
 // ---------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n_img, int H, int W, int C) {
@@ -487,6 +504,13 @@ extern "C" int seer_b200_conv_out(const float* x, const float* w_packed, const f
   static SmemAttrOnce smem_attr;
   if (smem > 48 * 1024) { cudaError_t e = smem_attr.ensure(conv_out_kernel, (int)smem); if (e != cudaSuccess) return (int)e; }
   { cudaError_t le__ = launch_pdl(conv_out_kernel, dim3((unsigned)(B * F * H), (unsigned)ceil_div(W, CO_SEG)), CO_THREADS, smem, (cudaStream_t)stream, x, w_packed, bias, out, B, Cin, F, H, W, Cout); if (le__ != cudaSuccess) return (int)le__; }
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_tokens_to_nchw(const float* x, int ld, float* out, int B, int C, int F, int HW, void* stream) {
+  SEER_CHECK_ARG(x && out && B > 0 && C > 0 && F > 0 && HW > 0 && ld >= C);
+  { cudaError_t le__ = launch_pdl(tokens_to_nchw_kernel, grid_for((size_t)B * C * F * HW, 256), 256, 0, (cudaStream_t)stream, x, ld, out, B, C, F, HW); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

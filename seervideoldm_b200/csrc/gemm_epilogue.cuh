@@ -134,30 +134,16 @@ __device__ __forceinline__ void ldg128_f2(const float* p, f2_t& a, f2_t& b) {
   asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
 }
 
-// erf-GELU of a pair through the odd tanh fit erf(z) ~ tanh(z (1.12812423 + z^2 (0.10414107 - 0.00181363 z^2))), z = x/sqrt 2
-// (same fit and accuracy as gelu_erf_tanhfit in common.cuh: 1.9e-4 rel-L2 on N(0, 1.5) gates, below the bf16 rounding of the
-// stored product).  The SIGNED argument keeps everything on the packed pipe: gelu = hx + hx * erf(z), hx = x / 2.
+// erf-GELU of a pair through the clamp-free tanh form gelu(x) = hx + hx tanh(x (0.79788456 + 0.03567741 x^2)), hx = x / 2:
+// 1.8e-4 rel-L2 from the exact erf form on N(0, 1.5) gates (max abs 4.7e-4), an order of magnitude below the bf16 rounding of the
+// stored product.  Its cubic argument is monotone, so — unlike the quintic erf fit of common.cuh's gelu_erf_tanhfit, whose
+// leading coefficient turns negative beyond |z| ~ 7.6 — it needs no clamp: 5 packed fp32x2 instructions + 2 MUFU.TANH per
+// pair.  Measured against the quintic in the same build (profiles/r2_gemm_probe.txt): level-0 GEGLU launch 468 -> 447 us.
 __device__ __forceinline__ f2_t f2_gelu_erf(f2_t x) {
-#ifdef SEER_GELU_TANH_CUBIC
-  // the classic clamp-free form hx + hx tanh(x (0.79788456 + 0.03567741 x^2)): 1.8e-4 rel-L2 from the erf form (A/B build)
-  const f2_t x2c = f2_mul(x, x);
-  const f2_t pzc = f2_fma(x2c, f2_pack(0.0356774081f, 0.0356774081f), f2_pack(0.7978845608f, 0.7978845608f));
-  float ac, bc, tac, tbc;
-  f2_unpack(f2_mul(x, pzc), ac, bc);
-  asm("tanh.approx.f32 %0, %1;" : "=f"(tac) : "f"(ac));
-  asm("tanh.approx.f32 %0, %1;" : "=f"(tbc) : "f"(bc));
-  const f2_t hxc = f2_mul(x, f2_pack(0.5f, 0.5f));
-  return f2_fma(hxc, f2_pack(tac, tbc), hxc);
-#endif
-  const f2_t z = f2_mul(x, f2_pack(0.70710678118654752440f, 0.70710678118654752440f));
-  f2_t z2 = f2_mul(z, z);
-  float a, b;
-  f2_unpack(z2, a, b);
-  z2 = f2_pack(fminf(a, 25.0f), fminf(b, 25.0f));      // the cubic's coefficient turns negative beyond |z| ~ 7.6
-  f2_t pz = f2_fma(z2, f2_pack(-0.00181363f, -0.00181363f), f2_pack(0.10414107f, 0.10414107f));
-  pz = f2_fma(z2, pz, f2_pack(1.12812423f, 1.12812423f));
-  f2_unpack(f2_mul(z, pz), a, b);
-  float ta, tb;
+  const f2_t x2 = f2_mul(x, x);
+  const f2_t pz = f2_fma(x2, f2_pack(0.0356774081f, 0.0356774081f), f2_pack(0.7978845608f, 0.7978845608f));
+  float a, b, ta, tb;
+  f2_unpack(f2_mul(x, pz), a, b);
   asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(a));
   asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(b));
   const f2_t hx = f2_mul(x, f2_pack(0.5f, 0.5f));

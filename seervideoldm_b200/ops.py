@@ -354,6 +354,16 @@ def conv_out(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, B: int
 
 
 @_timed_op
+def tokens_to_nchw(x: torch.Tensor, B: int, C: int, F: int, H: int, W: int) -> torch.Tensor:
+    """x:[B*F*H*W, >= C] fp32 token-major -> (B, C, F, H, W) fp32 (the first C columns)."""
+    _cuda(x, "x")
+    out = torch.empty((B, C, F, H, W), device=x.device, dtype=torch.float32)
+    _ops.tokens_to_nchw(x, out)
+    _count()
+    return out
+
+
+@_timed_op
 def upsample2x(x: torch.Tensor, n_img: int, H: int, W: int) -> torch.Tensor:
     """x:[n_img*H*W, C] fp32 -> [n_img, 2H, 2W, C] bf16."""
     _cuda(x, "x")

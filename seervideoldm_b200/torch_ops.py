@@ -460,6 +460,17 @@ def _softmax_rows(S, scale, out) -> None:
     _lib.check(rc, "softmax_rows")
 
 
+def _tokens_to_nchw(x, out) -> None:
+    _chk(x, "x", f32, 2); _chk(out, "out", f32, 5, contiguous=True, dev=x.device)
+    B, C, F, H, W = out.shape
+    if x.shape[0] != B * F * H * W or x.shape[1] < C:
+        raise ValueError("tokens_to_nchw: x must be [B*F*H*W, >= C]")
+    with _Dev(x) as stream:
+        rc = _lib.lib().seer_b200_tokens_to_nchw(_p(x), x.stride(0), _p(out), B, C, F, H * W, stream)
+    _lib.check(rc, "tokens_to_nchw")
+
+
+_define("tokens_to_nchw(Tensor x, Tensor(a!) out) -> ()", _tokens_to_nchw)
 _define("softmax_rows(Tensor S, float scale, Tensor(a!) out) -> ()", _softmax_rows)
 _define("rope_table(Tensor freqs, Tensor(a!) out) -> ()", _rope_table)
 _define("rope(Tensor(a!) qk, int pos_div, int pos_mod, int heads, int head_dim, int q_col, int k_col, Tensor freqs) -> ()", _rope)

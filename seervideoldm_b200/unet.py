@@ -72,6 +72,7 @@ class SeerUNet(nn.Module):
         self._packed: Optional[dict] = None
         self._packed32: Optional[dict] = None
         self.rope_fuse_min_channels = 640
+        self.conv_out_tensor_core = True
         self._weights_version = 0       # bumped whenever the packed weights are dropped (captured CUDA graphs check it)
         self._kv_key = None
         self._kv: List[torch.Tensor] = []
@@ -206,6 +207,14 @@ class SeerUNet(nn.Module):
         pk["gno_g"], pk["gno_b"] = f32("conv_norm_out.weight"), f32("conv_norm_out.bias")
         pk["conv_out_w"] = packing.pack_conv_out(P("conv_out.weight"))
         pk["conv_out_b"] = f32("conv_out.bias")
+        # conv_out as a tensor-core implicit GEMM: output channels zero-padded to one 64-column tile (bf16 operands, fp32 out)
+        w_out = P("conv_out.weight")
+        if w_out.shape[0] <= 64 and w_out.shape[1] % 64 == 0:
+            w64 = torch.zeros((64,) + tuple(w_out.shape[1:]), device=dev, dtype=torch.float32)
+            w64[: w_out.shape[0]] = w_out
+            b64 = torch.zeros(64, device=dev, dtype=torch.float32)
+            b64[: w_out.shape[0]] = P("conv_out.bias")
+            pk["conv_out_w16"], pk["conv_out_b64"] = packing.pack_conv3x3(w64), b64
 
         temb_w, temb_b = [], []
         off = 0
@@ -521,6 +530,13 @@ class SeerUNet(nn.Module):
                 x = self._upsample_conv(blk["up"], x[2], B, F, h, w)
                 h, w = 2 * h, 2 * w
         # 6. out: GN -> SiLU -> conv_out, fp32, back to (B, C, F, H, W)
+        if self.conv_out_tensor_core and "conv_out_w16" in pk and x[1] is not None:
+            # bf16 operands on the tcgen05 implicit-GEMM conv (N = 64: the 4 real channels + zero rows), fp32 accumulate / out:
+            # the fp32 SIMT kernel below is FP32-pipe-bound at ~0.9 ms per evaluation, this path ~0.2 ms; the operand rounding
+            # adds ~1.5e-3 to the step's 7e-3 (rel-L2, in quadrature)
+            y16 = ops.groupnorm(x[0], None, B, pk["gno_g"], pk["gno_b"], cfg.norm_eps, True, stats1=x[1])
+            r = ops.conv3x3_ex(y16.view(B * F, h, w, y16.shape[1]), pk["conv_out_w16"], bias=pk["conv_out_b64"])
+            return ops.tokens_to_nchw(r.out, B, cfg.out_channels, F, h, w)
         y = ops.groupnorm(x[0], None, B, pk["gno_g"], pk["gno_b"], cfg.norm_eps, True, out_dtype=torch.float32, stats1=x[1])
         return ops.conv_out(y, pk["conv_out_w"], pk["conv_out_b"], B, F, h, w)
 
