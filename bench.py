@@ -42,6 +42,11 @@ TEXT_KV_GFLOP = {12: 35.42, 16: 47.23}        # text K/V, cached across evaluati
 # Upsample3D convs run as four 2x2-tap phase convs on the low-res image = 4/9 of the reference's 3x3-on-upsampled FLOPs
 # (SURVEY App. A "upsample conv3x3" row: 203.84 GFLOP at F = 12, x 16/12 at F = 16): 5/9 of them are never executed
 UPSAMPLE_SKIPPED_GFLOP = {12: 203.84 * 5 / 9, 16: 203.84 * 16 / 12 * 5 / 9}
+# CFG shared prefix (SURVEY §8d "exploitable redundancy"): for the second half of every CFG pair the layers in front of the first
+# cross-attention are not evaluated again — per SKIPPED batch-1 evaluation at F = 12 (x F/12; the self-attention core x (F/12) too,
+# it is per frame): conv_in 0.28 + first ResNet 2 x 45.30 + proj_in 5.03 + q/k/v 15.10 + to_out 5.03 + cross q 5.03 +
+# spatial self-attention core 16.11 GFLOP (SURVEY App. A level-0 rows divided by their instance counts)
+CFG_PREFIX_GFLOP = {f: (0.28 + 2 * 45.30 + 5.03 + 15.10 + 5.03 + 5.03 + 16.11) * f / 12 for f in (12, 16)}
 
 # BASELINE.json configs (name -> frames, reference frames, clips per GPU per sampling pass, total clips for strong scaling)
 WORKLOADS = {
@@ -423,7 +428,7 @@ def run_ours(args):
     if rank == 0:
         evals_per_s = EVALS * args.steps * len(batches) / (ms * 1e-3)
         algo_tflop_per_clip = (EVALS * 2 * (GFLOP_PER_EVAL[FRAMES] - UPSAMPLE_SKIPPED_GFLOP[FRAMES])
-                               - (EVALS - 1) * 2 * TEXT_KV_GFLOP[FRAMES]) / 1e3
+                               - (EVALS - 1) * 2 * TEXT_KV_GFLOP[FRAMES] - EVALS * CFG_PREFIX_GFLOP[FRAMES]) / 1e3
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
@@ -433,8 +438,9 @@ def run_ours(args):
                            "l2": "working set per evaluation (2.2 GB bf16 weights + multi-GB activations) >> 126 MB L2, no flush needed",
                            "ddim_evals_per_s": evals_per_s, "cuda_graph": True,
                            "algorithmic_tflop_per_clip": algo_tflop_per_clip,
-                           "algorithmic_note": "reference-algorithm FLOPs minus the work legitimately skipped: cached text K/V (evaluations 2-31) "
-                                               "and 5/9 of the Upsample3D conv FLOPs (2x2-tap phase convs on the low-res image)",
+                           "algorithmic_note": "reference-algorithm FLOPs minus the work legitimately skipped: cached text K/V (evaluations 2-31), "
+                                               "5/9 of the Upsample3D conv FLOPs (2x2-tap phase convs on the low-res image) and the context-free "
+                                               "front of the network for the second half of each CFG pair (conv_in, first ResNet, first text block up to to_q2)",
                            "achieved_tflops_whole_step": value * algo_tflop_per_clip,
                            "frac_of_sustained_peak_whole_step": value * algo_tflop_per_clip / world / peaks["sustained"]},
                 "clocks": clk,

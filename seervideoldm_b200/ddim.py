@@ -77,6 +77,7 @@ class DDIMSampler(object):
         self._branch = None            # (process group, branch index) while the CFG-branch split is enabled
         self._graphs = collections.OrderedDict()      # LRU of captured evaluations (each pins a private activation pool)
         self.max_graphs = int(kwargs.get("max_graphs", 3))
+        self.share_cfg_prefix = bool(kwargs.get("share_cfg_prefix", True))   # evaluate the context-free front of the UNet once per CFG pair
 
     def register_buffer(self, name, attr):
         if isinstance(attr, torch.Tensor) and attr.device != self.device:
@@ -181,19 +182,24 @@ class DDIMSampler(object):
         self._branch = None
         return self
 
-    def _evaluate(self, unet, x_in, t_in, c_in, cond_frame):
-        """One UNet evaluation; replayed from a CUDA graph when the model is a seer_b200 SeerUNet."""
-        if not (self.use_cuda_graph and isinstance(unet, SeerUNet) and x_in.is_cuda):
+    def _evaluate(self, unet, x_in, t_in, c_in, cond_frame, cfg_shared: bool = False):
+        """One UNet evaluation; replayed from a CUDA graph when the model is a seer_b200 SeerUNet.  `cfg_shared`: x_in / t_in
+        are the CFG batch `[x; x]`, `[t; t]` this sampler built itself (identical halves) — the seer_b200 UNet then evaluates
+        the context-free front of the network once."""
+        if not isinstance(unet, SeerUNet):
             return unet(x_in, t_in, c_in, cond_frame=cond_frame)
-        key = (id(unet), tuple(x_in.shape), tuple(c_in.shape), cond_frame, unet.precision, str(x_in.device))
+        cfg_shared = bool(cfg_shared and self.share_cfg_prefix and unet.precision == "bf16")
+        if not (self.use_cuda_graph and x_in.is_cuda):
+            return unet(x_in, t_in, c_in, cond_frame=cond_frame, cfg_shared_input=cfg_shared)
+        key = (id(unet), tuple(x_in.shape), tuple(c_in.shape), cond_frame, unet.precision, str(x_in.device), cfg_shared)
         g = self._graphs.get(key)
-        if g is not None and not g.matches(unet, x_in, c_in, cond_frame):      # id() reuse after garbage collection, or the
+        if g is not None and not g.matches(unet, x_in, c_in, cond_frame, cfg_shared):      # id() reuse after garbage collection, or the
             del self._graphs[key]                                              # model's weights changed since the capture
             g = None
         if g is None:
             while len(self._graphs) >= max(1, self.max_graphs):                # least recently used first: alternating shapes
                 self._graphs.popitem(last=False)                               # (a last partial batch) do not thrash
-            g = self._graphs[key] = GraphedUNet(unet, x_in, t_in, c_in, cond_frame)
+            g = self._graphs[key] = GraphedUNet(unet, x_in, t_in, c_in, cond_frame, cfg_shared=cfg_shared)
         else:
             self._graphs.move_to_end(key)
         return g(x_in, t_in, c_in)
@@ -223,7 +229,8 @@ class DDIMSampler(object):
             eps = gather_cfg_branches(self._evaluate(unet, x_cat, t, uc if branch == 0 else c, cond_frames), group)
         elif uc.shape[2] == c.shape[2]:
             c_in = self._cfg_context(uc, c)
-            eps = self._evaluate(unet, torch.cat([x_cat] * 2), torch.cat([t] * 2), c_in, cond_frames)
+            # the two halves of this batch are identical by construction (same latents, same per-sample timesteps)
+            eps = self._evaluate(unet, torch.cat([x_cat] * 2), torch.cat([t] * 2), c_in, cond_frames, cfg_shared=True)
         else:
             eps = torch.cat([self._evaluate(unet, x_cat, t, uc, cond_frames), self._evaluate(unet, x_cat, t, c, cond_frames)])
         coef = self._coef[index]

@@ -13,8 +13,10 @@ from . import ops
 
 
 class GraphedUNet:
-    def __init__(self, unet, x_in: torch.Tensor, t_in: torch.Tensor, c_in: torch.Tensor, cond_frame: int, warmup: int = 2):
+    def __init__(self, unet, x_in: torch.Tensor, t_in: torch.Tensor, c_in: torch.Tensor, cond_frame: int, warmup: int = 2,
+                 cfg_shared: bool = False):
         self.unet = unet
+        self.cfg_shared = cfg_shared
         self.x = x_in.detach().clone().float().contiguous()
         self.t = t_in.detach().clone()
         self.c = c_in.detach().clone().contiguous()
@@ -27,7 +29,7 @@ class GraphedUNet:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(warmup):                   # packs weights, fills the text K/V cache, sets func attributes
-                    unet(self.x, self.t, self.c, cond_frame=cond_frame)
+                    unet(self.x, self.t, self.c, cond_frame=cond_frame, cfg_shared_input=self.cfg_shared)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             self._capture(unet, cond_frame)
@@ -43,11 +45,11 @@ class GraphedUNet:
         before = ops.LAUNCHES
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = unet(self.x, self.t, self.c, cond_frame=cond_frame)
+            self.out = unet(self.x, self.t, self.c, cond_frame=cond_frame, cfg_shared_input=self.cfg_shared)
         self.launches_per_replay = ops.LAUNCHES - before
 
-    def matches(self, unet, x_in, c_in, cond_frame) -> bool:
-        return (self.unet is unet and tuple(self.x.shape) == tuple(x_in.shape) and tuple(self.c.shape) == tuple(c_in.shape)
+    def matches(self, unet, x_in, c_in, cond_frame, cfg_shared: bool = False) -> bool:
+        return (self.unet is unet and self.cfg_shared == cfg_shared and tuple(self.x.shape) == tuple(x_in.shape) and tuple(self.c.shape) == tuple(c_in.shape)
                 and self.cond_frame == cond_frame and self.precision == unet.precision
                 and self.weights_version == unet._weights_version and self.device == x_in.device)
 

@@ -339,17 +339,27 @@ class SeerUNet(nn.Module):
         hid = ops.gemm_ex(tok, t["ff1_w"], bias=t["ff1_b"], geglu=True, ln=(rstats, t["ff1_cs"], 1e-5)).out
         return ops.gemm_ex(hid, t["ff2_w"], bias=t["ff2_b"], residual=tok, out=out_rows, out_dtype=torch.bfloat16).out
 
-    def _transformer(self, t: dict, x, B, F, H, W, kv, cond_frame, want: str = "f32"):
+    def _transformer(self, t: dict, x, B, F, H, W, kv, cond_frame, want: str = "f32", dup: bool = False):
         """SpatialTransformer3D.forward (attention.py:129-145) with its text (:308-327) or temporal (:231-248) block.
         The token stream inside the block is bf16 (what the reference computes under autocast: Linear outputs and the
         residual adds are low precision there too) with per-row (sum, sumsq) written by the producing GEMM's epilogue for
-        the LayerNorm folded into the next projection; the block input / output (the UNet's residual stream) stay fp32."""
+        the LayerNorm folded into the next projection; the block input / output (the UNet's residual stream) stay fp32.
+
+        `dup` (text block only): `x` holds the FIRST HALF of a CFG batch whose two halves are identical up to here (same
+        latents, same timestep — ddim_video.py:199-203); everything that does not see the text context (GroupNorm, proj_in,
+        LN1 + q/k/v, self-attention, to_out, LN2 + cross-attention query) is computed once on B/2 samples, then the
+        token stream, the query and the block input are duplicated and the block continues on B samples."""
         C, heads = t["C"], self.cfg.heads
         d = C // heads
         hw, T = H * W, F * H * W
-        M = B * T
         bf = torch.bfloat16
         xt, xs = x[:2]
+        Bfull = B
+        if dup:
+            if t["temporal"] or B % 2:
+                raise RuntimeError("dup: text block on an even CFG batch only")
+            B = B // 2
+        M = B * T
         hn = ops.groupnorm(xt, None, B, t["gn_g"], t["gn_b"], 1e-6, False, stats1=xs)
         r = ops.gemm_ex(hn, t["pin_w"], bias=t["pin_b"], out_dtype=bf, row_stats=True)
         rope = None
@@ -375,6 +385,12 @@ class SeerUNet(nn.Module):
         r = ops.gemm_ex(att, t["o1_w"], bias=t["o1_b"], residual=r.out, out_dtype=bf, row_stats=True)
         if not t["temporal"]:
             q2 = ops.gemm_ex(r.out, t["q2_w"], bias=t["q2_b"], out_dtype=bf, ln=(r.row_stats, t["q2_cs"], 1e-5)).out
+            if dup:
+                # the two CFG branches diverge here: same queries / token stream / block input, different text K/V
+                q2 = torch.cat([q2, q2])
+                r = ops.GemmOut(torch.cat([r.out, r.out]))
+                xt = torch.cat([xt, xt])
+                B, M = Bfull, Bfull * T
             Lk = kv.shape[0] // (B * F)
             att2 = ops.attention(q2, kv[:, :C], kv[:, C:], mode=ops.ATTN_CROSS, heads=heads, n_outer=B * F, Lq=hw, Lk=Lk)
             r = ops.gemm_ex(att2, t["o2_w"], bias=t["o2_b"], residual=r.out, out_dtype=bf, row_stats=True)
@@ -433,7 +449,12 @@ class SeerUNet(nn.Module):
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, sample: torch.Tensor, timestep, context: Optional[torch.Tensor] = None, cond_frame: int = 0,
-                return_attn: bool = False, encoder_hidden_states: Optional[torch.Tensor] = None) -> torch.Tensor:
+                return_attn: bool = False, encoder_hidden_states: Optional[torch.Tensor] = None,
+                cfg_shared_input: bool = False) -> torch.Tensor:
+        """`cfg_shared_input=True` (not in the reference's signature; DDIMSampler sets it) promises that the batch is the
+        sampler's CFG batch `[x; x]` with one timestep — identical halves that differ only in `context` — so the layers in
+        front of the first cross-attention are evaluated once instead of twice (bit-identical result)."""
+        self._cfg_shared = bool(cfg_shared_input)
         # every kernel launches on the current stream of the CURRENT device and tensor maps are encoded in its context:
         # make the model's device current for the whole evaluation (a module on cuda:1 called while cuda:0 is current)
         if self.device.type == "cuda":
@@ -485,9 +506,13 @@ class SeerUNet(nn.Module):
         kvs = iter(self._context_kv(pk, context.to(dev)))
 
         # 2. conv_in -> token-major fp32 stream
-        x = ops.conv_in(sample.contiguous(), pk["conv_in_w"], pk["conv_in_b"], col_stats=True) + (None,)   # (fp32, col_stats, bf16)
+        # CFG batch with identical halves: conv_in, the first ResNet block and the context-free front of the first text block
+        # run on the first half only (ddim_video.py:199-203 builds x_in = cat([x] * 2), t_in = cat([t] * 2))
+        shared = (getattr(self, "_cfg_shared", False) and B % 2 == 0 and bool(pk["down"][0]["attn"]) and (F * H * W) % 32 == 0)
+        Bc = B // 2 if shared else B
+        x = ops.conv_in(sample[:Bc].contiguous(), pk["conv_in_w"], pk["conv_in_b"], col_stats=True) + (None,)   # (fp32, col_stats, bf16)
         h, w = H, W
-        skips: List[tuple] = [x]
+        skips: List[tuple] = [(torch.cat([x[0], x[0]]), torch.cat([x[1], x[1]]), None) if shared else x]
         n = len(cfg.block_out_channels)
         # 3. down
         for i, blk in enumerate(pk["down"]):
@@ -495,9 +520,10 @@ class SeerUNet(nn.Module):
             for j, r in enumerate(blk["res"]):
                 # the block's last tensor also feeds the stride-2 conv, which reads bf16
                 last = "both" if (blk["down"] is not None and j == nres - 1) else "f32"
-                x = self._resnet(r, x, None, B, F, h, w, temb_all, want="f32" if blk["attn"] else last)
+                first = shared and i == 0 and j == 0
+                x = self._resnet(r, x, None, Bc if first else B, F, h, w, temb_all, want="f32" if blk["attn"] else last)
                 if blk["attn"]:
-                    x = self._transformer(blk["attn"][j], x, B, F, h, w, next(kvs), cond_frame)
+                    x = self._transformer(blk["attn"][j], x, B, F, h, w, next(kvs), cond_frame, dup=first)
                     x = self._transformer(blk["tattn"][j], x, B, F, h, w, None, cond_frame, want=last)
                 skips.append(x)
             if blk["down"] is not None:

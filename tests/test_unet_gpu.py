@@ -98,6 +98,22 @@ def test_batch_independence_bit_exact(model, B, Fr, H):
         assert torch.equal(one[0], both[i]), (B, Fr, H, i, float((one[0] - both[i]).abs().max()))
 
 
+@pytest.mark.parametrize("b,Fr,H,cf", [(1, 2, 8, 0), (2, 4, 16, 1), (2, 4, 32, 0)])
+def test_cfg_shared_prefix_bit_exact(model, b, Fr, H, cf):
+    """The sampler's CFG batch [x; x] / [t; t] / [uc; c] has identical halves up to the first cross-attention: evaluating the
+    context-free front of the network once (`cfg_shared_input=True`, set by DDIMSampler) is bit-identical to evaluating it twice."""
+    net, _ = model
+    x = gen(33, b, 4, Fr, H, H).cuda()
+    t = torch.randint(1, 1000, (b,), generator=torch.Generator().manual_seed(5)).cuda()
+    c_in = torch.cat([gen(34, b, Fr, 77, 768), gen(35, b, Fr, 77, 768)]).cuda()
+    x_in, t_in = torch.cat([x, x]), torch.cat([t, t])
+    plain = net(x_in, t_in, c_in, cond_frame=cf)
+    before = ops.LAUNCHES
+    shared = net(x_in, t_in, c_in, cond_frame=cf, cfg_shared_input=True)
+    assert torch.equal(plain, shared)
+    assert not torch.equal(shared[:b], shared[b:])              # the halves do differ (different text)
+
+
 def test_ddim_loop_vs_oracle(model):
     """31-evaluation DDIM + CFG 7.5 with 1 reference frame, identical x_T: final latents within 5e-2."""
     net, sd = model
