@@ -97,7 +97,7 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, float* __rest
 // up to 8 batch rows per warp pass.  Used for time_embedding.linear_{1,2} and all 22 time_emb_proj at once
 // (their weights are concatenated along n).   resnet.py:190-192, unet_3d_condition.py:308.
 // ---------------------------------------------------------------------------------------------------
-constexpr int SL_ROWS = 8;
+constexpr int SL_ROWS = 16;    // batch rows per block pass: the CFG batch of the benchmark (16) reads the weights exactly once
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in, int ldi, const float* __restrict__ W,
                                                            const float* __restrict__ bias, const float* __restrict__ add,
                                                            float* __restrict__ out, int ldo, int B, int N, int K,
@@ -111,8 +111,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 #pragma unroll
   for (int r = 0; r < SL_ROWS; ++r) acc[r] = 0.f;
   const float4* w4 = reinterpret_cast<const float4*>(W + (size_t)n * K);
-  for (int k4 = lane; k4 < K / 4; k4 += 32) {
-    const float4 w = __ldg(w4 + k4);
+  auto accumulate = [&](const float4& w, int k4) {
 #pragma unroll
     for (int r = 0; r < SL_ROWS; ++r) {
       if (b0 + r < B) {
@@ -121,7 +120,15 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
         acc[r] += (x.x * w.x + x.y * w.y) + (x.z * w.z + x.w * w.w);
       }
     }
+  };
+  // the weight row streams from HBM once: four independent 16-byte loads in flight per lane (the loop was latency-bound)
+  const int n4 = K / 4;
+  int k4 = lane;
+  for (; k4 + 96 < n4; k4 += 128) {
+    const float4 wa = __ldg(w4 + k4), wb = __ldg(w4 + k4 + 32), wc = __ldg(w4 + k4 + 64), wd = __ldg(w4 + k4 + 96);
+    accumulate(wa, k4); accumulate(wb, k4 + 32); accumulate(wc, k4 + 64); accumulate(wd, k4 + 96);
   }
+  for (; k4 < n4; k4 += 32) accumulate(__ldg(w4 + k4), k4);
 #pragma unroll
   for (int r = 0; r < SL_ROWS; ++r) {
     const float v = warp_sum(acc[r]);
