@@ -392,18 +392,28 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   pl.cg = cg;
   const int tiles_m = ceil_div(d.M, BM * cg);
   const int nsm = num_sms() / cg;                  // scheduling units: CTAs or CTA pairs
-  // tile width: the widest BN that divides N, unless a narrower one fills the SMs with fewer rounds of tiles
-  static const int cand_plain[] = {320, 256, 192, 160, 128, 64};
+  // Tile width by a small time model (clocks per scheduling unit), calibrated on tools/gemm_bench.py --sweep at the UNet's shapes
+  // (profiles/r2_gemm_sweep_320.txt, r2_gemm_sweep_L2L3.txt).  Per tile: main loop = k-blocks x 2 BN clocks / e(BN), where
+  // e(BN) is the operand-delivery efficiency of a BN-wide pair tile (narrow tiles re-read A from L2 once per n-block: 128-wide
+  // tiles measured ~1000, 160 ~1250, 256 ~1500, 320 ~1600+ TF/s on the same long-K conv); epilogue = chunks per warp x a
+  // per-chunk latency; the two overlap (two TMEM accumulators) except for BN = 320 (single buffer).  The launch as a whole
+  // cannot beat its HBM stream.  The former rule (rounds x (BN + 24)) treated a column as equally expensive at every width and
+  // chose 160-wide tiles for the N = 1280 convs / FF-out of the 8x8 level (measured 392 vs 323 us) and for the 4x4 level.
+  static const int cand_plain[] = {160, 256, 192, 320, 128, 64};      // ties (HBM-bound launches) go to the earlier entry
   static const int cand_geglu[] = {256, 128};
   const int* cand = d.geglu ? cand_geglu : cand_plain;
   const int ncand = d.geglu ? 2 : 6;
-  // 320-wide pair tiles (single-buffered 512-column accumulator): N = 320 / 640 launches with a long main loop
-  // (measured, profiles/r2_gemm_sweep_320.txt: concat convs K >= 8640 1250 -> 1600+ TF/s, K = 2880 +4 %; K <= 2560 linear
-  // launches with an fp32 residual lose 5-10 % to the exposed epilogue)
-  const bool allow320 = cg == 2 && Kd >= 2880.0 && N % 256 != 0 && !d.rope_tab && env_int("SEER_GEMM_BN320", 1);
+  // 320-wide pair tiles: one single-buffered 512-column accumulator, two N = 160 UMMAs per A stage (long main loops only)
+  const bool allow320 = cg == 2 && Kd >= 1280.0 && !d.rope_tab && env_int("SEER_GEMM_BN320", 1);
+  const double kb = Kd / BK;
+  const bool of32 = d.out_f32 != nullptr;
+  const double epi_clk = d.geglu ? 1300.0 : ((of32 && d.residual && !d.residual_bf16) ? 1000.0 : (of32 ? 800.0 : 600.0));
+  const int nhalf_guess = (d.geglu || !of32 || Kd <= 1280.0) ? 2 : 1;
+  const double mem_clk = bytes / 5.5e12 * 1.9e9;
   int best = 0;
   double best_cost = 1e30;
   const int forced = env_int("SEER_GEMM_BN", 0);   // tuning hook
+  const bool old_model = env_int("SEER_GEMM_OLDPLAN", 0) != 0;      // A/B hook: the round-1 cost rule
   for (int i = 0; i < ncand; ++i) {
     const int bn = cand[i];
     if (N % bn) continue;
@@ -411,7 +421,19 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
     if (forced && bn != forced) continue;
     const long tiles = (long)tiles_m * (N / bn);
     const long rounds = (tiles + nsm - 1) / nsm;
-    const double cost = (double)rounds * (bn + 24);     // per-tile time ~ BN + fixed overhead (in column units)
+    double cost;
+    if (old_model) {
+      if (bn == 320 && !(Kd >= 2880.0 && N % 256 != 0)) continue;
+      cost = (double)rounds * (bn + 24);
+    } else {
+      const double eff = bn >= 320 ? 1.0 : (bn >= 256 ? 0.95 : (bn >= 192 ? 0.85 : (bn >= 160 ? 0.76 : (bn >= 128 ? 0.62 : 0.40))));
+      const double main_clk = kb * 2.0 * bn / eff;
+      const int chunks = bn / (d.geglu ? 64 : 32);
+      const double epi = (double)((chunks + nhalf_guess - 1) / nhalf_guess) * epi_clk;
+      const double tile = bn == 320 ? (main_clk + epi) * 1.03 : (main_clk > epi ? main_clk : epi);
+      cost = (double)rounds * tile;
+      if (cost < mem_clk) cost = mem_clk;
+    }
     if (cost < best_cost * 0.999) { best_cost = cost; best = bn; }
   }
   if (!best) {
