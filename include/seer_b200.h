@@ -157,6 +157,11 @@ int seer_b200_rope_inplace(void* qk_bf16, int ld, int M, int tokens_per_clip, in
  * out: T * n_freqs * 2 halves. */
 int seer_b200_rope_table(const float* freqs, int n_freqs, int T, void* out, void* stream);
 
+/* RoPE in place on the Q and K column blocks of a bf16 [M, ld] buffer from that table (16 frequencies = rotary dim 32; position =
+ * row % tokens_per_clip): vectorised stand-alone pass, attention.py:649-651. */
+int seer_b200_rope_apply_table(void* qk_bf16, int ld, long long M, int tokens_per_clip, int heads, int head_dim, int q_col, int k_col,
+                               const void* tab, void* stream);
+
 /* diffusers Timesteps(dim, flip_sin_to_cos, shift): t[B] (fp32) -> out[B, dim].  unet_3d_condition.py:307. */
 int seer_b200_timestep_embedding(const float* t, float* out, int B, int dim, float shift, int flip_sin_to_cos, void* stream);
 

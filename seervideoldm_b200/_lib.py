@@ -62,6 +62,7 @@ SIGNATURES = {
     "seer_b200_scta_row_index": (_i, [_i, _i, _i, _i, _vp, _ip, _ip, _vp]),
     "seer_b200_rope_inplace": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "seer_b200_rope_table": (_i, [_vp, _i, _i, _vp, _vp]),
+    "seer_b200_rope_apply_table": (_i, [_vp, _i, _ll, _i, _i, _i, _i, _i, _vp, _vp]),
     "seer_b200_timestep_embedding": (_i, [_vp, _vp, _i, _i, _f, _i, _vp]),
     "seer_b200_small_linear": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "seer_b200_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -73,6 +73,35 @@ __global__ void rope_table_kernel(const float* __restrict__ freqs, int half, int
   tab[i] = __floats2half2_rn(cs, sn);
 }
 
+// RoPE from the fp16 (cos, sin) table (seer_b200_rope_table), in place on the Q and K column blocks of a bf16 [M, ld] buffer:
+// one thread = 8 channels (4 rotary pairs, one 16-byte load / store) of one (row, q|k, head); consecutive threads walk a row's
+// heads, so a warp touches a few contiguous 16-byte pieces per row and the row's 64 table bytes are shared through L1.  The
+// stand-alone pass of the 320-channel level (the q/k/v projection there is epilogue-bound, the fused form costs more).
+__global__ void rope_tab_kernel(__nv_bfloat16* __restrict__ qk, int ld, size_t M, int T, int heads, int head_dim, int q_col, int k_col,
+                                const __half2* __restrict__ tab) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
+  const int per_row = 2 * heads * 4;
+  const size_t total = M * (size_t)per_row;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / per_row;
+    const int s = (int)(i - row * per_row);
+    const int quad = s & 3, head = (s >> 2) % heads, sec = (s >> 2) / heads;
+    const int pos = (int)(row % (size_t)T);
+    const uint4 tq = __ldg(reinterpret_cast<const uint4*>(tab + (size_t)pos * 16 + 4 * quad));
+    uint4* p = reinterpret_cast<uint4*>(qk + row * ld + (sec ? k_col : q_col) + head * head_dim + 8 * quad);
+    uint4 v = *p;
+    const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w};
+    uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 cs = __half22float2(*reinterpret_cast<const __half2*>(&tw[k]));
+      const float2 x = unpack_bf16(vw[k]);
+      vw[k] = pack_bf16(fmaf(x.x, cs.x, -(x.y * cs.y)), fmaf(x.y, cs.x, x.x * cs.y));
+    }
+    *p = make_uint4(vw[0], vw[1], vw[2], vw[3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Timestep embedding (diffusers 0.10.2 Timesteps, flip_sin_to_cos): out[b] = [cos(t*f_i) | sin(t*f_i)],
 // f_i = exp(-ln(10000) * i / (half - shift)).   Call site unet_3d_condition.py:307.
@@ -466,6 +495,17 @@ extern "C" int seer_b200_rope_inplace(void* qk_bf16, int ld, int M, int tokens_p
 extern "C" int seer_b200_rope_table(const float* freqs, int n_freqs, int T, void* out, void* stream) {
   SEER_CHECK_ARG(freqs && out && n_freqs > 0 && T > 0);
   { cudaError_t le__ = launch_pdl(rope_table_kernel, ceil_div(T * n_freqs, 256), 256, 0, (cudaStream_t)stream, freqs, n_freqs, T, (__half2*)out); if (le__ != cudaSuccess) return (int)le__; }
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_rope_apply_table(void* qk_bf16, int ld, long long M, int tokens_per_clip, int heads, int head_dim, int q_col,
+                                          int k_col, const void* tab, void* stream) {
+  SEER_CHECK_ARG(qk_bf16 && tab && M > 0 && tokens_per_clip > 0 && heads > 0 && head_dim >= 32);
+  SEER_CHECK_ARG(ld % 8 == 0 && q_col % 8 == 0 && k_col % 8 == 0 && head_dim % 8 == 0 && ((uintptr_t)qk_bf16 % 16) == 0);
+  const size_t total = (size_t)M * 2 * heads * 4;
+  { cudaError_t le__ = launch_pdl(rope_tab_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (__nv_bfloat16*)qk_bf16, ld, (size_t)M,
+                                  tokens_per_clip, heads, head_dim, q_col, k_col, (const __half2*)tab); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

@@ -446,8 +446,9 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
     // or a clip evaluated alone and inside a batch would sum its (sum, sumsq) in different orders (one fp32 ulp in mean / rstd,
     // a handful of bf16 outputs rounding the other way: profiles/r1_batch_dependence_probe.txt).  The tile width is therefore
     // a function of N alone here, and the launch always runs 8 epilogue warps (two partials per tile).
-    // (160 is also what the cost model picks for N = 320 / 640 / 1280 at the benchmark's M)
-    best = N % 160 == 0 ? 160 : (N % 128 == 0 ? 128 : 64);
+    // (256 for the 1280-channel levels, 160 for 320 / 640: what the time model picks at the benchmark's M; measured
+    // profiles/r2_gemm_sweep_L2L3.txt: proj_in at M = 16384 52 vs 58 us)
+    best = (N % 256 == 0 && N >= 1024) ? 256 : (N % 160 == 0 ? 160 : (N % 128 == 0 ? 128 : 64));
   }
   pl.bn = best;
   pl.tiles_n = N / best;

@@ -296,14 +296,18 @@ def rope_table(freqs: torch.Tensor, T: int) -> torch.Tensor:
 
 @_timed_op
 def rope_inplace(qkv: torch.Tensor, tokens_per_clip: int, heads: int, head_dim: int, q_col: int, k_col: int,
-                 freqs: torch.Tensor) -> None:
-    """RoPE on the Q / K column blocks of a bf16 [M, ld] buffer; position = row % tokens_per_clip (attention.py:649-651)."""
+                 freqs: torch.Tensor, tab: Optional[torch.Tensor] = None) -> None:
+    """RoPE on the Q / K column blocks of a bf16 [M, ld] buffer; position = row % tokens_per_clip (attention.py:649-651).
+    With `tab` (rope_table(freqs, tokens_per_clip)) the vectorised table kernel runs, else sincosf per (token, pair)."""
     _cuda(qkv, "qkv")
     if qkv.dtype != torch.bfloat16:
         raise TypeError("rope_inplace: bf16 buffer expected")
     if qkv.shape[0] % tokens_per_clip:
         raise ValueError("rope_inplace: rows must be a multiple of tokens_per_clip")
-    _ops.rope(qkv, 1, int(tokens_per_clip), int(heads), int(head_dim), int(q_col), int(k_col), freqs)
+    if tab is not None and head_dim % 8 == 0 and q_col % 8 == 0 and k_col % 8 == 0 and qkv.stride(0) % 8 == 0:
+        _ops.rope_apply_table(qkv, int(tokens_per_clip), int(heads), int(head_dim), int(q_col), int(k_col), tab)
+    else:
+        _ops.rope_inplace(qkv, int(tokens_per_clip), int(heads), int(head_dim), int(q_col), int(k_col), freqs)
     _count()
 
 

@@ -472,6 +472,28 @@ def _tokens_to_nchw(x, out) -> None:
 
 _define("tokens_to_nchw(Tensor x, Tensor(a!) out) -> ()", _tokens_to_nchw)
 _define("softmax_rows(Tensor S, float scale, Tensor(a!) out) -> ()", _softmax_rows)
+def _rope_apply_table(qk, tokens_per_clip, heads, head_dim, q_col, k_col, tab) -> None:
+    _chk(qk, "qk", bf16, 2); _chk(tab, "tab", torch.float16, 3, contiguous=True, dev=qk.device)
+    if tuple(tab.shape) != (tokens_per_clip, 16, 2) or qk.shape[0] % tokens_per_clip:
+        raise ValueError("rope_apply_table: tab must be [tokens_per_clip, 16, 2] and rows a multiple of tokens_per_clip")
+    with _Dev(qk) as stream:
+        rc = _lib.lib().seer_b200_rope_apply_table(_p(qk), qk.stride(0), qk.shape[0], tokens_per_clip, heads, head_dim, q_col, k_col,
+                                                   _p(tab), stream)
+    _lib.check(rc, "rope_apply_table")
+
+
+def _rope_inplace(qk, tokens_per_clip, heads, head_dim, q_col, k_col, freqs) -> None:
+    _chk(qk, "qk", bf16, 2); _chk(freqs, "freqs", f32, 1, dev=qk.device)
+    if qk.shape[0] % tokens_per_clip:
+        raise ValueError("rope_inplace: rows must be a multiple of tokens_per_clip")
+    with _Dev(qk) as stream:
+        rc = _lib.lib().seer_b200_rope_inplace(_p(qk), qk.stride(0), qk.shape[0], tokens_per_clip, heads, head_dim, q_col, k_col,
+                                               _p(freqs), freqs.numel(), stream)
+    _lib.check(rc, "rope_inplace")
+
+
+_define("rope_apply_table(Tensor(a!) qk, int tokens_per_clip, int heads, int head_dim, int q_col, int k_col, Tensor tab) -> ()", _rope_apply_table)
+_define("rope_inplace(Tensor(a!) qk, int tokens_per_clip, int heads, int head_dim, int q_col, int k_col, Tensor freqs) -> ()", _rope_inplace)
 _define("rope_table(Tensor freqs, Tensor(a!) out) -> ()", _rope_table)
 _define("rope(Tensor(a!) qk, int pos_div, int pos_mod, int heads, int head_dim, int q_col, int k_col, Tensor freqs) -> ()", _rope)
 _define("timestep_embedding(Tensor t, Tensor(a!) out, float shift, bool flip_sin_to_cos) -> ()", _timestep_embedding)

@@ -362,21 +362,23 @@ class SeerUNet(nn.Module):
         M = B * T
         hn = ops.groupnorm(xt, None, B, t["gn_g"], t["gn_b"], 1e-6, False, stats1=xs)
         r = ops.gemm_ex(hn, t["pin_w"], bias=t["pin_b"], out_dtype=bf, row_stats=True)
-        rope = None
-        if t["temporal"] and T % 32 == 0 and t["freqs"].numel() == 16 and C >= self.rope_fuse_min_channels:
-            # rotary embedding of q and k (attention.py:649-651) fused into the projection's epilogue; the (cos, sin) table of
-            # this clip length is built once per layer (outside any graph capture: the warm-up evaluations fill the cache).
-            # Only where the GEMM's main loop hides the extra epilogue work (K = C >= 640): at the 320-channel level the
-            # projection is epilogue-bound and the fused form measured SLOWER than the separate pass (+119 us vs 94 us,
-            # profiles/r2_gemm_probe.txt), so level 0 keeps `rope_inplace`.
+        rope = tab = None
+        if t["temporal"] and t["freqs"].numel() == 16:
+            # fp16 (cos, sin) table of this clip length, built once per layer (outside any graph capture: the warm-up
+            # evaluations fill the cache); read by the fused epilogue below or by the vectorised stand-alone pass
             tab = t.setdefault("rope_tabs", {}).get(T)
             if tab is None:
                 tab = t["rope_tabs"][T] = ops.rope_table(t["freqs"], T)
+        if tab is not None and T % 32 == 0 and C >= self.rope_fuse_min_channels:
+            # rotary embedding of q and k (attention.py:649-651) fused into the projection's epilogue.
+            # Only where the GEMM's main loop hides the extra epilogue work (K = C >= 640): at the 320-channel level the
+            # projection is epilogue-bound and the fused form measured SLOWER than the separate pass (+119 us vs 94 us,
+            # profiles/r2_gemm_probe.txt), so level 0 keeps `rope_inplace`.
             rope = (tab, 2 * C, d)
         qkv = ops.gemm_ex(r.out, t["qkv_w"], bias=t["qkv_b"], out_dtype=bf, ln=(r.row_stats, t["qkv_cs"], 1e-5), rope=rope).out   # [M, 3C]
         if t["temporal"]:
             if rope is None:
-                ops.rope_inplace(qkv, T, heads, d, 0, C, t["freqs"])
+                ops.rope_inplace(qkv, T, heads, d, 0, C, t["freqs"], tab=tab)
             att = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], mode=ops.ATTN_SCTA, heads=heads, n_outer=B,
                                 F=F, H=H, W=W)
         else:

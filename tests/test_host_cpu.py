@@ -45,6 +45,14 @@ def test_random_state_dict_is_deterministic_and_loads():
     assert fresh.config.cross_attention_dim == 64 and fresh.config["layers_per_block"] == 2
     with pytest.raises(RuntimeError, match="CUDA only"):
         fresh(torch.zeros(1, 4, 2, 8, 8), 3, torch.zeros(1, 2, 77, 64))
+    # every way of changing the parameters bumps the weights version captured CUDA graphs are keyed on (graph.GraphedUNet.matches)
+    v0 = fresh._weights_version
+    fresh.load_state_dict(a, strict=True)
+    v1 = fresh._weights_version
+    fresh.float()
+    v2 = fresh._weights_version
+    fresh.reset_parameters()
+    assert v0 < v1 < v2 < fresh._weights_version and fresh._packed is None
 
 
 def test_sampler_schedule_matches_reference_golden(golden_dir):
@@ -256,7 +264,7 @@ def test_torch_op_library_registration():
     from seervideoldm_b200 import ops, torch_ops  # noqa: F401
     want = {"gemm_ex", "gemm_row_parts", "groupnorm", "groupnorm_from_stats", "layernorm", "attention", "scta_row_index", "rope",
             "timestep_embedding", "small_linear", "conv_in", "conv_out", "upsample2x", "im2col3x3", "cast_bf16", "cfg_ddim_update",
-            "split3", "geglu_f32", "rope_table"}
+            "split3", "geglu_f32", "rope_table", "rope_inplace", "rope_apply_table", "softmax_rows", "tokens_to_nchw"}
     assert want <= set(torch_ops.OP_NAMES)
     for name in want:
         op = getattr(torch.ops.seer_b200, name).default

@@ -567,9 +567,14 @@ def test_rope_matches_oracle():
     for which in (0, 1):
         r = so.rope_interleaved(ref[:, :, which].permute(0, 2, 1, 3).cpu(), pos, 32)     # (B, heads, T, d)
         ref[:, :, which] = r.permute(0, 2, 1, 3).to(DEV)
+    qkv_tab = qkv.clone()
     ops.rope_inplace(qkv, Fr * hw, heads, d, 0, C, freqs)
     assert rel(qkv.float(), ref.reshape(M, 3 * C)) < 4e-3
     assert torch.equal(qkv[:, 2 * C:].float(), ref.reshape(M, 3 * C)[:, 2 * C:])          # V untouched
+    # the vectorised table kernel (fp16 (cos, sin) table): same rotation up to the table's 2^-11 rounding
+    ops.rope_inplace(qkv_tab, Fr * hw, heads, d, 0, C, freqs, tab=ops.rope_table(freqs, Fr * hw))
+    assert rel(qkv_tab.float(), ref.reshape(M, 3 * C)) < 4e-3
+    assert torch.equal(qkv_tab[:, 2 * C:], qkv[:, 2 * C:])
 
 
 def test_time_embedding_and_small_linear():

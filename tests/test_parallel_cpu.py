@@ -106,3 +106,42 @@ def test_cfg_branch_split_argument_checks():
     with pytest.raises(ValueError, match="branch must be"):
         s.enable_cfg_branch_split(None, 2)
     assert s.enable_cfg_branch_split(None, 1)._branch == (None, 1) and s.disable_cfg_branch_split()._branch is None
+
+
+def _starved_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sample_sharded(lambda ids: torch.zeros(len(ids), 2), 1, 8)      # 1 clip, 2 ranks: rank 1 would own nothing
+        q.put((rank, "no error"))
+    except ValueError as e:
+        q.put((rank, str(e)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fewer_clips_than_ranks_fails_on_every_rank():
+    """n_clips < owners must raise on EVERY rank before any work (a rank-local error would leave the others in the all-gather)."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_starved_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all("must be >= the number of owners" in res[r] for r in range(2)), res
+
+
+def test_sampler_host_logic_cpu():
+    """DDIMSampler host logic that needs no GPU: the graph cache is an LRU bounded by `max_graphs`, the reference's dead
+    `null_cond_prob` branch raises NotImplementedError, the CFG prefix sharing can be switched off."""
+    from seervideoldm_b200.ddim import DDIMSampler
+    s = DDIMSampler("cpu", max_graphs=2, share_cfg_prefix=False)
+    assert s.max_graphs == 2 and s.share_cfg_prefix is False and len(s._graphs) == 0
+    s.make_schedule(30, verbose=False)
+    x = torch.zeros(1, 4, 2, 8, 8)
+    with pytest.raises(NotImplementedError, match="null_cond_prob"):
+        s.p_sample_ddim(None, x, None, torch.tensor([1]), index=0, is_3d=True, null_cond_prob=0.1)
