@@ -205,6 +205,21 @@ int seer_b200_cfg_ddim_update(const float* eps, const float* x, float* x_prev, f
                               int HW, int use_cfg, float scale, float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev,
                               float dir_coef, void* stream);
 
+/* The same update with the two CFG branches on two GPUs of one NVLink domain (CFG-branch split, the reference has no
+ * counterpart: its `[uc; c]` batch at ddim_video.py:199-207 runs on one device).  This rank holds branch `branch`
+ * (0 = unconditional, 1 = conditional) in eps_local (b, C, cond_f+F2, H, W).  One launch pushes the frames >= cond_f of
+ * eps_local into `peer_recv` (the PARTNER's receive slot, b*C*F2*HW floats, mapped into this process: CUDA VMM / IPC peer
+ * mapping), releases `seq` into `peer_flag` (partner's flag word), waits until `local_flag` (this rank's flag word, written
+ * by the partner) reaches `seq`, then combines eps_local with `local_recv` (this rank's receive slot).  `counter` is a
+ * zero-initialised device word private to this rank.  The caller alternates two (slot, flag) pairs by step parity and
+ * increases `seq` (!= 0) every step; both ranks must launch with the same arguments apart from branch / pointers.
+ * Bit-identical to seer_b200_cfg_ddim_update on the concatenated `[e_u; e_c]`.  Waits at most ~20 s, then traps. */
+int seer_b200_cfg_ddim_update_p2p(const float* eps_local, int branch, float* peer_recv, const float* local_recv,
+                                  unsigned* peer_flag, const unsigned* local_flag, unsigned* counter, unsigned seq,
+                                  const float* x, float* x_prev, float* pred_x0, int b, int C, int F2, int cond_f, int HW,
+                                  float scale, float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef,
+                                  void* stream);
+
 /* ---- fp32-parity path (rel-L2 <= 1e-4 against the reference's fp32 PyTorch forward) --------------------------------
  * Contractions run on seer_b200_gemm_ex with error-compensated bf16 operands: A' = [a_hi | a_hi | a_lo] (this split),
  * W' = [w_hi | w_lo | w_hi] (host packing), so A'.W' = a_hi.w_hi + a_hi.w_lo + a_lo.w_hi with fp32 accumulation. */

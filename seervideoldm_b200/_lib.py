@@ -16,6 +16,7 @@ BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 _c = ctypes
 _vp, _i, _f, _ll = _c.c_void_p, _c.c_int, _c.c_float, _c.c_longlong
 _ip = _c.POINTER(_c.c_int)
+_u32 = _c.c_uint32
 
 
 
@@ -74,6 +75,7 @@ SIGNATURES = {
     "seer_b200_im2col3x3_to_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "seer_b200_cast_f32_to_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "seer_b200_cfg_ddim_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f, _vp]),
+    "seer_b200_cfg_ddim_update_p2p": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f, _vp]),
     # fp32-parity path
     "seer_b200_split3_bf16": (_i, [_vp, _i, _ll, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "seer_b200_layernorm_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp]),

@@ -26,6 +26,33 @@
 
 namespace seer {
 
+// Share of the exp2 evaluated on the FMA pipe instead of MUFU (unmasked tiles only): SEER_ATTN_POLY of every 4 score pairs.
+// 2^x = 2^n * p(f), n = round(x), f = x - n in [-0.5, 0.5], p = degree-3 minimax (max relative error 7.5e-5, far below the
+// bf16 rounding of P, 2^-9); n comes out of the magic-number add (1.5 * 2^23), its low bits are shifted into the exponent.
+// Measured on B200 (profiles/r2_attn_poly_ab.txt, spatial / SCTA at d = 40, L = 1024): share 0 -> 859 / 615 us, 1/4 -> 856 / 645,
+// 2/4 -> 874 / 677, 3/4 -> 993 / 747.  The XU pipe is ~60 % busy: the softmax warps are bound by their dependent chain and
+// issue slots (two warps per scheduler at the 168-register cap), not by MUFU throughput, so moving work to the FMA pipe
+// only adds instructions.  Kept as a build-time switch (-DSEER_ATTN_POLY=n), off by default.
+#ifndef SEER_ATTN_POLY
+#define SEER_ATTN_POLY 0
+#endif
+__device__ __forceinline__ void exp2_poly_pair(f2_t X, float& e0, float& e1) {
+  float x0, x1;
+  f2_unpack(X, x0, x1);
+  const f2_t xc = f2_pack(fmaxf(x0, -126.f), fmaxf(x1, -126.f));       // below 2^-126 the exponent add would wrap
+  const f2_t rr = f2_add(xc, f2_pack(12582912.f, 12582912.f));
+  const f2_t tt = f2_add(rr, f2_pack(-12582912.f, -12582912.f));
+  const f2_t fr = f2_fma(tt, f2_pack(-1.f, -1.f), xc);
+  f2_t pp = f2_fma(f2_pack(0.05517132207751274f, 0.05517132207751274f), fr, f2_pack(0.24261054396629333f, 0.24261054396629333f));
+  pp = f2_fma(pp, fr, f2_pack(0.6932609677314758f, 0.6932609677314758f));
+  pp = f2_fma(pp, fr, f2_pack(0.9999281167984009f, 0.9999281167984009f));
+  float r0, r1, p0, p1;
+  f2_unpack(rr, r0, r1);
+  f2_unpack(pp, p0, p1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(r0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
+}
+
 constexpr int AT_BM = 128;     // queries per CTA
 constexpr int AT_BN = 128;     // keys per tile
 constexpr int AT_DP = 64;      // padded head dim (one 128-byte swizzle atom)
@@ -690,9 +717,14 @@ attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 float x0, x1, e0, e1;
-                f2_unpack(f2_fma(f2_pack_u(v[c][8 * g + 2 * k], v[c][8 * g + 2 * k + 1]), sl22, nmsc2), x0, x1);
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+                const f2_t xs = f2_fma(f2_pack_u(v[c][8 * g + 2 * k], v[c][8 * g + 2 * k + 1]), sl22, nmsc2);
+                if (k >= 4 - SEER_ATTN_POLY) {                       // compile-time: this pair goes through the FMA pipe
+                  exp2_poly_pair(xs, e0, e1);
+                } else {
+                  f2_unpack(xs, x0, x1);
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+                }
                 sum2[k & 1] = f2_add(sum2[k & 1], f2_pack(e0, e1));
                 o[k] = pack_bf16(e0, e1);
               }

@@ -465,6 +465,79 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps, const float* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// CFG-branch split over NVLink peer memory (parallel.py): the two ranks of a pair each hold ONE branch of
+// the noise prediction.  One kernel per rank and step does the exchange and the update:
+//   phase 1  every CTA PUSHES its part of this rank's branch (frames >= cond_f only: (b, C, F2, HW) fp32) into the
+//            partner's receive slot with plain stores through the peer mapping (posted writes over NVLink);
+//   signal   fence.sys per thread, one device-scope counter per CTA; the last CTA to finish releases `seq` into the
+//            partner's flag word (st.release.sys);
+//   wait     thread 0 of every CTA acquires this rank's own flag (ld.acquire.sys) until it reaches `seq`;
+//   phase 2  the update of cfg_ddim_kernel, bit for bit: e_u / e_c come from the local tensor and the receive slot
+//            (ld.global.cg: the slot is written by the peer, never through this SM's L1).
+// Both ranks compute the same x_prev / pred_x0 redundantly, so nothing flows back.  The host alternates two receive
+// slots / flag words by step parity: the partner overwrites slot s two steps later, after it has seen this rank's flag
+// of the step in between, which this rank only sends after its reads of slot s have completed (stream order).
+// Every CTA spins, so the grid must be co-resident: the launcher caps it at one CTA per SM.  The wait is bounded
+// (~20 s of %globaltimer, then trap): a lost partner fails the launch instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+cfg_ddim_p2p_kernel(const float* __restrict__ eps_local, int branch, float* __restrict__ peer_recv, const float* local_recv,
+                    unsigned* peer_flag, const unsigned* local_flag, unsigned* counter, unsigned seq,
+                    const float* __restrict__ x, float* __restrict__ x_prev, float* __restrict__ pred_x0, int b, int C, int F2,
+                    int cond_f, int HW, float scale, float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef) {
+  pdl_wait();
+  const size_t total = (size_t)b * C * F2 * HW;
+  const size_t fstride = (size_t)F2 * HW, estride = (size_t)(F2 + cond_f) * HW, eoff = (size_t)cond_f * HW;
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = i0; i < total; i += step) {
+    const size_t bc = i / fstride;
+    peer_recv[i] = eps_local[bc * estride + eoff + (i - bc * fstride)];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(counter, 1u) == gridDim.x - 1) {
+      atomicExch(counter, 0u);                      // next launch on this stream starts from zero
+      __threadfence_system();
+      st_release_sys(peer_flag, seq);
+    }
+    const unsigned long long t0 = globaltimer_ns();
+    while ((int)(ld_acquire_sys(local_flag) - seq) < 0) {
+      __nanosleep(64);
+      if (globaltimer_ns() - t0 > 20000000000ull) __trap();
+    }
+  }
+  __syncthreads();
+  for (size_t i = i0; i < total; i += step) {
+    const size_t bc = i / fstride;
+    const float mine = eps_local[bc * estride + eoff + (i - bc * fstride)];
+    const float theirs = __ldcg(local_recv + i);
+    const float eu = branch == 0 ? mine : theirs;
+    const float ec = branch == 0 ? theirs : mine;
+    const float e = __fadd_rn(eu, __fmul_rn(scale, __fsub_rn(ec, eu)));
+    const float xv = x[i];
+    const float p0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(sqrt_one_minus_at, e)), sqrt_at);
+    const float xp = __fadd_rn(__fmul_rn(sqrt_a_prev, p0), __fmul_rn(dir_coef, e));
+    pred_x0[i] = p0;
+    x_prev[i] = xp;
+  }
+}
+
 static inline int grid_for(size_t n, int threads) {
   size_t b = (n + threads - 1) / threads;
   const size_t cap = (size_t)148 * 32;
@@ -585,6 +658,23 @@ extern "C" int seer_b200_im2col3x3_to_bf16(const void* x, int in_is_bf16, void* 
     { cudaError_t le__ = launch_pdl(im2col3x3_kernel<true>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, n_img, H, W, C, stride); if (le__ != cudaSuccess) return (int)le__; }
   else
     { cudaError_t le__ = launch_pdl(im2col3x3_kernel<false>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, n_img, H, W, C, stride); if (le__ != cudaSuccess) return (int)le__; }
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_cfg_ddim_update_p2p(const float* eps_local, int branch, float* peer_recv, const float* local_recv,
+                                             unsigned* peer_flag, const unsigned* local_flag, unsigned* counter, unsigned seq,
+                                             const float* x, float* x_prev, float* pred_x0, int b, int C, int F2, int cond_f, int HW,
+                                             float scale, float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef,
+                                             void* stream) {
+  SEER_CHECK_ARG(eps_local && peer_recv && local_recv && peer_flag && local_flag && counter && x && x_prev && pred_x0);
+  SEER_CHECK_ARG((branch == 0 || branch == 1) && b > 0 && C > 0 && F2 > 0 && HW > 0 && cond_f >= 0 && seq != 0);
+  const size_t total = (size_t)b * C * F2 * HW;
+  const size_t blocks = (total + 255) / 256;
+  const int grid = (int)(blocks < 148 ? blocks : 148);      // every CTA spins on the partner's flag: keep the grid co-resident
+  { cudaError_t le__ = launch_pdl(cfg_ddim_p2p_kernel, grid, 256, 0, (cudaStream_t)stream, eps_local, branch, peer_recv, local_recv, peer_flag,
+                                  local_flag, counter, seq, x, x_prev, pred_x0, b, C, F2, cond_f, HW, scale, sqrt_one_minus_at, sqrt_at,
+                                  sqrt_a_prev, dir_coef); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

@@ -75,6 +75,7 @@ class DDIMSampler(object):
         self.device = torch.device(device) if not isinstance(device, torch.device) else device
         self.use_cuda_graph = kwargs.get("use_cuda_graph", True)
         self._branch = None            # (process group, branch index) while the CFG-branch split is enabled
+        self._transport, self._exchange = "nccl", None
         self._graphs = collections.OrderedDict()      # LRU of captured evaluations (each pins a private activation pool)
         self.max_graphs = int(kwargs.get("max_graphs", 3))
         self.share_cfg_prefix = bool(kwargs.get("share_cfg_prefix", True))   # evaluate the context-free front of the UNet once per CFG pair
@@ -169,17 +170,29 @@ class DDIMSampler(object):
                 intermediates["pred_x0"].append(pred_x0)
         return img, intermediates
 
-    def enable_cfg_branch_split(self, group, branch: int) -> "DDIMSampler":
+    def enable_cfg_branch_split(self, group, branch: int, transport: str = "auto") -> "DDIMSampler":
         """Optional latency mode (parallel.py): this rank evaluates only CFG branch `branch` (0 = unconditional,
         1 = conditional) and exchanges the noise prediction with its partner in `group` every step.  Both ranks must
-        sample the same clips with the same seeds; eta > 0 additionally needs identical CUDA RNG states."""
+        sample the same clips with the same seeds; eta > 0 additionally needs identical CUDA RNG states.
+
+        transport: "p2p" — the exchange happens inside the CFG+DDIM update kernel through NVLink peer memory
+        (parallel.CfgPeerExchange, no NCCL call in the loop); "nccl" — one all-gather of the prediction per step, then the
+        ordinary update kernel (gloo on CPU tensors never reaches the update: the sampler is CUDA-only); "auto" = "p2p" on
+        a CUDA sampler."""
         if branch not in (0, 1):
             raise ValueError("branch must be 0 (unconditional) or 1 (conditional)")
+        if transport not in ("auto", "p2p", "nccl"):
+            raise ValueError('transport must be "auto", "p2p" or "nccl"')
+        if transport == "auto":
+            transport = "p2p" if self.device.type == "cuda" else "nccl"
         self._branch = (group, branch)
+        self._transport = transport
+        self._exchange = None          # CfgPeerExchange, built (collectively) at the first step that knows the latent size
         return self
 
     def disable_cfg_branch_split(self) -> "DDIMSampler":
         self._branch = None
+        self._exchange = None
         return self
 
     def _evaluate(self, unet, x_in, t_in, c_in, cond_frame, cfg_shared: bool = False):
@@ -221,12 +234,22 @@ class DDIMSampler(object):
             x_cat = torch.cat([x0_emb, x], dim=2)
         uc = unconditional_conditioning
         use_cfg = not (uc is None or unconditional_guidance_scale == 1.)
+        p2p = False
         if not use_cfg:
             eps = self._evaluate(unet, x_cat, t, c, 0)                        # ddim_video.py:196 passes no cond_frame
         elif self._branch is not None:
-            from .parallel import gather_cfg_branches
             group, branch = self._branch
-            eps = gather_cfg_branches(self._evaluate(unet, x_cat, t, uc if branch == 0 else c, cond_frames), group)
+            eps = self._evaluate(unet, x_cat, t, uc if branch == 0 else c, cond_frames)
+            if self._transport == "p2p":
+                from .parallel import CfgPeerExchange
+                if not (x.is_cuda and eps.dtype == torch.float32):
+                    raise RuntimeError("DDIMSampler (seer_b200) needs CUDA fp32 latents; there is no CPU fallback")
+                if self._exchange is None or self._exchange.numel < x.numel():
+                    self._exchange = CfgPeerExchange(group, branch, x.numel(), x.device)
+                p2p = True
+            else:
+                from .parallel import gather_cfg_branches
+                eps = gather_cfg_branches(eps, group)
         elif uc.shape[2] == c.shape[2]:
             c_in = self._cfg_context(uc, c)
             # the two halves of this batch are identical by construction (same latents, same per-sample timesteps)
@@ -235,7 +258,10 @@ class DDIMSampler(object):
             eps = torch.cat([self._evaluate(unet, x_cat, t, uc, cond_frames), self._evaluate(unet, x_cat, t, c, cond_frames)])
         coef = self._coef[index]
         sigma = float(coef[4])
-        if x.is_cuda and eps.dtype == torch.float32:
+        if p2p:
+            x_prev, pred_x0 = self._exchange.update(eps.contiguous(), x.contiguous().float(), cond_f,
+                                                    float(unconditional_guidance_scale), coef)
+        elif x.is_cuda and eps.dtype == torch.float32:
             x_prev, pred_x0 = ops.cfg_ddim_update(eps.contiguous(), x.contiguous().float(), cond_f, use_cfg,
                                                   float(unconditional_guidance_scale), float(coef[0]), float(coef[1]),
                                                   float(coef[2]), float(coef[3]))

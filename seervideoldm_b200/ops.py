@@ -413,6 +413,21 @@ def cfg_ddim_update(eps: torch.Tensor, x: torch.Tensor, cond_f: int, use_cfg: bo
     return x_prev, pred_x0
 
 
+@_timed_op
+def cfg_ddim_update_p2p(eps_local: torch.Tensor, branch: int, peer_recv: torch.Tensor, local_recv: torch.Tensor,
+                        peer_flag: torch.Tensor, local_flag: torch.Tensor, counter: torch.Tensor, seq: int, x: torch.Tensor,
+                        cond_f: int, scale: float, sqrt_one_minus_at: float, sqrt_at: float, sqrt_a_prev: float, dir_coef: float):
+    """CFG-branch split: eps_local (b,C,cond_f+F2,H,W) is this rank's branch; the partner's arrives through `local_recv`
+    (NVLink peer memory, see parallel.CfgPeerExchange) inside the same kernel -> (x_prev, pred_x0)."""
+    _cuda(eps_local, "eps_local")
+    x_prev, pred_x0 = torch.empty_like(x), torch.empty_like(x)
+    _ops.cfg_ddim_update_p2p(eps_local, int(branch), peer_recv, local_recv, peer_flag, local_flag, counter, int(seq), x, x_prev,
+                             pred_x0, int(cond_f), float(scale), float(sqrt_one_minus_at), float(sqrt_at), float(sqrt_a_prev),
+                             float(dir_coef))
+    _count()
+    return x_prev, pred_x0
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # fp32-parity path (csrc/fp32_path.cu): error-compensated bf16 operands for the tcgen05 GEMM, fp32 everywhere else
 # ---------------------------------------------------------------------------------------------------------------------

@@ -107,3 +107,60 @@ def gather_cfg_branches(eps_local: torch.Tensor, group) -> torch.Tensor:
     out = torch.empty((2 * eps_local.shape[0],) + tuple(eps_local.shape[1:]), dtype=eps_local.dtype, device=eps_local.device)
     dist.all_gather_into_tensor(out, eps_local, group=group)
     return out
+
+
+class CfgPeerExchange:
+    """Per-step CFG-branch exchange through NVLink peer memory instead of an NCCL all-gather: the transport of
+    `ops.cfg_ddim_update_p2p` (csrc/elementwise.cu `cfg_ddim_p2p_kernel`).
+
+    One symmetric allocation per rank of the pair (`torch.distributed._symmetric_memory`: CUDA VMM memory every rank of the
+    group maps into its own address space) holds two receive slots of `numel` fp32 noise-prediction values and two flag
+    words; the partner's copy is mapped with `get_buffer`.  The sampler's update kernel pushes this rank's branch straight
+    into the partner's slot, signals, waits for the partner's signal and combines — one launch per step, no NCCL call and
+    no extra pass over eps inside the denoising loop.  Slots and flags alternate by step parity (see the kernel's header
+    comment for why two are enough); `seq` increases by one per step for the life of the object.
+
+    Collective over `group` (exactly two ranks): construct it on both ranks with the same `numel`."""
+
+    FLAG_WORDS = 32             # the two flag words sit 64 B apart at the end of the allocation
+
+    def __init__(self, group, branch: int, numel: int, device: Optional[torch.device] = None):
+        import torch.distributed._symmetric_memory as symm_mem
+        if branch not in (0, 1):
+            raise ValueError("branch must be 0 (unconditional) or 1 (conditional)")
+        if dist.get_world_size(group) != 2:
+            raise ValueError("CfgPeerExchange pairs exactly two ranks")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("CfgPeerExchange needs CUDA peer memory (NVLink / NVSwitch); on CPU use gather_cfg_branches")
+        self.branch, self.group = int(branch), group
+        self.numel = int((numel + 31) // 32 * 32)               # slots stay 128-byte aligned
+        words = 2 * self.numel + self.FLAG_WORDS
+        self._buf = symm_mem.empty(words, dtype=torch.float32, device=device)
+        self._buf.zero_()
+        self._hdl = symm_mem.rendezvous(self._buf, group)
+        me = self._hdl.rank
+        peer = self._hdl.get_buffer(1 - me, (words,), torch.float32)
+        self._peer = peer
+        self._local_recv = [self._buf[s * self.numel:(s + 1) * self.numel] for s in (0, 1)]
+        self._peer_recv = [peer[s * self.numel:(s + 1) * self.numel] for s in (0, 1)]
+        lf = self._buf[2 * self.numel:].view(torch.int32)
+        pf = peer[2 * self.numel:].view(torch.int32)
+        self._local_flag = [lf[0:1], lf[16:17]]
+        self._peer_flag = [pf[0:1], pf[16:17]]
+        self._counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self._seq = 0
+        torch.cuda.synchronize(device)
+        self._hdl.barrier(channel=0)                             # both allocations zeroed before either rank's first push
+
+    def update(self, eps_local: torch.Tensor, x: torch.Tensor, cond_f: int, scale: float, coef) -> Tuple[torch.Tensor, torch.Tensor]:
+        """eps_local (b, C, cond_f+F2, H, W): this rank's branch; x (b, C, F2, H, W); coef = the step's
+        (sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), dir) -> (x_prev, pred_x0), identical on both ranks."""
+        from . import ops
+        if x.numel() > self.numel:
+            raise ValueError(f"exchange sized for {self.numel} values per step, got {x.numel()}")
+        self._seq += 1
+        s = self._seq & 1
+        return ops.cfg_ddim_update_p2p(eps_local, self.branch, self._peer_recv[s], self._local_recv[s], self._peer_flag[s],
+                                       self._local_flag[s], self._counter, self._seq, x, cond_f, scale, float(coef[0]),
+                                       float(coef[1]), float(coef[2]), float(coef[3]))

@@ -421,6 +421,31 @@ def _cfg_ddim_update(eps, x, x_prev, pred_x0, cond_f, use_cfg, scale, sqrt_one_m
     _lib.check(rc, "cfg_ddim_update")
 
 
+def _cfg_ddim_update_p2p(eps_local, branch, peer_recv, local_recv, peer_flag, local_flag, counter, seq, x, x_prev, pred_x0, cond_f,
+                         scale, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef) -> None:
+    _chk(eps_local, "eps_local", f32, 5, contiguous=True)
+    for n, t in (("x", x), ("x_prev", x_prev), ("pred_x0", pred_x0)):
+        _chk(t, n, f32, 5, contiguous=True, dev=eps_local.device)
+    b, C, F2, H, W = x.shape
+    if tuple(eps_local.shape) != (b, C, F2 + cond_f, H, W) or x_prev.shape != x.shape or pred_x0.shape != x.shape:
+        raise ValueError(f"eps_local shape {tuple(eps_local.shape)} inconsistent with x {tuple(x.shape)}")
+    # peer_recv / peer_flag live on the PARTNER's device (mapped here through symmetric memory): no device check on them
+    for n, t, dt in (("peer_recv", peer_recv, f32), ("local_recv", local_recv, f32)):
+        if not (t.is_cuda and t.dtype == dt and t.is_contiguous() and t.numel() >= x.numel()):
+            raise ValueError(f"{n}: contiguous CUDA {dt} tensor of at least {x.numel()} elements expected")
+    for n, t in (("peer_flag", peer_flag), ("local_flag", local_flag), ("counter", counter)):
+        if not (t.is_cuda and t.dtype == torch.int32 and t.numel() >= 1):
+            raise ValueError(f"{n}: CUDA int32 word expected")
+    if branch not in (0, 1) or not (0 < seq < 2 ** 31):
+        raise ValueError("branch must be 0 or 1 and 0 < seq < 2**31")
+    with _Dev(eps_local) as stream:
+        rc = _lib.lib().seer_b200_cfg_ddim_update_p2p(_p(eps_local), int(branch), _p(peer_recv), _p(local_recv), _p(peer_flag),
+                                                      _p(local_flag), _p(counter), int(seq), _p(x), _p(x_prev), _p(pred_x0), b, C, F2,
+                                                      cond_f, H * W, float(scale), float(sqrt_one_minus_at), float(sqrt_at),
+                                                      float(sqrt_a_prev), float(dir_coef), stream)
+    _lib.check(rc, "cfg_ddim_update_p2p")
+
+
 def _split3(x, out, ctot, col0, up_n_img, up_H, up_W) -> None:
     _chk(x, "x", f32, 2); _chk(out, "out", bf16, 2, dev=x.device)
     M, C = x.shape
@@ -505,5 +530,8 @@ _define("im2col3x3(Tensor x, Tensor(a!) out, int stride) -> ()", _im2col3x3)
 _define("cast_bf16(Tensor x, Tensor(a!) out) -> ()", _cast_bf16)
 _define("cfg_ddim_update(Tensor eps, Tensor x, Tensor(a!) x_prev, Tensor(b!) pred_x0, int cond_f, bool use_cfg, float scale, "
         "float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef) -> ()", _cfg_ddim_update)
+_define("cfg_ddim_update_p2p(Tensor eps_local, int branch, Tensor(a!) peer_recv, Tensor local_recv, Tensor(b!) peer_flag, "
+        "Tensor local_flag, Tensor(c!) counter, int seq, Tensor x, Tensor(d!) x_prev, Tensor(e!) pred_x0, int cond_f, float scale, "
+        "float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef) -> ()", _cfg_ddim_update_p2p)
 _define("split3(Tensor x, Tensor(a!) out, int ctot, int col0, int up_n_img, int up_H, int up_W) -> ()", _split3)
 _define("geglu_f32(Tensor h, Tensor(a!) out) -> ()", _geglu_f32)

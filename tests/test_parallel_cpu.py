@@ -106,6 +106,13 @@ def test_cfg_branch_split_argument_checks():
     with pytest.raises(ValueError, match="branch must be"):
         s.enable_cfg_branch_split(None, 2)
     assert s.enable_cfg_branch_split(None, 1)._branch == (None, 1) and s.disable_cfg_branch_split()._branch is None
+    with pytest.raises(ValueError, match="transport"):
+        s.enable_cfg_branch_split(None, 0, transport="mpi")
+    assert s.enable_cfg_branch_split(None, 0)._transport == "nccl"                  # "auto" on a CPU sampler: the all-gather
+    assert DDIMSampler(torch.device("cuda", 0)).enable_cfg_branch_split(None, 0)._transport == "p2p"
+    from seervideoldm_b200.parallel import CfgPeerExchange
+    with pytest.raises(ValueError, match="branch must be"):
+        CfgPeerExchange(None, 3, 1024)
 
 
 def _starved_worker(rank, world, port, q):

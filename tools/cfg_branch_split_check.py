@@ -25,6 +25,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--clips", type=int, default=1)
 ap.add_argument("--frames", type=int, default=16)
 ap.add_argument("--ref-frames", type=int, default=1)
+ap.add_argument("--steps", type=int, default=30, help="DDIM steps (30 = the reference's default: 31 evaluations)")
+ap.add_argument("--reps", type=int, default=3)
 args = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
@@ -48,14 +50,14 @@ for F, F1 in ((args.frames, args.ref_frames), (12, 2)):       # bench shape, the
     shape = (b, 4, F - F1, 32, 32)
 
 
-    def run(sampler, reps=3):
+    def run(sampler, reps=args.reps):
         out, best = None, 1e9
         for _ in range(reps):
             dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = ddim_sample_latents(sampler, net, shape, c, x_T, x0, ddim_steps=30, scale=7.5, uc=uc)
+            out = ddim_sample_latents(sampler, net, shape, c, x_T, x0, ddim_steps=args.steps, scale=7.5, uc=uc)
             e1.record()
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
@@ -65,22 +67,27 @@ for F, F1 in ((args.frames, args.ref_frames), (12, 2)):       # bench shape, the
 
 
     single, ms_single = run(DDIMSampler(torch.device("cuda", local)))
-    split_sampler = DDIMSampler(torch.device("cuda", local)).enable_cfg_branch_split(group, branch)
-    split, ms_split = run(split_sampler)
+    nccl, ms_nccl = run(DDIMSampler(torch.device("cuda", local)).enable_cfg_branch_split(group, branch, transport="nccl"))
+    split, ms_split = run(DDIMSampler(torch.device("cuda", local)).enable_cfg_branch_split(group, branch, transport="p2p"))
+    transports_agree = bool(torch.equal(nccl, split))
 
     same = bool(torch.equal(single, split))
     rel = float((single - split).norm() / single.norm())
     other = [torch.empty_like(split) for _ in range(world)]
     dist.all_gather(other, split)
     ranks_agree = all(bool(torch.equal(o, split)) for o in other)
-    flags = torch.tensor([int(rel <= TOL), int(ranks_agree), int(same)], device="cuda")
+    flags = torch.tensor([int(rel <= TOL), int(ranks_agree), int(same), int(transports_agree)], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-    ok_all = ok_all and bool(flags[0]) and bool(flags[1])
+    ok_all = ok_all and bool(flags[0]) and bool(flags[1]) and bool(flags[3])
     if rank == 0:
-        print(f"CFG-branch split, {b} clip(s) x {F} frames ({F1} ref), 31 evaluations, guidance 7.5, {world} GPUs")
-        print(f"  single GPU ([uc; c] batch of {2 * b}): {ms_single:8.1f} ms per pass = {ms_single / 31:.3f} ms per evaluation")
-        print(f"  branch split (UNet batch {b} per GPU + 1 all-gather of eps per step): {ms_split:8.1f} ms per pass = "
-              f"{ms_split / 31:.3f} ms per step  -> latency x{ms_single / ms_split:.2f}")
+        ne = args.steps + 1
+        print(f"CFG-branch split, {b} clip(s) x {F} frames ({F1} ref), {ne} evaluations, guidance 7.5, {world} GPUs")
+        print(f"  single GPU ([uc; c] batch of {2 * b}): {ms_single:8.1f} ms per pass = {ms_single / ne:.3f} ms per evaluation")
+        print(f"  branch split, NCCL all-gather of eps + update kernel per step: {ms_nccl:8.1f} ms per pass = "
+              f"{ms_nccl / ne:.3f} ms per step  -> latency x{ms_single / ms_nccl:.2f}")
+        print(f"  branch split, exchange inside the update kernel over NVLink peer memory: {ms_split:8.1f} ms per pass = "
+              f"{ms_split / ne:.3f} ms per step  -> latency x{ms_single / ms_split:.2f}")
+        print(f"  p2p == nccl bit for bit: {bool(flags[3])}")
         print(f"  latents vs the single-GPU run: rel-L2 {rel:.3e} (<= {TOL:g}: {bool(flags[0])}; bit-identical: {bool(flags[2])}); "
               f"both ranks of the pair hold bit-identical latents: {bool(flags[1])}")
 dist.barrier()
