@@ -8,13 +8,17 @@ only exchange is `all_gather_into_tensor` of (n_local, 4, F2, H, W) fp32 latents
 Optional latency mode — CFG-branch split (BASELINE.json north_star "sharding independent clips and CFG branches",
 SURVEY §8e row 2): when there are more GPUs than clips, ranks pair up (2p, 2p+1); the even rank evaluates the
 unconditional branch, the odd rank the conditional one (UNet batch b instead of 2b), and the two exchange the noise
-prediction once per DDIM step (`gather_cfg_branches`: one all-gather of (b,4,F,H,W) fp32 inside the pair, 262 KB per
-clip at the bench shape) before both apply the fused CFG+DDIM update redundantly.  This is the one place a collective sits
-inside the step, so it is off by default.  Both ranks of a pair end with bit-identical latents.  Against the single-GPU
-`[uc; c]` batch the latents agree to bf16 rounding noise, not bit for bit (measured rel-L2 6.0e-3 after 31 steps at 16
-frames — the size of the bf16-vs-fp32 distance, 5.4e-3; budget 5e-2; `profiles/r1_cfg_branch_split_2gpu.txt`).  Batch independence IS
-bit-exact at the small test shape (tests/test_unet_gpu.py); at the full shape the LayerNorm row statistics a GEMM emits are
-split into a tile-plan-dependent number of partials, which moves mean / rstd by one fp32 ulp; measured latency gain 1.48x (16 frames) / 1.31x (12 frames).
+prediction once per DDIM step before both apply the CFG+DDIM update redundantly.  This is the one place data crosses GPUs
+inside the step, so it is off by default.  Two transports:
+  * "p2p" (default on CUDA): `CfgPeerExchange` — the update kernel itself pushes this rank's branch into the partner's
+    receive slot through NVLink peer memory (symmetric memory), signals, waits for the partner and combines: one launch per
+    step, no NCCL call in the loop (csrc/elementwise.cu `cfg_ddim_p2p_kernel`);
+  * "nccl": `gather_cfg_branches`, one all-gather of (b,4,F,H,W) fp32 inside the pair (262 KB per clip at the bench shape),
+    then the ordinary update kernel (also what the gloo CPU tests exercise).
+Both ranks of a pair end with bit-identical latents, the two transports agree bit for bit, and since the LayerNorm
+row-statistic producers use a batch-invariant tile plan the result is also bit-identical to the single-GPU `[uc; c]` batch
+(`profiles/r2_cfg_branch_split_2gpu.txt`; latency x1.35 at 16 frames, x1.30 at 12 frames: the UNet at batch 1 is
+launch-latency bound, not the exchange).
 """
 from __future__ import annotations
 

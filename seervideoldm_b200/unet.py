@@ -47,6 +47,9 @@ class _Config(SimpleNamespace):
         return getattr(self, k)
 
 
+_EMULATE_BF16_STREAM = bool(int(__import__('os').environ.get('SEER_EMULATE_BF16_STREAM', '0')))
+
+
 class SeerUNet(nn.Module):
     def __init__(self, sample_size=None, in_channels=4, out_channels=4, center_input_sample=False, flip_sin_to_cos=True,
                  freq_shift=0,
@@ -302,6 +305,8 @@ class SeerUNet(nn.Module):
         (bf16 only: the block feeds an Upsample3D conv and nothing else)."""
         if want == "bf16":
             return (None, None, g.out)
+        if _EMULATE_BF16_STREAM:                      # experiment: precision cost of a bf16 residual stream between blocks
+            g.out.copy_(g.out.to(torch.bfloat16))
         return (g.out, g.col_stats, g.out16)
 
     def _resnet(self, r: dict, x1, x2, B, F, H, W, temb_all, want: str = "f32"):

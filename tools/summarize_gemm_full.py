@@ -12,7 +12,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "r2_gemm_full.ncu-rep")
 lst = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "r2_gemm_launch_list.json")
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+csv_path = os.path.splitext(rep)[0] + "_raw.csv"          # exported on the GPU box by tools/capture_gemm_full.sh
+if os.path.exists(csv_path):
+    raw = open(csv_path).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+raw = raw[raw.index('"ID"'):] if '"ID"' in raw else raw
 rows = list(csv.DictReader(io.StringIO(raw)))[1:]          # first data row holds the units
 launches = json.load(open(lst))
 
