@@ -19,7 +19,7 @@ else:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
 raw = raw[raw.index('"ID"'):] if '"ID"' in raw else raw
 rows = list(csv.DictReader(io.StringIO(raw)))[1:]          # first data row holds the units
-launches = json.load(open(lst))
+launches = [e for e in json.load(open(lst)) if e["flops"] > 0]      # conv_in is not a gemm_tc_kernel launch: ncu -k regex:gemm_tc skipped it
 
 
 def unit_scale(col):
