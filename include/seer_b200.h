@@ -66,7 +66,8 @@ int seer_b200_gemm_bf16(const void* A, int lda, int K1, const void* A2, int lda2
  *                   parts = seer_b200_gemm_row_parts(desc).
  * Requirements: K1, K2 % 64 == 0; N % 64 == 0 (geglu: % 128); lda/lda2/ldo_bf16 % 8 == 0; ldr/ldo_f32 % 4 == 0
  * (ldr % 8 for a bf16 residual); all bases 16-byte aligned; conv: Cin % 64 == 0, W | 128, (128/W) | H or H | (128/W).
- * col_stats is computed from the fp32 values whichever output dtype is stored. */
+ * col_stats is computed from the fp32 values when an fp32 output exists, from the stored bf16 values of a bf16-only output (the
+ * statistics of exactly the tensor the consuming GroupNorm reads). */
 typedef struct SeerGemmDesc {
   const void* A; int lda; int K1;
   const void* X; int n_img, H, W, Cin;
@@ -124,9 +125,9 @@ int seer_b200_groupnorm_from_stats(const float* x1, int C1, const float* stats1,
                                    int B, int T, const float* gamma, const float* beta, float eps, int silu, float* scale_shift,
                                    void* y, int y_is_f32, void* raw_bf16, void* stream);
 
-/* As above with x1 optionally a bf16 tensor (x1_is_bf16: conv1's output, which only GroupNorm 2 of the ResNet block reads;
- * needs C2 == 0 and a bf16 y). */
-int seer_b200_groupnorm_from_stats_ex(const void* x1, int x1_is_bf16, int C1, const float* stats1, const float* x2, int C2,
+/* As above with bf16 sources (x1_is_bf16: x1 AND x2 are bf16 tensors — conv1's output, which only GroupNorm 2 of the ResNet
+ * block reads, or block outputs / skip partners of the bf16 residual stream); needs a bf16 y. */
+int seer_b200_groupnorm_from_stats_ex(const void* x1, int x1_is_bf16, int C1, const float* stats1, const void* x2, int C2,
                                       const float* stats2, int B, int T, const float* gamma, const float* beta, float eps, int silu,
                                       float* scale_shift, void* y, int y_is_f32, void* raw_bf16, void* stream);
 
@@ -178,6 +179,10 @@ int seer_b200_conv_in(const float* x, const float* w, const float* bias, float* 
  * statistics pass; col_stats may be NULL.  Needs B*F*H*W % 32 == 0 when given. */
 int seer_b200_conv_in_stats(const float* x, const float* w, const float* bias, float* out, float* col_stats, int B, int Cin, int F,
                             int H, int W, int Cout, void* stream);
+/* The same with the output stored as bf16 (out_is_bf16: the bf16 residual stream between blocks); the statistics are taken from
+ * the fp32 values either way. */
+int seer_b200_conv_in_ex(const float* x, const float* w, const float* bias, void* out, int out_is_bf16, float* col_stats, int B,
+                         int Cin, int F, int H, int W, int Cout, void* stream);
 /* conv_out (3x3, Cin -> <=4, fp32): x [B*F*H*W, Cin] -> out (B,Cout,F,H,W); w_packed[co][tap][Cin].  :205,370.  Any W (rows are
  * processed in 64-pixel segments); also the VAE decoder's 128 -> 3 output conv at 256x256. */
 int seer_b200_conv_out(const float* x, const float* w_packed, const float* bias, float* out, int B, int Cin, int F, int H,

@@ -308,6 +308,11 @@ __device__ __forceinline__ uint4 lds128u(const void* p) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
   return v;
 }
+__device__ __forceinline__ uint32_t lds32u(const void* p) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)));
+  return v;
+}
 __device__ __forceinline__ float lds32(const void* p) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));

@@ -174,8 +174,9 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 // [B*F*H*W, Cout] fp32.   unet_3d_condition.py:94,311.
 // ---------------------------------------------------------------------------------------------------
 constexpr int CI_PIX = 64;     // pixels per block: the 36 weights a thread keeps in registers are fetched once per 64 pixels
+template <bool OUT_BF16>
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                               float* __restrict__ out, int B, int Cin, int F, int H, int W, int Cout, float2* __restrict__ col_stats) {
+                               void* __restrict__ outv, int B, int Cin, int F, int H, int W, int Cout, float2* __restrict__ col_stats) {
   pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
   extern __shared__ __align__(16) float s_in[];  // [CI_PIX][Cin*9]
   constexpr int K = 36;  // Cin == 4 (checked on the host)
@@ -214,8 +215,9 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
         acc += v.z * wr[4 * k4 + 2];
         acc += v.w * wr[4 * k4 + 3];
       }
-      out[(p0 + pi) * Cout + co] = acc;
-      ssum += acc;
+      if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(outv)[(p0 + pi) * Cout + co] = __float2bfloat16_rn(acc);
+      else reinterpret_cast<float*>(outv)[(p0 + pi) * Cout + co] = acc;
+      ssum += acc;                           // statistics of the fp32 values, whatever dtype is stored
       ssq = fmaf(acc, acc, ssq);
       if (col_stats && ((pi & 31) == 31)) {
         col_stats[((p0 + pi) >> 5) * Cout + co] = make_float2(ssum, ssq);     // same layout as SeerGemmDesc::col_stats
@@ -605,16 +607,27 @@ extern "C" int seer_b200_conv_in(const float* x, const float* w, const float* bi
   return seer_b200_conv_in_stats(x, w, bias, out, nullptr, B, Cin, F, H, W, Cout, stream);
 }
 
-extern "C" int seer_b200_conv_in_stats(const float* x, const float* w, const float* bias, float* out, float* col_stats, int B, int Cin,
-                                       int F, int H, int W, int Cout, void* stream) {
+extern "C" int seer_b200_conv_in_ex(const float* x, const float* w, const float* bias, void* out, int out_is_bf16, float* col_stats,
+                                    int B, int Cin, int F, int H, int W, int Cout, void* stream) {
   SEER_CHECK_ARG(x && w && bias && out && Cin == 4);
   const size_t npix = (size_t)B * F * H * W;
   SEER_CHECK_ARG(!col_stats || npix % 32 == 0);
   const int threads = Cout >= 320 ? 320 : ((Cout + 31) / 32) * 32;
-  { cudaError_t le__ = launch_pdl(conv_in_kernel, (unsigned)((npix + CI_PIX - 1) / CI_PIX), threads, CI_PIX * Cin * 9 * sizeof(float), (cudaStream_t)stream, 
-      x, w, bias, out, B, Cin, F, H, W, Cout, (float2*)col_stats); if (le__ != cudaSuccess) return (int)le__; }
+  const unsigned grid = (unsigned)((npix + CI_PIX - 1) / CI_PIX);
+  const size_t smem = CI_PIX * Cin * 9 * sizeof(float);
+  cudaError_t le__;
+  if (out_is_bf16)
+    le__ = launch_pdl(conv_in_kernel<true>, grid, threads, smem, (cudaStream_t)stream, x, w, bias, out, B, Cin, F, H, W, Cout, (float2*)col_stats);
+  else
+    le__ = launch_pdl(conv_in_kernel<false>, grid, threads, smem, (cudaStream_t)stream, x, w, bias, out, B, Cin, F, H, W, Cout, (float2*)col_stats);
+  if (le__ != cudaSuccess) return (int)le__;
   SEER_LAUNCH_CHECK();
   return SEER_OK;
+}
+
+extern "C" int seer_b200_conv_in_stats(const float* x, const float* w, const float* bias, float* out, float* col_stats, int B, int Cin,
+                                       int F, int H, int W, int Cout, void* stream) {
+  return seer_b200_conv_in_ex(x, w, bias, out, 0, col_stats, B, Cin, F, H, W, Cout, stream);
 }
 
 extern "C" int seer_b200_conv_out(const float* x, const float* w_packed, const float* bias, float* out, int B, int Cin, int F,

@@ -52,6 +52,9 @@ constexpr int EK_PIN16 = EF_OUT16 | EF_RSTAT;                         // proj_in
 constexpr int EK_ATTN_OUT16 = EF_RES16 | EF_OUT16 | EF_RSTAT;         // to_out + bf16 residual
 constexpr int EK_FF2_16 = EF_RES16 | EF_OUT16;                        // FF out + bf16 residual
 constexpr int EK_CONV16 = EF_OUT16 | EF_CSTAT;                        // conv1: bf16 out (only GroupNorm 2 reads it) + column sums
+// bf16 residual stream BETWEEN blocks (SeerUNet.residual_stream = "bf16"): block outputs are stored once, as bf16, next to the
+// GroupNorm column sums of the fp32 values; the block input is read back as a bf16 residual
+constexpr int EK_POUT16 = EF_RES16 | EF_OUT16 | EF_CSTAT;             // proj_out / conv2 + bf16 residual -> bf16 + column sums
 // SCTA's q/k/v projection: LayerNorm fold + rotary embedding of the Q and K heads (attention.py:649-651) applied to the fp32
 // accumulators before the single bf16 rounding — the separate read-modify-write RoPE pass over [M, 2C] disappears
 constexpr int EK_QKV_ROPE = EF_LN | EF_OUT16 | EF_ROPE;
@@ -521,7 +524,10 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
       // at ~1000 cycles of serial latency per warp (tools/tma_store_bench.cu).
       const int ocol = (GEGLU ? (n0 >> 1) : n0) + c * 32;
       __syncwarp();                          // every lane has read its residual row: the slot may be overwritten
-      if (f_o32 || f_cst) {
+      // bf16-only output with column sums: the sums are taken from the staged bf16 tile below (the statistics of exactly the
+      // tensor the consuming GroupNorm reads) — no second, fp32 staging round trip on the warp's dependent chain
+      const bool cst16 = f_cst && f_o16 && !f_o32;
+      if (f_o32 || (f_cst && !cst16)) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) sts128_f2(slot + sw128(lane, k), f[2 * k], f[2 * k + 1]);
         __syncwarp();
@@ -568,6 +574,27 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
           const int r = 8 * i + (lane >> 2);
           const uint4 t = lds128u(slot + sw64(r, lane & 3));
           if (row0 + r < p.M) *reinterpret_cast<uint4*>(dst + out_row(row0 + r) * p.ldo_bf16) = t;
+        }
+        if (cst16) {
+          // lane = (column pair cp, row parity h): (sum, sumsq) of columns 2cp, 2cp+1 over rows h, h+2, ... (adjacent rows sit 64 B
+          // apart: the two half-warps hit disjoint banks), halves combined with one shuffle; rows >= M were zeroed above
+          const int cp = lane & 15, h = lane >> 4;
+          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = 2 * i + h;
+            const float2 t = unpack_bf16(lds32u(slot + sw64(r, cp >> 2) + (cp & 3) * 4));
+            s0 += t.x; q0 = fmaf(t.x, t.x, q0);
+            s1 += t.y; q1 = fmaf(t.y, t.y, q1);
+          }
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+          q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+          if (h == 0 && row0 < p.M) {
+            const size_t slab = p.up_phase ? (((size_t)(row0 >> 5) << 2) + (size_t)(p.up_phase - 1)) : (size_t)(row0 >> 5);
+            reinterpret_cast<float4*>(p.col_stats)[(slab * p.N + ocol) / 2 + cp] = make_float4(s0, q0, s1, q1);
+          }
         }
         __syncwarp();
       }

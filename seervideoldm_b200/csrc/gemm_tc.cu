@@ -269,6 +269,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         case EK_ATTN_OUT16: SEER_EPI(EK_ATTN_OUT16); break;
         case EK_FF2_16: SEER_EPI(EK_FF2_16); break;
         case EK_CONV16: SEER_EPI(EK_CONV16); break;
+        case EK_POUT16: SEER_EPI(EK_POUT16); break;
         default: SEER_EPI(-1); break;
       }
     }
@@ -457,7 +458,7 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   // slot: residual chunk and staged output chunk share the bytes (fp32: 32 x 128 B, bf16: 32 x 64 B)
   const bool of = d.out_f32 != nullptr;
   const int rm = d.residual ? (d.residual_bf16 ? 2 : 1) : 0;
-  pl.slot_bytes = (of || rm == 1 || d.col_stats) ? 4096 : 2048;
+  pl.slot_bytes = (of || rm == 1) ? 4096 : 2048;      // bf16-only kinds stage bf16 (their column sums are read from that tile)
   // 8 epilogue warps (two per scheduler, so one warp's dependent-issue latency hides behind the other's) unless a long
   // main loop (big K) hides the epilogue anyway and the smem is better spent on operand stages
   pl.nepi = env_int("SEER_GEMM_NEPI", (d.geglu || !of || Kd <= 1280.0) ? 8 : 4);
@@ -613,7 +614,7 @@ extern "C" int seer_b200_gemm_ex(const SeerGemmDesc* desc, void* stream) {
                       (d.out_f32 ? EF_OUT32 : 0) | (d.out_bf16 ? EF_OUT16 : 0) | (d.col_stats ? EF_CSTAT : 0) |
                       (d.row_stats_out ? EF_RSTAT : 0) | (d.rope_tab ? EF_ROPE : 0);
     static const int kinds[] = {EK_PIN, EK_QKV, EK_ATTN_OUT, EK_FF1, EK_FF1_PLAIN, EK_FF2, EK_POUT, EK_CONV, EK_BF16,
-                                EK_PIN16, EK_ATTN_OUT16, EK_FF2_16, EK_CONV16, EK_QKV_ROPE};
+                                EK_PIN16, EK_ATTN_OUT16, EK_FF2_16, EK_CONV16, EK_POUT16, EK_QKV_ROPE};
     p.epi_spec = -1;
     const bool generic_forced = env_int("SEER_GEMM_GENERIC", 0) != 0 && !d.geglu;    // A/B hook
     if (d.bias && !generic_forced)

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) gn_finalize_cols_kernel(const float2* __r
 // Block = rps rows x (C/8) chunks (consecutive threads = consecutive chunks of a row: 32-byte pieces of one contiguous row),
 // it walks `rows_per_block` rows of ONE sample; grid = (blocks per sample, B).
 template <bool OUT_F32, bool IN_BF16>
-__global__ void __launch_bounds__(512) gn_apply_kernel(const void* __restrict__ x1v, int C1, const float* __restrict__ x2,
+__global__ void __launch_bounds__(512) gn_apply_kernel(const void* __restrict__ x1v, int C1, const void* __restrict__ x2v,
                                                        int C2, int T, int rows_per_block, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, int silu, void* __restrict__ y,
                                                        __nv_bfloat16* __restrict__ raw) {
@@ -206,10 +206,13 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const void* __restrict__ 
   const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + (size_t)b * C + c + 4));
   const bool first = c < C1;
   const int ldx = first ? C1 : C2;
-  // IN_BF16: x1 is a bf16 tensor (conv1's output, read only by this GroupNorm); the concat partner is fp32-only (C2 == 0)
+  // IN_BF16: both sources are bf16 tensors (conv1's output; or, with the bf16 residual stream, a block output and its skip partner)
   const float* src = IN_BF16 ? nullptr
-                             : (first ? reinterpret_cast<const float*>(x1v) + c : x2 + (c - C1)) + ((size_t)b * T + r_begin + rl) * ldx;
-  const __nv_bfloat16* src16 = IN_BF16 ? reinterpret_cast<const __nv_bfloat16*>(x1v) + c + ((size_t)b * T + r_begin + rl) * ldx : nullptr;
+                             : (first ? reinterpret_cast<const float*>(x1v) + c : reinterpret_cast<const float*>(x2v) + (c - C1)) +
+                                   ((size_t)b * T + r_begin + rl) * ldx;
+  const __nv_bfloat16* src16 = IN_BF16 ? (first ? reinterpret_cast<const __nv_bfloat16*>(x1v) + c
+                                                : reinterpret_cast<const __nv_bfloat16*>(x2v) + (c - C1)) + ((size_t)b * T + r_begin + rl) * ldx
+                                       : nullptr;
   const size_t out_off = ((size_t)b * T + r_begin + rl) * C + c;
   const size_t in_step = (size_t)rps * ldx, out_step = (size_t)rps * C;
 
@@ -371,21 +374,21 @@ extern "C" int seer_b200_groupnorm(const float* x1, int C1, const float* x2, int
   int ga_threads, ga_rows, ga_blocks;
   gn_apply_geometry(T, C, B, ga_threads, ga_rows, ga_blocks);
   if (y_is_f32)
-    { cudaError_t le__ = launch_pdl(gn_apply_kernel<true, false>, dim3(ga_blocks, B), ga_threads, 0, stream, (const void*)x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
+    { cudaError_t le__ = launch_pdl(gn_apply_kernel<true, false>, dim3(ga_blocks, B), ga_threads, 0, stream, (const void*)x1, C1, (const void*)x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
   else
-    { cudaError_t le__ = launch_pdl(gn_apply_kernel<false, false>, dim3(ga_blocks, B), ga_threads, 0, stream, (const void*)x1, C1, x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
+    { cudaError_t le__ = launch_pdl(gn_apply_kernel<false, false>, dim3(ga_blocks, B), ga_threads, 0, stream, (const void*)x1, C1, (const void*)x2, C2, T, ga_rows, scale, shift, silu, y, (__nv_bfloat16*)raw_bf16); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }
 
-extern "C" int seer_b200_groupnorm_from_stats_ex(const void* x1, int x1_is_bf16, int C1, const float* stats1, const float* x2, int C2,
+extern "C" int seer_b200_groupnorm_from_stats_ex(const void* x1, int x1_is_bf16, int C1, const float* stats1, const void* x2, int C2,
                                                  const float* stats2, int B, int T, const float* gamma, const float* beta, float eps,
                                                  int silu, float* scale_shift, void* y, int y_is_f32, void* raw_bf16, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int C = C1 + C2;
   SEER_CHECK_ARG(x1 && stats1 && gamma && beta && scale_shift && y && B > 0 && T > 0 && T % 32 == 0);
   SEER_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && (C2 == 0 || (x2 && stats2)) && C % (2 * GN_GROUPS) == 0 && C / 8 <= 512);
-  SEER_CHECK_ARG(!x1_is_bf16 || (C2 == 0 && !y_is_f32));
+  SEER_CHECK_ARG(!x1_is_bf16 || !y_is_f32);
   float* scale = scale_shift;
   float* shift = scale_shift + (size_t)B * C;
   { cudaError_t le__ = launch_pdl(gn_finalize_cols_kernel, dim3(GN_GROUPS, B), 256, 0, stream, (const float2*)stats1, C1, (const float2*)stats2, C2, T, eps,

@@ -22,6 +22,7 @@ class GraphedUNet:
         self.c = c_in.detach().clone().contiguous()
         self.cond_frame = cond_frame
         self.precision = unet.precision
+        self.residual_stream = getattr(unet, "residual_stream", None)
         self._src = (c_in, c_in._version)
         self.device = x_in.device
         with torch.cuda.device(self.device):
@@ -51,6 +52,7 @@ class GraphedUNet:
     def matches(self, unet, x_in, c_in, cond_frame, cfg_shared: bool = False) -> bool:
         return (self.unet is unet and self.cfg_shared == cfg_shared and tuple(self.x.shape) == tuple(x_in.shape) and tuple(self.c.shape) == tuple(c_in.shape)
                 and self.cond_frame == cond_frame and self.precision == unet.precision
+                and self.residual_stream == getattr(unet, "residual_stream", None)
                 and self.weights_version == unet._weights_version and self.device == x_in.device)
 
     def __call__(self, x_in: torch.Tensor, t_in: torch.Tensor, c_in: torch.Tensor) -> torch.Tensor:

@@ -27,7 +27,8 @@ PROFILE = None         # bench.py sets this to a list: (name, algorithmic flops,
 
 class _Timed:
     """CUDA events on the launching stream around one kernel launch (only while ops.PROFILE is a list).  Records
-    (name, executed FLOPs, start event, end event, algorithmic bytes = every operand / output tensor counted once)."""
+    (name, executed FLOPs, start event, end event, algorithmic bytes = every operand / output tensor counted once, the
+    library's description of the GEMM kernel the launch dispatched to)."""
 
     def __init__(self, name: str, flops: float, nbytes: float = 0.0):
         self.name, self.flops, self.nbytes = name, flops, nbytes
@@ -41,7 +42,8 @@ class _Timed:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.e1.record()
-            PROFILE.append((self.name, self.flops, self.e0, self.e1, self.nbytes))
+            detail = last_gemm_kernel() if (self.name.startswith("gemm") or self.name.startswith("conv")) and self.flops else ""
+            PROFILE.append((self.name, self.flops, self.e0, self.e1, self.nbytes, detail))
         return False
 
 
@@ -200,7 +202,8 @@ def groupnorm(x1: torch.Tensor, x2: Optional[torch.Tensor], B: int, gamma: torch
               stats1: Optional[torch.Tensor] = None, stats2: Optional[torch.Tensor] = None):
     """GroupNorm(32) over (C/32, T) per sample on the virtual concat [x1 | x2] (token-major fp32) (+SiLU).
     With `stats1` (and `stats2` when x2 is given) — the col_stats a gemm_ex launch emitted while producing the
-    tensor — the statistics pass over the activation is skipped; x1 may then be a bf16 tensor (a ResNet block's conv1 output)."""
+    tensor — the statistics pass over the activation is skipped; x1 / x2 may then be bf16 tensors (a ResNet block's conv1
+    output; block outputs of the bf16 residual stream)."""
     _cuda(x1, "x1")
     if x1.dim() != 2 or x1.shape[0] % B:
         raise ValueError("x1 must be contiguous [B*T, C1]")
@@ -210,8 +213,10 @@ def groupnorm(x1: torch.Tensor, x2: Optional[torch.Tensor], B: int, gamma: torch
     T = M // B
     C = C1 + C2
     use_stats = stats1 is not None and (x2 is None or stats2 is not None) and T % 32 == 0
-    if x1_bf16 and (x2 is not None or not use_stats or out_dtype != torch.bfloat16 or want_raw):
-        raise ValueError("a bf16 GroupNorm input needs producer statistics (T % 32 == 0), no concat partner and a bf16 output")
+    if x2 is not None and x2.dtype != x1.dtype:
+        raise ValueError("the two halves of a concat GroupNorm input must share one dtype")
+    if x1_bf16 and (not use_stats or out_dtype != torch.bfloat16):
+        raise ValueError("a bf16 GroupNorm input needs producer statistics (T % 32 == 0) and a bf16 output")
     ss = torch.empty(2 * B * C, device=x1.device, dtype=torch.float32)
     y = torch.empty((M, C), device=x1.device, dtype=out_dtype)
     raw = torch.empty((M, C), device=x1.device, dtype=torch.bfloat16) if want_raw else None
@@ -331,16 +336,16 @@ def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
 
 
 @_timed_op
-def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, col_stats: bool = False):
-    """x:(B,4,F,H,W) fp32 -> [B*F*H*W, Cout] fp32.  col_stats=True also returns the [M/32, Cout, 2] per-slab channel
-    (sum, sumsq) the consuming GroupNorms need (None when M % 32 != 0): returns (out, stats)."""
+def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, col_stats: bool = False, out_dtype: torch.dtype = torch.float32):
+    """x:(B,4,F,H,W) fp32 -> [B*F*H*W, Cout] fp32 (or bf16).  col_stats=True also returns the [M/32, Cout, 2] per-slab channel
+    (sum, sumsq of the fp32 values) the consuming GroupNorms need (None when M % 32 != 0): returns (out, stats)."""
     _cuda(x, "x")
     if x.dim() != 5:
         raise ValueError("x must be contiguous (B,C,F,H,W)")
     B, Cin, F, H, W = x.shape
     Cout = w.shape[0]
     M = B * F * H * W
-    out = torch.empty((M, Cout), device=x.device, dtype=torch.float32)
+    out = torch.empty((M, Cout), device=x.device, dtype=out_dtype)
     st = torch.empty((M // 32, Cout, 2), device=x.device, dtype=torch.float32) if (col_stats and M % 32 == 0) else None
     _ops.conv_in(x, w, bias, out, st)
     _count()

@@ -213,7 +213,7 @@ _define(f"gemm_row_parts({_GEMM_ARGS}) -> int", _gemm_row_parts, lambda *a, **k:
 def _gn_common(x1, x2, B, gamma, beta, scale_shift, y, raw):
     dev = x1.device
     _chk(x1, "x1", (f32, bf16), 2, contiguous=True)
-    _chk(x2, "x2", f32, 2, contiguous=True, optional=True, dev=dev)
+    _chk(x2, "x2", x1.dtype, 2, contiguous=True, optional=True, dev=dev)      # the two halves of a concat share one dtype
     M, C1 = x1.shape
     C2 = x2.shape[1] if x2 is not None else 0
     if M % B or (x2 is not None and x2.shape[0] != M):
@@ -357,12 +357,13 @@ def _conv_in(x, w, bias, out, col_stats) -> None:
     _chk(w, "w", f32, 2, contiguous=True, dev=x.device); _chk(bias, "bias", f32, 1, dev=x.device)
     Cout = w.shape[0]
     M = B * F * H * W
-    _chk(out, "out", f32, 2, contiguous=True, dev=x.device)
+    _chk(out, "out", (f32, bf16), 2, contiguous=True, dev=x.device)
     _chk(col_stats, "col_stats", f32, 3, contiguous=True, optional=True, dev=x.device)
     if tuple(out.shape) != (M, Cout) or w.shape[1] != Cin * 9 or (col_stats is not None and tuple(col_stats.shape) != (M // 32, Cout, 2)):
         raise ValueError("conv_in: w [Cout, Cin*9], out [B*F*H*W, Cout], col_stats [M/32, Cout, 2]")
     with _Dev(x) as stream:
-        rc = _lib.lib().seer_b200_conv_in_stats(_p(x), _p(w), _p(bias), _p(out), _p(col_stats), B, Cin, F, H, W, Cout, stream)
+        rc = _lib.lib().seer_b200_conv_in_ex(_p(x), _p(w), _p(bias), _p(out), int(out.dtype == bf16), _p(col_stats), B, Cin, F, H, W,
+                                             Cout, stream)
     _lib.check(rc, "conv_in")
 
 

@@ -15,6 +15,8 @@ Data layout in HBM (per evaluation, B = UNet batch after CFG):
 """
 from __future__ import annotations
 
+import os
+
 import math
 from dataclasses import asdict
 from types import SimpleNamespace
@@ -47,8 +49,6 @@ class _Config(SimpleNamespace):
         return getattr(self, k)
 
 
-_EMULATE_BF16_STREAM = bool(int(__import__('os').environ.get('SEER_EMULATE_BF16_STREAM', '0')))
-
 
 class SeerUNet(nn.Module):
     def __init__(self, sample_size=None, in_channels=4, out_channels=4, center_input_sample=False, flip_sin_to_cos=True,
@@ -76,6 +76,11 @@ class SeerUNet(nn.Module):
         self._packed32: Optional[dict] = None
         self.rope_fuse_min_channels = 640
         self.conv_out_tensor_core = True
+        # dtype of the residual stream BETWEEN blocks on the bf16 path.  "bf16": every block output is stored once, as bf16, next
+        # to the GroupNorm column sums of its fp32 values (what the reference's fp16 autocast does: conv / Linear outputs and
+        # the residual adds are half precision there, resnet.py:206, attention.py:143); "fp32": fp32 block outputs (round 1).
+        # Measured: step eps rel-L2 7.7e-3 -> 9.5e-3, 31-evaluation latents 6.9e-3 -> 9.6e-3 (budgets 2e-2 / 5e-2), -2.7 % time.
+        self.residual_stream = os.environ.get("SEER_RESIDUAL_STREAM", "bf16")
         self._weights_version = 0       # bumped whenever the packed weights are dropped (captured CUDA graphs check it)
         self._kv_key = None
         self._kv: List[torch.Tensor] = []
@@ -299,26 +304,37 @@ class SeerUNet(nn.Module):
 
     # ------------------------------------------------------------------ operators
     @staticmethod
-    def _emit(g: "ops.GemmOut", want: str):
-        """Block output record (fp32 stream, GroupNorm col_stats, bf16 copy) of the GEMM that produced it.  `want`: "f32" (fp32 +
-        statistics, the residual stream between blocks), "both" (+ bf16 copy: the stride-2 Downsample3D conv reads it), "bf16"
-        (bf16 only: the block feeds an Upsample3D conv and nothing else)."""
+    def _emit(g: "ops.GemmOut", want: str, s16: bool = False):
+        """Block output record (fp32 stream or None, GroupNorm col_stats, bf16 copy or None) of the GEMM that produced it.
+        `want`: "f32" (stream tensor + statistics, the residual stream between blocks), "both" (the stride-2 Downsample3D conv
+        also reads it: + bf16 copy on the fp32 stream), "bf16" (bf16 only, no statistics: the block feeds an Upsample3D conv and
+        nothing else).  `s16`: the stream itself is bf16 — the record carries no fp32 tensor."""
         if want == "bf16":
             return (None, None, g.out)
-        if _EMULATE_BF16_STREAM:                      # experiment: precision cost of a bf16 residual stream between blocks
-            g.out.copy_(g.out.to(torch.bfloat16))
+        if s16:
+            return (None, g.col_stats, g.out)
         return (g.out, g.col_stats, g.out16)
+
+    @staticmethod
+    def _stream(x):
+        """The tensor of a stream record that GroupNorm / the residual add read: fp32 when present, else the bf16 one."""
+        return x[0] if x[0] is not None else x[2]
 
     def _resnet(self, r: dict, x1, x2, B, F, H, W, temb_all, want: str = "f32"):
         """ResnetBlock3D.forward (resnet.py:174-208) on the virtual concat [x1 | x2].  Activations travel as
         (fp32 tensor, col_stats, bf16 copy or None) records: the GEMM that produced a tensor also emitted the per-channel
         partial sums the next GroupNorm needs, so no statistics pass re-reads the activation.  conv1's output is stored as
-        bf16 only (its single reader is GroupNorm 2; the statistics are taken from the fp32 accumulators)."""
+        bf16 only (its single reader is GroupNorm 2; the statistics are those of the stored bf16 values)."""
         T = F * H * W
         eps = self.cfg.norm_eps
         cin, cout = r["cin"], r["cout"]
-        (t1, s1), (t2, s2) = x1[:2], (x2[:2] if x2 is not None else (None, None))
-        if r["sc"]:
+        s16 = x1[0] is None                        # bf16 residual stream: records carry (None, col_stats, bf16)
+        t1, s1 = self._stream(x1), x1[1]
+        t2, s2 = (self._stream(x2), x2[1]) if x2 is not None else (None, None)
+        if r["sc"] and s16 and t2 is None:
+            # bf16 stream, no concat: the block input already is the bf16 operand of the fused 1x1 shortcut
+            h, raw = ops.groupnorm(t1, None, B, r["g1"], r["b1"], eps, True, stats1=s1), t1
+        elif r["sc"]:
             h, raw = ops.groupnorm(t1, t2, B, r["g1"], r["b1"], eps, True, want_raw=True, stats1=s1, stats2=s2)
         else:
             if t2 is not None:
@@ -330,13 +346,14 @@ class SeerUNet(nn.Module):
         else:       # no producer statistics for ragged samples: GroupNorm 2 takes its own pass over an fp32 tensor
             c1 = ops.conv3x3_ex(h.view(B * F, H, W, cin), r["w1"], bias=tb, bias_div=T)
         h2 = ops.groupnorm(c1.out, None, B, r["g2"], r["b2"], eps, True, stats1=c1.col_stats)
-        o32 = want != "bf16"
-        kw = dict(bias=r["bias2"], col_stats=o32, out_dtype=torch.float32 if o32 else torch.bfloat16, also_bf16=(want == "both"))
+        o32 = want != "bf16" and not s16
+        kw = dict(bias=r["bias2"], col_stats=(want != "bf16"), out_dtype=torch.float32 if o32 else torch.bfloat16,
+                  also_bf16=(want == "both" and o32))
         if r["sc"]:
             c2 = ops.conv3x3_ex(h2.view(B * F, H, W, cout), r["w2"], a2=raw, **kw)
         else:
             c2 = ops.conv3x3_ex(h2.view(B * F, H, W, cout), r["w2"], residual=t1, **kw)
-        return self._emit(c2, want)
+        return self._emit(c2, want, s16)
 
     def _ff(self, t: dict, tok, rstats, out_rows=None):
         """x + FF(LN3(x)) -> bf16 (feeds proj_out only).  attention.py:244,323 + 744-747,791-793.  LN3 is folded into
@@ -358,7 +375,8 @@ class SeerUNet(nn.Module):
         d = C // heads
         hw, T = H * W, F * H * W
         bf = torch.bfloat16
-        xt, xs = x[:2]
+        s16 = x[0] is None
+        xt, xs = self._stream(x), x[1]
         Bfull = B
         if dup:
             if t["temporal"] or B % 2:
@@ -413,10 +431,10 @@ class SeerUNet(nn.Module):
                     self._ff(t, tok[mid:hi], rstats[:, mid:hi].contiguous(), out_rows=y[mid:hi])
         else:
             y = self._ff(t, tok, rstats)
-        o32 = want != "bf16"
-        o = ops.gemm_ex(y, t["pout_w"], bias=t["pout_b"], residual=xt, col_stats=o32, also_bf16=(want == "both"),
+        o32 = want != "bf16" and not s16
+        o = ops.gemm_ex(y, t["pout_w"], bias=t["pout_b"], residual=xt, col_stats=(want != "bf16"), also_bf16=(want == "both" and o32),
                         out_dtype=torch.float32 if o32 else bf)
-        return self._emit(o, want)
+        return self._emit(o, want, s16)
 
     def _cross_layers(self, pk: dict) -> List[dict]:
         return [a for blk in pk["down"] for a in blk["attn"]] + [pk["mid"]["attn"]] + [a for blk in pk["up"] for a in blk["attn"]]
@@ -517,9 +535,14 @@ class SeerUNet(nn.Module):
         # run on the first half only (ddim_video.py:199-203 builds x_in = cat([x] * 2), t_in = cat([t] * 2))
         shared = (getattr(self, "_cfg_shared", False) and B % 2 == 0 and bool(pk["down"][0]["attn"]) and (F * H * W) % 32 == 0)
         Bc = B // 2 if shared else B
-        x = ops.conv_in(sample[:Bc].contiguous(), pk["conv_in_w"], pk["conv_in_b"], col_stats=True) + (None,)   # (fp32, col_stats, bf16)
+        # bf16 residual stream: needs producer statistics at every level (32-row slabs must not straddle samples)
+        s16 = self.residual_stream == "bf16" and (F * (H // 8) * (W // 8)) % 32 == 0
+        ci, cst = ops.conv_in(sample[:Bc].contiguous(), pk["conv_in_w"], pk["conv_in_b"], col_stats=True,
+                              out_dtype=torch.bfloat16 if s16 else torch.float32)
+        x = (None, cst, ci) if s16 else (ci, cst, None)                 # (fp32 stream | None, col_stats, bf16)
         h, w = H, W
-        skips: List[tuple] = [(torch.cat([x[0], x[0]]), torch.cat([x[1], x[1]]), None) if shared else x]
+        dup2 = lambda t_: None if t_ is None else torch.cat([t_, t_])
+        skips: List[tuple] = [tuple(dup2(t_) for t_ in x) if shared else x]
         n = len(cfg.block_out_channels)
         # 3. down
         for i, blk in enumerate(pk["down"]):
@@ -536,11 +559,12 @@ class SeerUNet(nn.Module):
             if blk["down"] is not None:
                 wd, bd = blk["down"]
                 # Downsample3D (resnet.py:95-104): stride-2 / pad-1 conv as an implicit GEMM over strided TMA boxes
-                dn = ops.gemm_ex(None, wd, x_img=x[2].view(B * F, h, w, x[2].shape[1]), conv_stride=2, bias=bd, col_stats=True)
+                odt = torch.bfloat16 if s16 else torch.float32
+                dn = ops.gemm_ex(None, wd, x_img=x[2].view(B * F, h, w, x[2].shape[1]), conv_stride=2, bias=bd, col_stats=True, out_dtype=odt)
                 if dn is None:       # geometry outside the TMA-box tiling: explicit im2col (still seer_b200 kernels)
                     cols = ops.im2col3x3(x[2].view(B * F, h, w, x[2].shape[1]), stride=2)
-                    dn = ops.gemm_ex(cols, wd, bias=bd, col_stats=True)
-                x = (dn.out, dn.col_stats, None)
+                    dn = ops.gemm_ex(cols, wd, bias=bd, col_stats=True, out_dtype=odt)
+                x = (None, dn.col_stats, dn.out) if s16 else (dn.out, dn.col_stats, None)
                 h, w = h // 2, w // 2
                 skips.append(x)
         # 4. mid
@@ -560,20 +584,22 @@ class SeerUNet(nn.Module):
                     x = self._transformer(blk["attn"][j], x, B, F, h, w, next(kvs), cond_frame)
                     x = self._transformer(blk["tattn"][j], x, B, F, h, w, None, cond_frame, want=last)
             if blk["up"] is not None:
-                x = self._upsample_conv(blk["up"], x[2], B, F, h, w)
+                x = self._upsample_conv(blk["up"], x[2], B, F, h, w, s16)
                 h, w = 2 * h, 2 * w
         # 6. out: GN -> SiLU -> conv_out, fp32, back to (B, C, F, H, W)
         if self.conv_out_tensor_core and "conv_out_w16" in pk and x[1] is not None:
             # bf16 operands on the tcgen05 implicit-GEMM conv (N = 64: the 4 real channels + zero rows), fp32 accumulate / out:
             # the fp32 SIMT kernel below is FP32-pipe-bound at ~0.9 ms per evaluation, this path ~0.2 ms; the operand rounding
             # adds ~1.5e-3 to the step's 7e-3 (rel-L2, in quadrature)
-            y16 = ops.groupnorm(x[0], None, B, pk["gno_g"], pk["gno_b"], cfg.norm_eps, True, stats1=x[1])
+            y16 = ops.groupnorm(self._stream(x), None, B, pk["gno_g"], pk["gno_b"], cfg.norm_eps, True, stats1=x[1])
             r = ops.conv3x3_ex(y16.view(B * F, h, w, y16.shape[1]), pk["conv_out_w16"], bias=pk["conv_out_b64"])
             return ops.tokens_to_nchw(r.out, B, cfg.out_channels, F, h, w)
-        y = ops.groupnorm(x[0], None, B, pk["gno_g"], pk["gno_b"], cfg.norm_eps, True, out_dtype=torch.float32, stats1=x[1])
+        xs_ = self._stream(x)
+        y = ops.groupnorm(xs_ if xs_.dtype == torch.float32 else xs_.float(), None, B, pk["gno_g"], pk["gno_b"], cfg.norm_eps, True,
+                          out_dtype=torch.float32, stats1=x[1])
         return ops.conv_out(y, pk["conv_out_w"], pk["conv_out_b"], B, F, h, w)
 
-    def _upsample_conv(self, up: tuple, x16: torch.Tensor, B: int, F: int, h: int, w: int):
+    def _upsample_conv(self, up: tuple, x16: torch.Tensor, B: int, F: int, h: int, w: int, s16: bool = False):
         """Upsample3D.forward (resnet.py:47-61): nearest 2x + conv3x3, computed as four 2x2-tap convs on the LOW-res image
         (packing.pack_upsample_phases) whose epilogues scatter their rows to the four pixel phases of the output — the
         upsampled tensor is never materialised and 5/9 of the FLOPs disappear."""
@@ -583,7 +609,7 @@ class SeerUNet(nn.Module):
         M = n_img * 4 * h * w
         img = x16.view(n_img, h, w, C)
         if (w & (w - 1)) == 0 and (F * h * w) % 32 == 0:        # 32-row statistics slabs must not straddle samples
-            out = torch.empty((M, wu.shape[0]), device=x16.device, dtype=torch.float32)
+            out = torch.empty((M, wu.shape[0]), device=x16.device, dtype=torch.bfloat16 if s16 else torch.float32)
             st = torch.empty((M // 32, wu.shape[0], 2), device=x16.device, dtype=torch.float32)
             ok = True
             for ph in range(4):
@@ -594,9 +620,9 @@ class SeerUNet(nn.Module):
                     ok = False
                     break
             if ok:
-                return (out, st, None)
+                return (None, st, out) if s16 else (out, st, None)
         # geometry outside the TMA-box tiling: materialise the upsampled image (nearest-2x of a bf16 tensor via torch indexing
         # would be a PyTorch op on the product path, so go through the fp32 upsample kernel)
         up_img = ops.upsample2x(x16.float(), n_img, h, w)
-        uc = ops.conv3x3_ex(up_img, wu, bias=bu, col_stats=True)
-        return (uc.out, uc.col_stats, None)
+        uc = ops.conv3x3_ex(up_img, wu, bias=bu, col_stats=True, out_dtype=torch.bfloat16 if s16 else torch.float32)
+        return (None, uc.col_stats, uc.out) if s16 else (uc.out, uc.col_stats, None)

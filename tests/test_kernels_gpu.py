@@ -217,6 +217,52 @@ def test_gemm_bf16_token_stream_kinds(M, N, K):
     assert torch.equal(r2.out, r.out)            # same values with and without the statistics output
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 320, 1280), (2048, 640, 640), (262144 // 8, 320, 320)])
+def test_gemm_bf16_residual_stream_kind(M, N, K):
+    """proj_out / conv2 of the bf16 residual stream: bf16 residual in, bf16 out, GroupNorm column sums of the fp32 values —
+    the same values and the same statistics as the fp32-output kind on the same operands."""
+    a = rn(143, M, K).bfloat16()
+    w = rn(144, N, K, scale=K ** -0.5).bfloat16()
+    bias, res16 = rn(145, N), rn(146, M, N).bfloat16()
+    r32 = ops.gemm_ex(a, w, bias=bias, residual=res16, col_stats=True)
+    r16 = ops.gemm_ex(a, w, bias=bias, residual=res16, col_stats=True, out_dtype=torch.bfloat16)
+    assert f"spec={128 | 16 | 32} " in ops.last_gemm_kernel()            # EK_POUT16: a compiled specialisation, not the generic path
+    assert r16.out.dtype == torch.bfloat16 and torch.equal(r16.out, r32.out.bfloat16())
+    full = a.double() @ w.double().t() + bias.double() + res16.double()
+    assert rel(r16.out.float(), full.float()) < 4e-3
+    # the column sums of a bf16-only output are those of the stored tensor (what the consuming GroupNorm normalises)
+    slabs = r16.out.double().reshape(-1, 32, N)
+    assert torch.allclose(r16.col_stats[..., 0].double(), slabs.sum(1), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(r16.col_stats[..., 1].double(), (slabs * slabs).sum(1), rtol=1e-5, atol=1e-4)
+    assert rel(r16.col_stats, r32.col_stats) < 2e-3
+
+
+def test_groupnorm_bf16_concat_sources_and_raw_copy():
+    """GroupNorm over the virtual concat of two bf16 block outputs (bf16 residual stream) with producer statistics: equals
+    GroupNorm of the fp32 tensors up to the bf16 rounding of the inputs; the raw copy is the bf16 concat itself."""
+    B, T, C1, C2, K = 2, 512, 640, 320, 128
+    M = B * T
+    mk = lambda i, C, dt: ops.gemm_ex(rn(i, M, K).bfloat16(), rn(i + 1, C, K, scale=K ** -0.5).bfloat16(), bias=rn(i + 2, C) + 0.25,
+                                      col_stats=True, out_dtype=dt)
+    p1, p2 = mk(150, C1, torch.bfloat16), mk(153, C2, torch.bfloat16)
+    q1, q2 = mk(150, C1, torch.float32), mk(153, C2, torch.float32)
+    g, b = rn(156, C1 + C2), rn(157, C1 + C2)
+    y16, raw = ops.groupnorm(p1.out, p2.out, B, g, b, 1e-5, True, want_raw=True, stats1=p1.col_stats, stats2=p2.col_stats)
+    y32 = ops.groupnorm(q1.out, q2.out, B, g, b, 1e-5, True, stats1=q1.col_stats, stats2=q2.col_stats)
+    assert y16.dtype == torch.bfloat16 and rel(y16.float(), y32.float()) < 6e-3
+    assert torch.equal(raw, torch.cat([p1.out, p2.out], 1))
+    with pytest.raises(ValueError, match="one dtype"):
+        ops.groupnorm(p1.out, q2.out, B, g, b, 1e-5, True, stats1=p1.col_stats, stats2=q2.col_stats)
+
+
+def test_conv_in_bf16_output():
+    x = rn(160, 2, 4, 3, 16, 16)
+    w, b = rn(161, 320, 36, scale=1 / 6.0), rn(162, 320)
+    o32, s32 = ops.conv_in(x, w, b, col_stats=True)
+    o16, s16 = ops.conv_in(x, w, b, col_stats=True, out_dtype=torch.bfloat16)
+    assert o16.dtype == torch.bfloat16 and torch.equal(o16, o32.bfloat16()) and torch.equal(s16, s32)
+
+
 def test_conv3x3_bf16_out_with_statistics():
     """conv1 of a ResNet block: bf16 output (read only by GroupNorm 2), column sums from the fp32 accumulators; the
     GroupNorm that consumes the bf16 tensor through those statistics equals GroupNorm of the fp32 conv output."""
@@ -231,7 +277,10 @@ def test_conv3x3_bf16_out_with_statistics():
     r32 = ops.conv3x3_ex(x, wp, bias=temb, bias_div=T, col_stats=True)
     r16 = ops.conv3x3_ex(x, wp, bias=temb, bias_div=T, col_stats=True, out_dtype=torch.bfloat16)
     assert r16.out.dtype == torch.bfloat16 and torch.equal(r16.out, r32.out.bfloat16())
-    assert torch.equal(r16.col_stats, r32.col_stats)
+    slabs = r16.out.double().reshape(-1, 32, Cout)          # column sums of the stored (bf16) tensor
+    assert torch.allclose(r16.col_stats[..., 0].double(), slabs.sum(1), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(r16.col_stats[..., 1].double(), (slabs * slabs).sum(1), rtol=1e-5, atol=1e-4)
+    assert rel(r16.col_stats, r32.col_stats) < 2e-3
     g, b = rn(50, Cout), rn(51, Cout)
     y32 = ops.groupnorm(r32.out, None, B, g, b, 1e-5, True, stats1=r32.col_stats)
     y16 = ops.groupnorm(r16.out, None, B, g, b, 1e-5, True, stats1=r16.col_stats)

@@ -154,6 +154,30 @@ def test_scale_one_skips_cfg(model):
     assert so.rel_l2(lat.cpu(), ref) < LOOP_TOL
 
 
+def test_residual_stream_modes(model):
+    """The bf16 residual stream between blocks (default) against the fp32 stream and the fp32-parity path at the Sthv2 shape:
+    both inside the bf16 step budget; eager == CUDA-graph capture is covered by the sampler tests, which run the default."""
+    net, _ = model
+    x, c = gen(71, 2, 4, 12, 32, 32).cuda(), gen(72, 2, 12, 77, 768).cuda()
+    t = torch.full((2,), 496, dtype=torch.long).cuda()
+    keep = net.residual_stream
+    try:
+        net.set_precision("fp32")
+        ref = net(x, t, c)
+        net.set_precision("bf16")
+        errs = {}
+        for mode in ("fp32", "bf16"):
+            net.residual_stream = mode
+            out = net(x, t, c)
+            errs[mode] = float((out - ref).norm() / ref.norm())
+            assert torch.equal(out, net(x, t, c))                 # deterministic
+        print(f"Sthv2-shape step vs the fp32 path: fp32 residual stream {errs['fp32']:.3e}, bf16 residual stream {errs['bf16']:.3e}")
+        assert errs["fp32"] < STEP_TOL_BF16 and errs["bf16"] < STEP_TOL_BF16
+    finally:
+        net.set_precision("bf16")
+        net.residual_stream = keep
+
+
 @pytest.mark.slow
 def test_full_size_sthv2_step(model):
     """BASELINE.json config 2 shape: UNet batch 2 (CFG), 12 frames, 32x32 latent, t = 991."""

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--latent", type=int, default=32)
     ap.add_argument("--warm", type=int, default=6)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--detail", default=None, help="print every launch whose op name contains this string (time + dispatched kernel / plan)")
     ap.add_argument("--fast-init", action="store_true", help="skip the seeded weight factory (profiling only)")
     args = ap.parse_args()
     cfg = sd15_config(sample_size=args.latent)
@@ -67,6 +68,12 @@ def main():
         tf = fl / ms / 1e9 if ms > 0 and fl > 0 else 0.0
         rows.append(dict(op=name, n=n, ms=ms, share=ms / tot, tflops=tf))
         print(f"{name:44s} n={n:3d} {ms:8.3f} ms {100 * ms / tot:5.1f}%  {tf:7.1f} TF/s  ({ms / n * 1e3:7.1f} us each)")
+    if args.detail:
+        print(f"-- launches matching {args.detail!r}")
+        for i, (name, flops, a, b, nbytes, *rest) in enumerate(prof):
+            if args.detail in name:
+                ms = a.elapsed_time(b)
+                print(f"  #{i:3d} {name:40s} {ms * 1e3:8.1f} us  {flops / ms / 1e9 if ms > 0 else 0:7.1f} TF/s  {nbytes / 1e6:7.1f} MB  {rest[0] if rest else ''}")
     if args.json:
         with open(args.json, "w") as f:
             json.dump(dict(wall_ms=wall, op_ms=tot, rows=rows), f, indent=1)
