@@ -359,6 +359,13 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
     const int row0 = m0 + q * 32;
     const int row = row0 + lane;
     const bool row_ok = row < p.M;
+    // warp-uniform: the fast copy-out form applies.  Not in the GEGLU instantiation: the second code path costs it 72 B more
+    // spills and 35 % of its speed (537 -> 728 us at level 0)
+#ifdef SEER_NO_FAST_COPYOUT
+    const bool plain_rows = false;
+#else
+    const bool plain_rows = !GEGLU && row0 + 32 <= p.M && p.up_phase == 0;
+#endif
     // ---- this tile's vectors: registers -> shared memory; LayerNorm mean / rstd of this lane's row ----
     const bool bias_smem = n_bias_smem;
     const float* bias_row = n_bias_row;
@@ -532,12 +539,22 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
         for (int k = 0; k < 8; ++k) sts128_f2(slot + sw128(lane, k), f[2 * k], f[2 * k + 1]);
         __syncwarp();
         if (f_o32) {
-          float* dst = p.out_f32 + ocol + (lane & 7) * 4;
+          if (plain_rows) {
+            // whole 32-row group inside M, output row = GEMM row: one pointer per chunk, constant row stride, no per-store
+            // bounds test / row mapping (the general form below costs ~15 instructions per store, this one 3)
+            float* d0 = p.out_f32 + (size_t)(row0 + (lane >> 3)) * p.ldo_f32 + ocol + (lane & 7) * 4;
+            const size_t rstep = (size_t)4 * p.ldo_f32;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + (lane >> 3);
-            const float4 t = lds128(slot + sw128(r, lane & 7));
-            if (row0 + r < p.M) *reinterpret_cast<float4*>(dst + out_row(row0 + r) * p.ldo_f32) = t;
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(d0 + i * rstep) = lds128(slot + sw128(4 * i + (lane >> 3), lane & 7));
+          } else {
+            float* dst = p.out_f32 + ocol + (lane & 7) * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + (lane >> 3);
+              const float4 t = lds128(slot + sw128(r, lane & 7));
+              if (row0 + r < p.M) *reinterpret_cast<float4*>(dst + out_row(row0 + r) * p.ldo_f32) = t;
+            }
           }
         }
         if (f_cst) {
@@ -568,12 +585,20 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
           sts128u(slot + sw64(lane, k), o);
         }
         __syncwarp();
-        __nv_bfloat16* dst = p.out_bf16 + ocol + (lane & 3) * 8;
+        if (plain_rows) {
+          __nv_bfloat16* d0 = p.out_bf16 + (size_t)(row0 + (lane >> 2)) * p.ldo_bf16 + ocol + (lane & 3) * 8;
+          const size_t rstep = (size_t)8 * p.ldo_bf16;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = 8 * i + (lane >> 2);
-          const uint4 t = lds128u(slot + sw64(r, lane & 3));
-          if (row0 + r < p.M) *reinterpret_cast<uint4*>(dst + out_row(row0 + r) * p.ldo_bf16) = t;
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(d0 + i * rstep) = lds128u(slot + sw64(8 * i + (lane >> 2), lane & 3));
+        } else {
+          __nv_bfloat16* dst = p.out_bf16 + ocol + (lane & 3) * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + (lane >> 2);
+            const uint4 t = lds128u(slot + sw64(r, lane & 3));
+            if (row0 + r < p.M) *reinterpret_cast<uint4*>(dst + out_row(row0 + r) * p.ldo_bf16) = t;
+          }
         }
         if (cst16) {
           // lane = (column pair cp, row parity h): (sum, sumsq) of columns 2cp, 2cp+1 over rows h, h+2, ... (adjacent rows sit 64 B
