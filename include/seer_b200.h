@@ -183,6 +183,9 @@ int seer_b200_conv_in_stats(const float* x, const float* w, const float* bias, f
  * the fp32 values either way. */
 int seer_b200_conv_in_ex(const float* x, const float* w, const float* bias, void* out, int out_is_bf16, float* col_stats, int B,
                          int Cin, int F, int H, int W, int Cout, void* stream);
+/* conv_in as a tensor-core GEMM: im2col of the 4-channel latent, x (B,4,F,H,W) fp32 -> a_bf16 [B*F*H*W, 64] (column c*9 + tap for the
+ * 36 real taps, zeros above); multiply by the (Cout, 36 -> 64 zero-padded) bf16 weight with seer_b200_gemm_ex. */
+int seer_b200_conv_in_im2col(const float* x, void* a_bf16, int B, int Cin, int F, int H, int W, void* stream);
 /* conv_out (3x3, Cin -> <=4, fp32): x [B*F*H*W, Cin] -> out (B,Cout,F,H,W); w_packed[co][tap][Cin].  :205,370.  Any W (rows are
  * processed in 64-pixel segments); also the VAE decoder's 128 -> 3 output conv at 256x256. */
 int seer_b200_conv_out(const float* x, const float* w_packed, const float* bias, float* out, int B, int Cin, int F, int H,

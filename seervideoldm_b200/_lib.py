@@ -69,6 +69,7 @@ SIGNATURES = {
     "seer_b200_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "seer_b200_conv_in_stats": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "seer_b200_conv_in_ex": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "seer_b200_conv_in_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "seer_b200_conv_out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "seer_b200_tokens_to_nchw": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "seer_b200_softmax_rows": (_i, [_vp, _i, _ll, _i, _f, _vp, _i, _vp]),

@@ -122,49 +122,70 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Small-batch linear: out[b, n] = dot(act(in[b, :]), W[n, :]) + bias[n] (+ add[n]);  fp32, one warp per n,
-// up to 8 batch rows per warp pass.  Used for time_embedding.linear_{1,2} and all 22 time_emb_proj at once
-// (their weights are concatenated along n).   resnet.py:190-192, unet_3d_condition.py:308.
+// Small-batch linear: out[b, n] = dot(act(in[b, :]), W[n, :]) + bias[n] (+ add[n]);  fp32 (exact: the fp32-parity path uses it
+// too).  Used for time_embedding.linear_{1,2} and all 22 time_emb_proj at once (their weights are concatenated along n:
+// 19520 x 1280 fp32 = 100 MB, the only large operand).   resnet.py:190-192, unet_3d_condition.py:308.
+// Block = 8 warps x 4 output columns, up to 16 batch rows (the benchmark's CFG batch: the weights are read exactly once).
+// The activation rows are staged in shared memory per 512-wide K tile (SiLU applied once there), so one weight float4 from
+// HBM meets 16 broadcast-free LDS.128 reused by the warp's 4 columns: 20 loads per 256 FMAs — the former one-column-per-warp
+// form issued 17 loads per 64 FMAs and ran at 0.8 TB/s (144 us for the 100 MB panel).
 // ---------------------------------------------------------------------------------------------------
-constexpr int SL_ROWS = 16;    // batch rows per block pass: the CFG batch of the benchmark (16) reads the weights exactly once
+constexpr int SL_ROWS = 16;    // batch rows per block pass
+constexpr int SL_NPW = 4;      // output columns per warp
+constexpr int SL_KT = 512;     // K tile (floats) staged in shared memory: 16 x 512 x 4 B = 32 KB
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in, int ldi, const float* __restrict__ W,
                                                            const float* __restrict__ bias, const float* __restrict__ add,
                                                            float* __restrict__ out, int ldo, int B, int N, int K,
                                                            int silu_in, int silu_out) {
   pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
-  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+  __shared__ float4 xs[SL_ROWS][SL_KT / 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * 8 + warp) * SL_NPW;
   const int b0 = blockIdx.y * SL_ROWS;
-  if (n >= N) return;
-  float acc[SL_ROWS];
+  float acc[SL_NPW][SL_ROWS];
 #pragma unroll
-  for (int r = 0; r < SL_ROWS; ++r) acc[r] = 0.f;
-  const float4* w4 = reinterpret_cast<const float4*>(W + (size_t)n * K);
-  auto accumulate = [&](const float4& w, int k4) {
+  for (int i = 0; i < SL_NPW; ++i)
 #pragma unroll
-    for (int r = 0; r < SL_ROWS; ++r) {
-      if (b0 + r < B) {
-        float4 x = *reinterpret_cast<const float4*>(in + (size_t)(b0 + r) * ldi + k4 * 4);
+    for (int r = 0; r < SL_ROWS; ++r) acc[i][r] = 0.f;
+  const int n4 = K / 4;
+  for (int kt4 = 0; kt4 < n4; kt4 += SL_KT / 4) {
+    __syncthreads();                        // the previous tile has been consumed
+    for (int idx = threadIdx.x; idx < SL_ROWS * (SL_KT / 4); idx += 256) {
+      const int r = idx / (SL_KT / 4), k4 = idx - r * (SL_KT / 4);
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b0 + r < B && kt4 + k4 < n4) {
+        x = *reinterpret_cast<const float4*>(in + (size_t)(b0 + r) * ldi + (size_t)(kt4 + k4) * 4);
         if (silu_in) { x.x = silu_f(x.x); x.y = silu_f(x.y); x.z = silu_f(x.z); x.w = silu_f(x.w); }
-        acc[r] += (x.x * w.x + x.y * w.y) + (x.z * w.z + x.w * w.w);
+      }
+      xs[r][k4] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SL_KT / 128; ++j) {
+      const int k4 = lane + 32 * j;
+      float4 w[SL_NPW];
+#pragma unroll
+      for (int i = 0; i < SL_NPW; ++i)
+        w[i] = (n0 + i < N && kt4 + k4 < n4) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + i) * K) + kt4 + k4)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < SL_ROWS; ++r) {
+        const float4 x = xs[r][k4];
+#pragma unroll
+        for (int i = 0; i < SL_NPW; ++i) acc[i][r] += (x.x * w[i].x + x.y * w[i].y) + (x.z * w[i].z + x.w * w[i].w);
       }
     }
-  };
-  // the weight row streams from HBM once: four independent 16-byte loads in flight per lane (the loop was latency-bound)
-  const int n4 = K / 4;
-  int k4 = lane;
-  for (; k4 + 96 < n4; k4 += 128) {
-    const float4 wa = __ldg(w4 + k4), wb = __ldg(w4 + k4 + 32), wc = __ldg(w4 + k4 + 64), wd = __ldg(w4 + k4 + 96);
-    accumulate(wa, k4); accumulate(wb, k4 + 32); accumulate(wc, k4 + 64); accumulate(wd, k4 + 96);
   }
-  for (; k4 < n4; k4 += 32) accumulate(__ldg(w4 + k4), k4);
 #pragma unroll
-  for (int r = 0; r < SL_ROWS; ++r) {
-    const float v = warp_sum(acc[r]);
-    if (lane == 0 && b0 + r < B) {
-      float o = v + (bias ? bias[n] : 0.f) + (add ? add[n] : 0.f);
-      if (silu_out) o = silu_f(o);
-      out[(size_t)(b0 + r) * ldo + n] = o;
+  for (int i = 0; i < SL_NPW; ++i) {
+#pragma unroll
+    for (int r = 0; r < SL_ROWS; ++r) {
+      const float v = warp_sum(acc[i][r]);
+      if (lane == 0 && b0 + r < B && n0 + i < N) {
+        float o = v + (bias ? bias[n0 + i] : 0.f) + (add ? add[n0 + i] : 0.f);
+        if (silu_out) o = silu_f(o);
+        out[(size_t)(b0 + r) * ldo + n0 + i] = o;
+      }
     }
   }
 }
@@ -224,6 +245,40 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
         ssum = ssq = 0.f;
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// conv_in on the tensor cores: im2col of the 4-channel latent (B, 4, F, H, W) fp32 -> bf16 [B*F*H*W, 64], column k = c * 9 + tap
+// for k < 36 (the order of the (Cout, Cin, 3, 3) weight), zeros above — one 64-wide k-block of the tcgen05 GEMM, whose epilogue
+// then emits the bias, the bf16 / fp32 stream tensor and the GroupNorm column sums like every other producer.  The fp32 SIMT
+// kernel above is FP32-pipe bound at ~380 us for 8 clips; this pass writes 17 MB and the GEMM streams the output once.
+// One thread = one pixel x 8 columns (one 16-byte store).
+// ---------------------------------------------------------------------------------------------------
+__global__ void conv_in_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int F, int H, int W) {
+  pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
+  const int HW = H * W;
+  const size_t total = (size_t)B * F * HW * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 7);
+    const size_t pix = i >> 3;
+    const int bf = (int)(pix / HW), rem = (int)(pix - (size_t)bf * HW);
+    const int b = bf / F, f = bf - b * F;
+    const int y = rem / W, xx0 = rem - y * W;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      v[j] = 0.f;
+      if (k < 36) {
+        const int c = k / 9, tap = k - c * 9, ky = tap / 3, kx = tap - ky * 3;
+        const int yy = y + ky - 1, xx = xx0 + kx - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v[j] = x[((((size_t)b * 4 + c) * F + f) * H + yy) * W + xx];
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(a + pix * 64 + g * 8) = o;
   }
 }
 
@@ -596,7 +651,7 @@ extern "C" int seer_b200_timestep_embedding(const float* t, float* out, int B, i
 extern "C" int seer_b200_small_linear(const float* in, int ldi, const float* W, const float* bias, const float* add, float* out,
                                       int ldo, int B, int N, int K, int silu_in, int silu_out, void* stream) {
   SEER_CHECK_ARG(in && W && out && B > 0 && N > 0 && K > 0 && K % 4 == 0 && ldi % 4 == 0);
-  dim3 grid(ceil_div(N, 8), ceil_div(B, SL_ROWS));
+  dim3 grid(ceil_div(N, 8 * SL_NPW), ceil_div(B, SL_ROWS));
   { cudaError_t le__ = launch_pdl(small_linear_kernel, grid, 256, 0, (cudaStream_t)stream, in, ldi, W, bias, add, out, ldo, B, N, K, silu_in, silu_out); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
@@ -621,6 +676,14 @@ extern "C" int seer_b200_conv_in_ex(const float* x, const float* w, const float*
   else
     le__ = launch_pdl(conv_in_kernel<false>, grid, threads, smem, (cudaStream_t)stream, x, w, bias, out, B, Cin, F, H, W, Cout, (float2*)col_stats);
   if (le__ != cudaSuccess) return (int)le__;
+  SEER_LAUNCH_CHECK();
+  return SEER_OK;
+}
+
+extern "C" int seer_b200_conv_in_im2col(const float* x, void* a_bf16, int B, int Cin, int F, int H, int W, void* stream) {
+  SEER_CHECK_ARG(x && a_bf16 && Cin == 4 && B > 0 && F > 0 && H > 0 && W > 0);
+  const size_t total = (size_t)B * F * H * W * 8;
+  { cudaError_t le__ = launch_pdl(conv_in_im2col_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, x, (__nv_bfloat16*)a_bf16, B, F, H, W); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;
 }

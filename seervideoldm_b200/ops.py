@@ -353,6 +353,18 @@ def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, col_stats: boo
 
 
 @_timed_op
+def conv_in_im2col(x: torch.Tensor) -> torch.Tensor:
+    """x:(B,4,F,H,W) fp32 -> bf16 [B*F*H*W, 64]: the 36 taps of the 4-channel 3x3 conv (column c*9 + tap), zero-padded to one
+    k-block; `gemm_ex(a, w16)` with the (Cout, 64) zero-padded bf16 weight is conv_in on the tensor cores."""
+    _cuda(x, "x")
+    B, Cin, F, H, W = x.shape
+    out = torch.empty((B * F * H * W, 64), device=x.device, dtype=torch.bfloat16)
+    _ops.conv_in_im2col(x, out)
+    _count()
+    return out
+
+
+@_timed_op
 def conv_out(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, B: int, F: int, H: int, W: int) -> torch.Tensor:
     """x:[B*F*H*W, Cin] fp32 -> (B,Cout,F,H,W) fp32."""
     _cuda(x, "x")

@@ -367,6 +367,17 @@ def _conv_in(x, w, bias, out, col_stats) -> None:
     _lib.check(rc, "conv_in")
 
 
+def _conv_in_im2col(x, out) -> None:
+    _chk(x, "x", f32, 5, contiguous=True)
+    B, Cin, F, H, W = x.shape
+    _chk(out, "out", bf16, 2, contiguous=True, dev=x.device)
+    if Cin != 4 or tuple(out.shape) != (B * F * H * W, 64):
+        raise ValueError("conv_in_im2col: x (B, 4, F, H, W), out [B*F*H*W, 64]")
+    with _Dev(x) as stream:
+        rc = _lib.lib().seer_b200_conv_in_im2col(_p(x), _p(out), B, Cin, F, H, W, stream)
+    _lib.check(rc, "conv_in_im2col")
+
+
 def _conv_out(x, w_packed, bias, out) -> None:
     _chk(x, "x", f32, 2, contiguous=True); _chk(out, "out", f32, 5, contiguous=True, dev=x.device)
     _chk(w_packed, "w_packed", f32, 3, contiguous=True, dev=x.device); _chk(bias, "bias", f32, 1, dev=x.device)
@@ -525,6 +536,7 @@ _define("rope(Tensor(a!) qk, int pos_div, int pos_mod, int heads, int head_dim, 
 _define("timestep_embedding(Tensor t, Tensor(a!) out, float shift, bool flip_sin_to_cos) -> ()", _timestep_embedding)
 _define("small_linear(Tensor x, Tensor w, Tensor? bias, Tensor? add, Tensor(a!) out, bool silu_in, bool silu_out) -> ()", _small_linear)
 _define("conv_in(Tensor x, Tensor w, Tensor bias, Tensor(a!) out, Tensor(b!)? col_stats) -> ()", _conv_in)
+_define("conv_in_im2col(Tensor x, Tensor(a!) out) -> ()", _conv_in_im2col)
 _define("conv_out(Tensor x, Tensor w_packed, Tensor bias, Tensor(a!) out) -> ()", _conv_out)
 _define("upsample2x(Tensor x, Tensor(a!) out) -> ()", _upsample2x)
 _define("im2col3x3(Tensor x, Tensor(a!) out, int stride) -> ()", _im2col3x3)

@@ -76,6 +76,9 @@ class SeerUNet(nn.Module):
         self._packed32: Optional[dict] = None
         self.rope_fuse_min_channels = 640
         self.conv_out_tensor_core = True
+        # conv_in as im2col + tcgen05 GEMM (ops.conv_in_im2col): 378 -> 172 us per 16-sample evaluation, but rounding the latent to
+        # bf16 moves the step error 9.7e-3 -> 1.01e-2 for 0.15 % of the step: off by default
+        self.conv_in_tensor_core = False
         # dtype of the residual stream BETWEEN blocks on the bf16 path.  "bf16": every block output is stored once, as bf16, next
         # to the GroupNorm column sums of its fp32 values (what the reference's fp16 autocast does: conv / Linear outputs and
         # the residual adds are half precision there, resnet.py:206, attention.py:143); "fp32": fp32 block outputs (round 1).
@@ -210,6 +213,10 @@ class SeerUNet(nn.Module):
         pk: dict = {}
         pk["conv_in_w"] = P("conv_in.weight").float().reshape(self.cfg.block_out_channels[0], -1).contiguous()
         pk["conv_in_b"] = f32("conv_in.bias")
+        if self.cfg.in_channels == 4:               # conv_in as one 64-wide k-block of the tcgen05 GEMM (36 real taps)
+            w64 = torch.zeros((pk["conv_in_w"].shape[0], 64), dtype=torch.float32, device=pk["conv_in_w"].device)
+            w64[:, :36] = pk["conv_in_w"]
+            pk["conv_in_w16"] = w64.to(torch.bfloat16).contiguous()
         pk["te1_w"], pk["te1_b"] = f32("time_embedding.linear_1.weight"), f32("time_embedding.linear_1.bias")
         pk["te2_w"], pk["te2_b"] = f32("time_embedding.linear_2.weight"), f32("time_embedding.linear_2.bias")
         pk["gno_g"], pk["gno_b"] = f32("conv_norm_out.weight"), f32("conv_norm_out.bias")
@@ -537,8 +544,16 @@ class SeerUNet(nn.Module):
         Bc = B // 2 if shared else B
         # bf16 residual stream: needs producer statistics at every level (32-row slabs must not straddle samples)
         s16 = self.residual_stream == "bf16" and (F * (H // 8) * (W // 8)) % 32 == 0
-        ci, cst = ops.conv_in(sample[:Bc].contiguous(), pk["conv_in_w"], pk["conv_in_b"], col_stats=True,
-                              out_dtype=torch.bfloat16 if s16 else torch.float32)
+        Mc = Bc * F * H * W
+        if self.conv_in_tensor_core and "conv_in_w16" in pk and Mc % 32 == 0 and pk["conv_in_w16"].shape[0] % 64 == 0:
+            # bf16 operands (the latent is rounded once, like every other activation operand), fp32 accumulate; the fp32 SIMT
+            # kernel is FP32-pipe bound (380 us for 8 clips)
+            g0 = ops.gemm_ex(ops.conv_in_im2col(sample[:Bc].contiguous()), pk["conv_in_w16"], bias=pk["conv_in_b"], col_stats=True,
+                             out_dtype=torch.bfloat16 if s16 else torch.float32)
+            ci, cst = g0.out, g0.col_stats
+        else:
+            ci, cst = ops.conv_in(sample[:Bc].contiguous(), pk["conv_in_w"], pk["conv_in_b"], col_stats=True,
+                                  out_dtype=torch.bfloat16 if s16 else torch.float32)
         x = (None, cst, ci) if s16 else (ci, cst, None)                 # (fp32 stream | None, col_stats, bf16)
         h, w = H, W
         dup2 = lambda t_: None if t_ is None else torch.cat([t_, t_])

@@ -637,6 +637,28 @@ def test_time_embedding_and_small_linear():
     assert rel(out, refo) < 1e-5
     x = rn(74, 19, 1280)
     assert rel(ops.small_linear(x, rn(75, 640, 1280), None), x @ rn(75, 640, 1280).t()) < 1e-5
+    # ragged N (not a multiple of the block's 32 columns) and K (not a multiple of the 512-wide shared-memory tile)
+    x, w, b = rn(76, 5, 516), rn(77, 1001, 516, scale=516 ** -0.5), rn(78, 1001)
+    refr = (x.double() @ w.double().t() + b.double()).float()
+    assert rel(ops.small_linear(x, w, b), refr) < 1e-6
+
+
+def test_conv_in_tensor_core_im2col():
+    """conv_in as im2col (36 taps zero-padded to one 64-wide k-block) + tcgen05 GEMM: the bf16-operand product of the same conv."""
+    B, Fr, H = 2, 3, 16
+    x = rn(180, B, 4, Fr, H, H)
+    w, b = rn(181, 320, 4, 3, 3, scale=1 / 6.0), rn(182, 320)
+    a = ops.conv_in_im2col(x)
+    assert a.shape == (B * Fr * H * H, 64) and a.dtype == torch.bfloat16 and not a[:, 36:].any()
+    w64 = torch.zeros(320, 64, device=DEV)
+    w64[:, :36] = w.reshape(320, 36)
+    r = ops.gemm_ex(a, w64.bfloat16(), bias=b, col_stats=True, out_dtype=torch.bfloat16)
+    ref = so.conv_framewise(x.bfloat16().float().cpu(), w.bfloat16().float().cpu(), b.cpu()).permute(0, 2, 3, 4, 1).reshape(-1, 320)
+    assert rel(r.out.float(), ref) < 4e-3                       # bf16 rounding of the output only
+    exact = so.conv_framewise(x.cpu(), w.cpu(), b.cpu()).permute(0, 2, 3, 4, 1).reshape(-1, 320)
+    assert rel(r.out.float(), exact) < 8e-3                     # + bf16 rounding of the latent and the weight
+    r32 = ops.gemm_ex(a, w64.bfloat16(), bias=b, col_stats=True)
+    assert rel(r32.out, ref) < 2e-5
 
 
 def test_conv_in_out():
