@@ -240,13 +240,21 @@ def run_stress(args):
             for _ in range(max(3, args.warmup)):
                 fn()
             torch.cuda.synchronize()
+            # the timed launches are replayed from a CUDA graph: the smallest of these kernels (50 us) are shorter than an eager
+            # launch through the torch dispatcher, which would otherwise be what this loop measures
+            n_launch = args.steps * 4
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for _ in range(n_launch):
+                    fn()
+            graph.replay()
+            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(args.steps * 4):
-                fn()
+            graph.replay()
             e1.record()
             torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / (args.steps * 4)
+            ms = e0.elapsed_time(e1) / n_launch
             rows.append({"op": f"{name} h={h} d={d}", "us": ms * 1e3, "tflops": flops / ms / 1e9, "layers": reps, "kernel": ops.last_attention_kernel()})
             tot_ms += ms * reps
             tot_fl += flops * reps
