@@ -8,7 +8,7 @@ whole forward runs on hand-written sm_100a kernels in one canonical channels-las
 [(b f h w), C]; there is no PyTorch/CPU fallback — a missing libseer_b200.so raises.
 
 Data layout in HBM (per evaluation, B = UNet batch after CFG):
-  * residual stream   fp32 [B*F*h*w, C]            (GroupNorm/LayerNorm inputs, skip connections)
+  * residual stream   bf16 [B*F*h*w, C]            (block outputs / skip connections; fp32 with residual_stream = "fp32")
   * GEMM/conv operands bf16, same token-major shape (normalised activations, q/k/v, FF hidden)
   * packed weights    bf16 [N, K] K-major           (conv3x3: K = [Cin/64][ky][kx][64] (+ fused 1x1 shortcut))
   * text K/V          bf16 [B*F*77, 2C] per cross-attention layer, cached across the 31 DDIM steps
@@ -161,8 +161,8 @@ class SeerUNet(nn.Module):
         return self.conv_in.weight.device
 
     def set_precision(self, precision: str) -> "SeerUNet":
-        """"bf16" (default, the product path: bf16 tensor-core operands, fp32 accumulation / residual stream; what the
-        reference computes under accelerate's mixed precision) or "fp32" (parity mode, unet_fp32.py: error-compensated
+        """"bf16" (default, the product path: bf16 tensor-core operands and activations, fp32 accumulation / statistics; what
+        the reference computes under accelerate's mixed precision) or "fp32" (parity mode, unet_fp32.py: error-compensated
         bf16 operand pairs on the same tcgen05 kernels, everything else fp32; matches the reference's fp32 forward to
         rel-L2 <= 1e-4)."""
         if precision not in ("bf16", "fp32"):
@@ -372,7 +372,7 @@ class SeerUNet(nn.Module):
         """SpatialTransformer3D.forward (attention.py:129-145) with its text (:308-327) or temporal (:231-248) block.
         The token stream inside the block is bf16 (what the reference computes under autocast: Linear outputs and the
         residual adds are low precision there too) with per-row (sum, sumsq) written by the producing GEMM's epilogue for
-        the LayerNorm folded into the next projection; the block input / output (the UNet's residual stream) stay fp32.
+        the LayerNorm folded into the next projection; the block input / output follow `residual_stream` (bf16 by default).
 
         `dup` (text block only): `x` holds the FIRST HALF of a CFG batch whose two halves are identical up to here (same
         latents, same timestep — ddim_video.py:199-203); everything that does not see the text context (GroupNorm, proj_in,
@@ -537,7 +537,7 @@ class SeerUNet(nn.Module):
         temb_all = ops.small_linear(emb, pk["temb_w"], pk["temb_b"])      # all 22 time_emb_proj at once
         kvs = iter(self._context_kv(pk, context.to(dev)))
 
-        # 2. conv_in -> token-major fp32 stream
+        # 2. conv_in -> token-major residual stream
         # CFG batch with identical halves: conv_in, the first ResNet block and the context-free front of the first text block
         # run on the first half only (ddim_video.py:199-203 builds x_in = cat([x] * 2), t_in = cat([t] * 2))
         shared = (getattr(self, "_cfg_shared", False) and B % 2 == 0 and bool(pk["down"][0]["attn"]) and (F * H * W) % 32 == 0)
