@@ -461,6 +461,8 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   pl.slot_bytes = (of || rm == 1) ? 4096 : 2048;      // bf16-only kinds stage bf16 (their column sums are read from that tile)
   // 8 epilogue warps (two per scheduler, so one warp's dependent-issue latency hides behind the other's) unless a long
   // main loop (big K) hides the epilogue anyway and the smem is better spent on operand stages
+  // (4 warps + the extra operand stages for the K >= 1280 FF-out launches: level 0 229 vs 237 us, but the evaluation as a whole
+  //  measured 0.5 ms slower in two A/B repetitions — not adopted; 4 vs 8 everywhere: profiles/r2_breakdown_nepi4.txt / nepi8.txt)
   pl.nepi = env_int("SEER_GEMM_NEPI", (d.geglu || !of || Kd <= 1280.0) ? 8 : 4);
   // 320-wide tiles are single-buffered: the epilogue is exposed, so it gets all 8 warps (and a short residual ring)
   if (best == 320) pl.nepi = env_int("SEER_GEMM_NEPI320", 8);
