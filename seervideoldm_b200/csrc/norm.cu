@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const void* __restrict__ 
                   fmaf(a1.x, s1.x, h1.x), fmaf(a1.y, s1.y, h1.y), fmaf(a1.z, s1.z, h1.z), fmaf(a1.w, s1.w, h1.w)};
     if (silu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+      for (int j = 0; j < 8; ++j) v[j] = OUT_F32 ? silu_f(v[j]) : silu_fast(v[j]);    // fp32 output = the fp32-parity path: exact form
     }
     if (OUT_F32) {
       float* dst = reinterpret_cast<float*>(y) + off;

@@ -55,7 +55,13 @@ def _timed_op(fn):
     def wrapper(*a, **k):
         if PROFILE is None:
             return fn(*a, **k)
-        with _Timed(fn.__name__, 0.0):
+        name = fn.__name__
+        if name == "groupnorm":          # shape and input dtype in the label: the per-level passes differ by 16x in bytes
+            x2 = a[1] if len(a) > 1 else k.get("x2")
+            name = (f"groupnorm M={a[0].shape[0]} C={a[0].shape[1] + (x2.shape[1] if x2 is not None else 0)} "
+                    f"{'bf16' if a[0].dtype == torch.bfloat16 else 'f32'}->{'f32' if k.get('out_dtype') == torch.float32 else 'bf16'}"
+                    f"{' +raw' if k.get('want_raw') else ''}")
+        with _Timed(name, 0.0):
             return fn(*a, **k)
     return wrapper
 
