@@ -80,15 +80,21 @@ __global__ void rope_table_kernel(const float* __restrict__ freqs, int half, int
 __global__ void rope_tab_kernel(__nv_bfloat16* __restrict__ qk, int ld, size_t M, int T, int heads, int head_dim, int q_col, int k_col,
                                 const __half2* __restrict__ tab) {
   pdl_wait();   // PDL secondary only: multi-wave grids must not hand their SMs to the successor early
+  // thread -> (row within the block's row group, piece s of the row): no 64-bit division per element (the former flat index
+  // cost two of them per 16 bytes and made this pass ALU-bound); the position inside the clip advances incrementally
   const int per_row = 2 * heads * 4;
-  const size_t total = M * (size_t)per_row;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t row = i / per_row;
-    const int s = (int)(i - row * per_row);
-    const int quad = s & 3, head = (s >> 2) % heads, sec = (s >> 2) / heads;
-    const int pos = (int)(row % (size_t)T);
+  const int rpb = blockDim.x / per_row;                      // rows per block pass (host guarantees >= 1)
+  if ((int)threadIdx.x >= rpb * per_row) return;
+  const int rl = threadIdx.x / per_row, s = threadIdx.x - rl * per_row;
+  const int quad = s & 3, head = (s >> 2) % heads, sec = (s >> 2) / heads;
+  const int col = (sec ? k_col : q_col) + head * head_dim + 8 * quad;
+  const size_t row_step = (size_t)gridDim.x * rpb;
+  const int pos_step = (int)(row_step % (size_t)T);
+  size_t row = (size_t)blockIdx.x * rpb + rl;
+  int pos = (int)(row % (size_t)T);
+  for (; row < M; row += row_step) {
     const uint4 tq = __ldg(reinterpret_cast<const uint4*>(tab + (size_t)pos * 16 + 4 * quad));
-    uint4* p = reinterpret_cast<uint4*>(qk + row * ld + (sec ? k_col : q_col) + head * head_dim + 8 * quad);
+    uint4* p = reinterpret_cast<uint4*>(qk + row * ld + col);
     uint4 v = *p;
     const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w};
     uint32_t vw[4] = {v.x, v.y, v.z, v.w};
@@ -99,6 +105,8 @@ __global__ void rope_tab_kernel(__nv_bfloat16* __restrict__ qk, int ld, size_t M
       vw[k] = pack_bf16(fmaf(x.x, cs.x, -(x.y * cs.y)), fmaf(x.y, cs.x, x.x * cs.y));
     }
     *p = make_uint4(vw[0], vw[1], vw[2], vw[3]);
+    pos += pos_step;
+    if (pos >= T) pos -= T;
   }
 }
 
@@ -633,8 +641,12 @@ extern "C" int seer_b200_rope_apply_table(void* qk_bf16, int ld, long long M, in
                                           int k_col, const void* tab, void* stream) {
   SEER_CHECK_ARG(qk_bf16 && tab && M > 0 && tokens_per_clip > 0 && heads > 0 && head_dim >= 32);
   SEER_CHECK_ARG(ld % 8 == 0 && q_col % 8 == 0 && k_col % 8 == 0 && head_dim % 8 == 0 && ((uintptr_t)qk_bf16 % 16) == 0);
-  const size_t total = (size_t)M * 2 * heads * 4;
-  { cudaError_t le__ = launch_pdl(rope_tab_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (__nv_bfloat16*)qk_bf16, ld, (size_t)M,
+  const int per_row = 2 * heads * 4;
+  SEER_CHECK_ARG(per_row <= 1024);
+  const int threads = per_row <= 256 ? (256 / per_row) * per_row : per_row;
+  const size_t blocks = ((size_t)M + threads / per_row - 1) / (threads / per_row);
+  const size_t cap = (size_t)148 * 32;
+  { cudaError_t le__ = launch_pdl(rope_tab_kernel, (unsigned)(blocks < cap ? blocks : cap), threads, 0, (cudaStream_t)stream, (__nv_bfloat16*)qk_bf16, ld, (size_t)M,
                                   tokens_per_clip, heads, head_dim, q_col, k_col, (const __half2*)tab); if (le__ != cudaSuccess) return (int)le__; }
   SEER_LAUNCH_CHECK();
   return SEER_OK;

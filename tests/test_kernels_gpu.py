@@ -626,6 +626,26 @@ def test_rope_matches_oracle():
     assert torch.equal(qkv_tab[:, 2 * C:], qkv[:, 2 * C:])
 
 
+def test_rope_table_kernel_large_grid():
+    """More rows than one pass of the capped grid covers: the row loop and the incremental position (pos += step mod T) of the
+    table kernel against the direct kernel."""
+    heads, d, T, B = 8, 40, 12288, 2
+    C = heads * d
+    qkv = rn(170, B * T, 3 * C).bfloat16()
+    freqs = (1.0 / (10000.0 ** (torch.arange(0, 32, 2).float() / 32))).to(DEV)
+    a, b = qkv.clone(), qkv.clone()
+    ops.rope_inplace(a, T, heads, d, 0, C, freqs)
+    ops.rope_inplace(b, T, heads, d, 0, C, freqs, tab=ops.rope_table(freqs, T))
+    assert rel(b.float(), a.float()) < 3e-3
+    assert torch.equal(b[:, 2 * C:], qkv[:, 2 * C:])
+    # a row far into the second clip: position = row mod T
+    row = T + 7777
+    x = qkv[row, :32].float().cpu()
+    ang = 7777 * freqs.cpu()
+    want0 = x[0] * torch.cos(ang[0]) - x[1] * torch.sin(ang[0])
+    assert abs(float(b[row, 0]) - float(want0)) < 0.03 * (abs(float(want0)) + 1.0)
+
+
 def test_time_embedding_and_small_linear():
     t = torch.tensor([991.0, 1.0, 496.0], device=DEV)
     emb = ops.timestep_embedding(t, 320, 0.0, True)
