@@ -442,6 +442,8 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
       if (N % cand[i] == 0 && cand[i] != 320) best = cand[i];
     if (!best) return SEER_EUNSUPPORTED;
   }
+  // tuning hook: 320-wide (single-accumulator, non-resident-panel) tiles on the K <= 640 linear launches whose N allows it
+  if (env_int("SEER_GEMM_320_SMALLK", 0) && cg == 2 && !d.X && Kd <= 640.0 && N % 320 == 0 && !d.rope_tab && !d.geglu && !forced) best = 320;
   if (d.row_stats_out && !forced) {
     // LayerNorm row-statistic producers: the number and the column extent of the per-row partial sums must not depend on M,
     // or a clip evaluated alone and inside a batch would sum its (sum, sumsq) in different orders (one fp32 ulp in mean / rstd,
@@ -450,6 +452,7 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
     // (256 for the 1280-channel levels, 160 for 320 / 640: what the time model picks at the benchmark's M; measured
     // profiles/r2_gemm_sweep_L2L3.txt: proj_in at M = 16384 52 vs 58 us)
     best = (N % 256 == 0 && N >= 1024) ? 256 : (N % 160 == 0 ? 160 : (N % 128 == 0 ? 128 : 64));
+    if (env_int("SEER_GEMM_320_SMALLK", 0) && cg == 2 && !d.X && Kd <= 640.0 && N % 320 == 0) best = 320;
   }
   pl.bn = best;
   pl.tiles_n = N / best;
@@ -476,7 +479,9 @@ static int make_plan(const SeerGemmDesc& d, Plan& pl) {
   const int Ktot_i = (int)Kd;
   const int panel_bytes = (Ktot_i / BK) * (best / cg) * BK * 2;
   const int units_bs = (nsm / pl.tiles_n) * pl.tiles_n;
-  pl.bstat = bstat_ok && panel_bytes <= 120 * 1024 && units_bs > 0 && pl.num_tiles >= 2 * units_bs;
+  // (320-wide tiles issue two UMMAs per stage from a split Wt stage: the resident-panel layout does not provide that — a forced
+  //  SEER_GEMM_BN=320 on a K <= 320 launch used to deadlock here, caught by the bounded mbarrier wait)
+  pl.bstat = bstat_ok && best != 320 && panel_bytes <= 120 * 1024 && units_bs > 0 && pl.num_tiles >= 2 * units_bs;
   if (pl.bstat) pl.grid = units_bs * cg;
   const int stage_bytes = pl.bstat ? A_BYTES : A_BYTES + (best / cg) * BK * 2;
   const int rope_bytes = d.rope_tab ? MAX_EPI_WARPS * ROPE_BYTES_PER_WARP : 0;
