@@ -576,6 +576,7 @@ cfg_ddim_p2p_kernel(const float* __restrict__ eps_local, int branch, float* __re
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();                         // cumulative over the CTA's pushes (ordered before it by the barrier)
     if (atomicAdd(counter, 1u) == gridDim.x - 1) {
       atomicExch(counter, 0u);                      // next launch on this stream starts from zero
       __threadfence_system();
