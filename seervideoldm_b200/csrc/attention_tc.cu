@@ -69,6 +69,7 @@ struct AttnTcParams {
   int F, H, W, nwx, nwin;      // SCTA geometry (window side fixed at 8)
   float scale_log2;            // d^-0.5 * log2(e)
   int causal;
+  int look_ahead;              // persistent kernel: issue the next item's first S before the current item's last P V
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -576,15 +577,32 @@ attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       }
       __syncwarp();
     };
+    // Optional (p.look_ahead, an A/B switch that did not pay): S of the first tile of the NEXT item issued before P V of the current
+    // item's last tile, as S(j+1) precedes P V(j) inside an item — Q / K of the next item arrive as soon as the last S of this one
+    // has read the buffers, and the softmax warps hand S back (s_free) at the start of their pass
+    const bool look_ahead = p.look_ahead != 0;
+    bool s_issued = false;
     for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n) {
       int prob, qt;
       decode(idx, prob, qt);
       const int n_kv = p.causal ? min(n_kv_full, qt + 1) : n_kv_full;
-      mbar_wait(q_full, n & 1);
-      issue_s(it, n_kv == 1);
+      if (!s_issued) {
+        mbar_wait(q_full, n & 1);
+        issue_s(it, n_kv == 1);
+      }
+      s_issued = false;
       for (int j = 0; j < n_kv; ++j, ++it) {
         const uint32_t ph = it & 1;
-        if (j + 1 < n_kv) issue_s(it + 1, j + 2 == n_kv);
+        if (j + 1 < n_kv) {
+          issue_s(it + 1, j + 2 == n_kv);
+        } else if (look_ahead && idx + (int)gridDim.x < total) {
+          int prob2, qt2;
+          decode(idx + (int)gridDim.x, prob2, qt2);
+          const int n_kv2 = p.causal ? min(n_kv_full, qt2 + 1) : n_kv_full;
+          mbar_wait(q_full, (n + 1) & 1);
+          issue_s(it + 1, n_kv2 == 1);
+          s_issued = true;
+        }
         mbar_wait(v_full, ph);
         mbar_wait(p_full, ph);                 // P of this tile in smem; any rescale of O by the softmax warps has retired
         if (j == 0) mbar_wait(o_free, (n & 1) ^ 1);   // the previous item's O has been read out of TMEM
@@ -886,6 +904,9 @@ extern "C" int seer_b200_attention(const void* q, int ldq, const void* k, int ld
       // (measured, profiles/r2_attn_bench_p_tmem.txt: 870 vs 854 us spatial, 655 vs 616 us SCTA — the TMEM store + wait costs more
       //  than the smem store + proxy fence it replaces at 168 registers; kept as an A/B switch, off by default)
       const bool pt = env_flag("SEER_ATTN_P_TMEM", 0) != 0;
+      // (measured, profiles/r2_attn_lookahead_ab.txt: cross 241.8 -> 239.1 us, spatial 857.7 -> 877.1 us, SCTA unchanged — the first S
+      //  of an item is not what its softmax warps wait for; off)
+      p.look_ahead = env_flag("SEER_ATTN_LOOKAHEAD", 0);
       auto kern = pt ? attention_tc_persist_kernel<40, true> : attention_tc_persist_kernel<40, false>;
       static SmemAttrOnce smem_attr_attr_done_p[2];
   { cudaError_t e = smem_attr_attr_done_p[pt].ensure(kern, AT_SMEM); if (e != cudaSuccess) return (int)e; }
