@@ -347,6 +347,32 @@ def test_upsample_conv_phases(n_img, H, C, Cout):
     assert torch.allclose(S[..., 1], (v * v).sum(1), rtol=1e-5, atol=1e-2)
 
 
+@pytest.mark.parametrize("n_img,H,C,Cout", [(6, 16, 128, 320), (16, 8, 1280, 1280)])
+def test_upsample_conv_phases_bf16_stream(n_img, H, C, Cout):
+    """The same four phase convs writing the bf16 residual stream: bf16 rows scattered to the pixel phases, column sums of the
+    stored values in the phase-interleaved slab order."""
+    from seervideoldm_b200.packing import pack_upsample_phases
+    x = rn(155, n_img, H, H, C).bfloat16()
+    w = rn(156, Cout, C, 3, 3, scale=(9 * C) ** -0.5)
+    b = rn(157, Cout)
+    phases = [p.to(DEV) for p in pack_upsample_phases(w.cpu())]
+    M = n_img * 4 * H * H
+    out32 = torch.empty((M, Cout), device=DEV)
+    st32 = torch.empty((M // 32, Cout, 2), device=DEV)
+    out16 = torch.full((M, Cout), float("nan"), device=DEV).bfloat16()
+    st16 = torch.full((M // 32, Cout, 2), float("nan"), device=DEV)
+    for ph in range(4):
+        kw = dict(x_img=x, conv_taps=(2, 2, (ph & 1) - 1, (ph >> 1) - 1), up_phase=1 + ph, bias=b)
+        assert ops.gemm_ex(None, phases[ph], out=out32, col_stats=st32, **kw) is not None
+        assert ops.gemm_ex(None, phases[ph], out=out16, col_stats=st16, **kw) is not None
+    assert torch.equal(out16, out32.bfloat16())
+    assert torch.isfinite(st16).all() and rel(st16, st32) < 2e-3
+    S = st16.double().reshape(n_img, -1, Cout, 2).sum(1)
+    v = out16.double().reshape(n_img, -1, Cout)
+    assert torch.allclose(S[..., 0], v.sum(1), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(S[..., 1], (v * v).sum(1), rtol=1e-5, atol=1e-2)
+
+
 def test_gemm_320_wide_pair_tiles():
     """BN = 320 plan (one single-buffered 256 x 320 pair accumulator, two N = 160 UMMAs per A stage) — forced through the
     tuning hook on small shapes, and as the planner picks it at the level-0 / level-1 shapes of the benchmark."""
