@@ -306,6 +306,12 @@ def test_conv3x3_stride2_implicit(n_img, H, C, Cout):
     assert rel(r.out, ops.gemm(cols, wp, bias=b)) < 2e-6
     slabs = r.out.double().reshape(-1, 32, Cout)
     assert torch.allclose(r.col_stats[..., 0].double(), slabs.sum(1), rtol=1e-5, atol=1e-3)
+    # the bf16 residual stream's form of the same launch: bf16 rows, column sums of the stored values
+    r16 = ops.gemm_ex(None, wp, x_img=x, conv_stride=2, bias=b, col_stats=True, out_dtype=torch.bfloat16)
+    assert torch.equal(r16.out, r.out.bfloat16())
+    slabs16 = r16.out.double().reshape(-1, 32, Cout)
+    assert torch.allclose(r16.col_stats[..., 0].double(), slabs16.sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(r16.col_stats[..., 1].double(), (slabs16 * slabs16).sum(1), rtol=1e-5, atol=1e-3)
 
 
 @pytest.mark.parametrize("n_img,H,C,Cout", [(4, 8, 64, 160), (6, 16, 128, 320), (32, 4, 192, 160), (5, 16, 640, 640), (16, 8, 1280, 1280)])
